@@ -1,0 +1,162 @@
+// Shared device/host helpers for the CALD B200 scoring engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <stdexcept>
+
+#define CALD_CUDA_CHECK(expr)                                                            \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      char _b[512];                                                                      \
+      snprintf(_b, sizeof(_b), "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,      \
+               cudaGetErrorString(_e));                                                  \
+      throw std::runtime_error(_b);                                                      \
+    }                                                                                    \
+  } while (0)
+
+namespace cald {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------
+// Split-bf16 activation format.  A real value v is stored as hi = bf16(v) and
+// lo = bf16(v - hi) in two planes; hi + lo carries 16 mantissa bits.  The tensor-core
+// path multiplies A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with fp32 accumulation in TMEM,
+// which is what keeps the detector's discrete stages (top-k / NMS / arg-max) on the
+// same side of their thresholds as the reference's fp32 CPU run.
+// ---------------------------------------------------------------------------------
+__host__ __device__ inline void split_bf16(float v, bf16& hi, bf16& lo) {
+#ifdef __CUDA_ARCH__
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+#else
+  hi = __float2bfloat16(v);
+  lo = __float2bfloat16(v - __bfloat162float(hi));
+#endif
+}
+
+__device__ __forceinline__ float join_bf16(bf16 hi, bf16 lo) {
+  return __bfloat162float(hi) + __bfloat162float(lo);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// ---------------------------------------------------------------------------------
+// Conv / GEMM problem description shared by the tcgen05 kernel and the SIMT checker.
+// ---------------------------------------------------------------------------------
+enum { OUT_NHWC = 0, OUT_PHASE = 1 };
+enum { RES_NONE = 0, RES_SAME = 1, RES_NEAREST = 2 };
+
+struct ConvParams {
+  // ---- A operand (activations, split planes [planes][n_img][H_in][W_in][Cin])
+  int n_img;           // images (views) in the batch; 1 in linear mode
+  int H, W;            // OUTPUT spatial size (== input size for stride 1); linear: H = 1, W = M
+  int Cin;             // multiple of 64
+  int taps;            // 1 (1x1 / linear) or 9 (3x3)
+  int tap_dy[9], tap_dx[9], tap_img[9];  // per tap: input offset and image-index offset (phase planes)
+  int a_lo_img;        // image-index offset of the lo plane in the A tensor map
+  // ---- tiling
+  int tw, th;          // spatial tile, tw * th == 128
+  int tiles_x, tiles_y;
+  int n_blocks;        // ceil(Cout / BLOCK_N)
+  int num_tiles;
+  // ---- B operand (weights [2][Cout][taps*Cin])
+  int Cout;
+  // ---- epilogue
+  const float* bias;   // [Cout] or null
+  int relu;
+  int res_mode;        // RES_*
+  const bf16* res_hi;
+  const bf16* res_lo;
+  int res_H, res_W;    // for RES_NEAREST: source size
+  int out_mode;        // OUT_*
+  bf16* out_hi;        // null when only fp32 output is wanted
+  bf16* out_lo;        // null in bf16 (non-split) mode
+  float* out_f32;      // optional fp32 NHWC copy (heads)
+  int ldc;             // channel stride of the output row (>= Cout)
+  int res_ld;
+  int out_H2, out_W2;  // OUT_PHASE: ceil(H/2), ceil(W/2)
+};
+
+// ATen nearest-neighbour source index (UpSampleKernel: nearest_idx), float scale.
+__host__ __device__ inline int nearest_src(int dst, int in_size, int out_size) {
+  if (out_size == in_size) return dst;
+  if (out_size == 2 * in_size) return dst >> 1;
+  float scale = (float)in_size / (float)out_size;
+  int s = (int)floorf((float)dst * scale);
+  return s < in_size - 1 ? s : in_size - 1;
+}
+
+// Row (pixel) -> output element offset (without channel).  Returns -1 if masked.
+__device__ __forceinline__ long long out_row_offset(const ConvParams& p, int n, int y, int x) {
+  if (p.out_mode == OUT_PHASE) {
+    int ph = (y & 1) * 2 + (x & 1);
+    long long img = (long long)ph * p.n_img + n;
+    return ((img * p.out_H2 + (y >> 1)) * p.out_W2 + (x >> 1)) * (long long)p.ldc;
+  }
+  return (((long long)n * p.H + y) * p.W + x) * (long long)p.ldc;
+}
+
+__device__ __forceinline__ long long res_row_offset(const ConvParams& p, int n, int y, int x) {
+  if (p.res_mode == RES_NEAREST) {
+    int sy = nearest_src(y, p.res_H, p.H);
+    int sx = nearest_src(x, p.res_W, p.W);
+    return (((long long)n * p.res_H + sy) * p.res_W + sx) * (long long)p.res_ld;
+  }
+  return (((long long)n * p.H + y) * p.W + x) * (long long)p.res_ld;
+}
+
+// Apply bias / residual / ReLU to 8 consecutive channels and store them.
+__device__ __forceinline__ void epilogue_store8(const ConvParams& p, long long orow, long long rrow,
+                                                int c, float* v) {
+  if (p.bias) {
+    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + c);
+    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + c + 4);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (p.res_mode != RES_NONE) {
+    uint4 rh = *reinterpret_cast<const uint4*>(p.res_hi + rrow + c);
+    const bf16* h = reinterpret_cast<const bf16*>(&rh);
+    if (p.res_lo) {
+      uint4 rl = *reinterpret_cast<const uint4*>(p.res_lo + rrow + c);
+      const bf16* l = reinterpret_cast<const bf16*>(&rl);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += join_bf16(h[i], l[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += __bfloat162float(h[i]);
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (p.out_f32) {
+    float4* o = reinterpret_cast<float4*>(p.out_f32 + orow + c);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (p.out_hi) {
+    bf16 h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
+    uint4 ph = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]),
+                          pack_bf16x2(h[6], h[7]));
+    *reinterpret_cast<uint4*>(p.out_hi + orow + c) = ph;
+    if (p.out_lo) {
+      uint4 pl = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]),
+                            pack_bf16x2(l[6], l[7]));
+      *reinterpret_cast<uint4*>(p.out_lo + orow + c) = pl;
+    }
+  }
+}
+
+}  // namespace cald

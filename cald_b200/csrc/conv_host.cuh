@@ -1,0 +1,217 @@
+// Host side of the implicit-GEMM engine: tensor-map construction, tile choice, launch.
+#pragma once
+#include <cstring>
+#include <vector>
+#include <cstdlib>
+#include "igemm.cuh"
+
+namespace cald {
+
+// ---- split-bf16 NHWC activation: planes [hi | lo], each [phases*n][h][w][c]
+struct Act {
+  bf16* hi = nullptr;
+  int n = 0, h = 0, w = 0, c = 0;
+  int phases = 1;
+  bool split = true;
+  size_t plane_elems() const { return (size_t)phases * n * h * w * c; }
+  bf16* lo() const { return split ? hi + plane_elems() : nullptr; }
+  size_t bytes() const { return plane_elems() * (split ? 2 : 1) * sizeof(bf16); }
+};
+
+// ---- conv / linear weights on device: [2][cout_pad][taps*cin] bf16 (BN already folded) + fp32 bias
+struct ConvW {
+  bf16* w = nullptr;
+  float* bias = nullptr;
+  int cout = 0, cout_pad = 0, cin = 0, taps = 1;
+  size_t plane_elems() const { return (size_t)cout_pad * taps * cin; }
+};
+
+struct ConvOpts {
+  bool relu = false;
+  int stride = 1;               // 3x3: 1 or 2 (2 => input must be phase-split); 1x1: caller subsamples first
+  int res_mode = RES_NONE;
+  const Act* res = nullptr;
+  bool out_phase = false;       // write the output phase-split (feeds a stride-2 3x3)
+  int full_h = 0, full_w = 0;   // out_phase: logical (full-resolution) output size
+  float* out_f32 = nullptr;     // fp32 NHWC output instead of / in addition to split bf16
+  bool no_bf16_out = false;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CALD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+    if (!p || qr != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled unavailable");
+    fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// 4-D bf16 tensor map, innermost box = 64 elements (128 B) with 128B swizzle.
+inline CUtensorMap make_tmap(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t b1,
+                             uint32_t b2) {
+  CUtensorMap tm;
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {d0 * 2, d0 * d1 * 2, d0 * d1 * d2 * 2};
+  cuuint32_t box[4] = {64, b1, b2, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = get_encode_tiled()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                                  box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[256];
+    snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu,%llu,%llu box=%u,%u", (int)r,
+             (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)d3, b1, b2);
+    throw std::runtime_error(b);
+  }
+  return tm;
+}
+
+inline void choose_tile(int H, int W, int& th, int& tw) {
+  static const int cand[8][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {64, 2}, {1, 128}, {128, 1}};
+  long long best = -1;
+  for (auto& c : cand) {
+    long long area = (long long)((H + c[0] - 1) / c[0]) * c[0] * ((W + c[1] - 1) / c[1]) * c[1];
+    if (best < 0 || area < best) { best = area; th = c[0]; tw = c[1]; }
+  }
+}
+
+enum ConvImpl { CONV_TC = 0, CONV_SIMT = 1 };
+
+struct ConvEngine {
+  int num_sms = 148;
+  ConvImpl impl = CONV_TC;
+  bool split = true;       // false: single-pass bf16 (hi plane only)
+  int force_block_n = 0;   // 0 = auto
+  long long launches = 0;  // kernels launched (bench's gpu_launches)
+  double flops = 0;        // algorithmic 2*MAC of the launches
+
+  template <int BN, bool SP>
+  void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
+    using Cfg = IgemmCfg<BN, SP>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<BN, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+      attr_set = true;
+    }
+    int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    igemm_tc_kernel<BN, SP><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    CALD_CUDA_CHECK(cudaGetLastError());
+  }
+
+  // out must be pre-shaped by the caller (n, h, w, c = cout_pad or larger ldc).
+  void run(const Act& in, const ConvW& w, Act& out, const ConvOpts& o, cudaStream_t st) {
+    if (in.c != w.cin || (w.cin % 64) != 0) throw std::runtime_error("conv: Cin mismatch or not a multiple of 64");
+    if (in.split != split) throw std::runtime_error("conv: activation precision mode mismatch");
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    const bool spatial = (w.taps == 9) || o.out_phase || o.res_mode == RES_NEAREST;
+    p.Cin = w.cin;
+    p.taps = w.taps;
+    p.Cout = w.cout_pad;
+    int n_img_in;
+    if (spatial) {
+      p.n_img = out.n;
+      p.H = o.out_phase ? o.full_h : out.h;
+      p.W = o.out_phase ? o.full_w : out.w;
+      n_img_in = in.n;
+      if (w.taps == 1) {
+        if (in.phases != 1) throw std::runtime_error("conv: 1x1 needs a plain input");
+        p.tap_dy[0] = p.tap_dx[0] = p.tap_img[0] = 0;
+      } else if (o.stride == 2) {
+        if (in.phases != 4) throw std::runtime_error("conv: stride-2 3x3 needs a phase-split input");
+        for (int r = 0; r < 3; ++r)
+          for (int s = 0; s < 3; ++s) {
+            int t = r * 3 + s;
+            p.tap_dy[t] = (r == 0) ? -1 : 0;
+            p.tap_dx[t] = (s == 0) ? -1 : 0;
+            p.tap_img[t] = (((r == 1) ? 0 : 1) * 2 + ((s == 1) ? 0 : 1)) * in.n;
+          }
+      } else {
+        if (in.phases != 1) throw std::runtime_error("conv: stride-1 3x3 needs a plain input");
+        for (int r = 0; r < 3; ++r)
+          for (int s = 0; s < 3; ++s) {
+            p.tap_dy[r * 3 + s] = r - 1;
+            p.tap_dx[r * 3 + s] = s - 1;
+            p.tap_img[r * 3 + s] = 0;
+          }
+      }
+      choose_tile(p.H, p.W, p.th, p.tw);
+      p.tiles_x = (p.W + p.tw - 1) / p.tw;
+      p.tiles_y = (p.H + p.th - 1) / p.th;
+      p.a_lo_img = in.phases * in.n;
+    } else {
+      // linear: all pixels of all images are rows of one [M][K] matrix
+      if (in.phases != 1) throw std::runtime_error("conv: 1x1 needs a plain input");
+      p.n_img = 1;
+      p.H = 1;
+      long long M = (long long)in.n * in.h * in.w;
+      p.W = (int)M;
+      p.th = 1; p.tw = 128;
+      p.tiles_x = (int)((M + 127) / 128);
+      p.tiles_y = 1;
+      p.a_lo_img = 1;
+      n_img_in = 1;
+    }
+    int BN = force_block_n ? force_block_n : (w.cout_pad <= 64 ? 64 : 128);
+    if (!force_block_n && !split && w.cout_pad % 256 == 0) BN = 256;
+    p.n_blocks = (w.cout_pad + BN - 1) / BN;
+    p.num_tiles = p.n_blocks * p.tiles_x * p.tiles_y * p.n_img;
+    p.bias = w.bias;
+    p.relu = o.relu ? 1 : 0;
+    p.res_mode = o.res_mode;
+    if (o.res_mode != RES_NONE) {
+      p.res_hi = o.res->hi;
+      p.res_lo = o.res->lo();
+      p.res_H = o.res->h;
+      p.res_W = o.res->w;
+      p.res_ld = o.res->c;
+    }
+    p.out_mode = o.out_phase ? OUT_PHASE : OUT_NHWC;
+    p.out_hi = o.no_bf16_out ? nullptr : out.hi;
+    p.out_lo = o.no_bf16_out ? nullptr : out.lo();
+    p.out_f32 = o.out_f32;
+    p.ldc = out.c;
+    p.out_H2 = out.h;
+    p.out_W2 = out.w;
+    launches++;
+    flops += 2.0 * (double)p.n_img * p.H * p.W * (double)w.cout * w.taps * w.cin;
+
+    if (impl == CONV_SIMT) {
+      SimtOperands so;
+      so.a_hi = in.hi; so.a_lo = in.lo();
+      so.b_hi = w.w; so.b_lo = split ? w.w + w.plane_elems() : nullptr;
+      if (spatial) { so.H_in = in.h; so.W_in = in.w; } else { so.H_in = 1; so.W_in = p.W; }
+      so.n_img_in = n_img_in;
+      long long total = (long long)p.n_img * p.H * p.W * ((p.Cout + 7) / 8);
+      int blocks = (int)((total + 127) / 128);
+      conv_simt_kernel<<<blocks, 128, 0, st>>>(p, so);
+      CALD_CUDA_CHECK(cudaGetLastError());
+      return;
+    }
+    CUtensorMap ta, tb;
+    if (spatial)
+      ta = make_tmap(in.hi, in.c, in.w, in.h, (uint64_t)in.phases * in.n * (split ? 2 : 1), p.tw, p.th);
+    else
+      ta = make_tmap(in.hi, in.c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);
+    tb = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, split ? 2 : 1, BN, 1);
+    if (split) {
+      if (BN == 64) launch_tc<64, true>(ta, tb, p, st);
+      else if (BN == 128) launch_tc<128, true>(ta, tb, p, st);
+      else launch_tc<256, true>(ta, tb, p, st);
+    } else {
+      if (BN == 64) launch_tc<64, false>(ta, tb, p, st);
+      else if (BN == 128) launch_tc<128, false>(ta, tb, p, st);
+      else launch_tc<256, false>(ta, tb, p, st);
+    }
+  }
+};
+
+}  // namespace cald

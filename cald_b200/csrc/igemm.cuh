@@ -1,0 +1,326 @@
+// Implicit-GEMM convolution / GEMM on tcgen05 tensor cores (sm_100a).
+//
+// One persistent, warp-specialised kernel serves every dense contraction of the
+// detectors the CALD scoring path runs (a11 ResNet body, a12 FPN,
+// a13 RPN head, a15 box head, a18 RetinaNet heads):
+//   warp 0   : TMA producer  (cp.async.bulk.tensor 4-D boxes -> 128B-swizzled smem)
+//   warp 1   : MMA issuer    (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM)
+//   warps 2-5: epilogue      (tcgen05.ld -> bias / residual / ReLU -> split-bf16 NHWC)
+// A tile = 128 output pixels (th x tw patch of one image, or 128 rows in linear
+// mode) x 64 input channels; the 3x3 taps are realised as shifted TMA boxes with
+// hardware zero fill at the borders, so no im2col buffer ever exists in HBM.
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#pragma once
+#include "common.cuh"
+
+namespace cald {
+
+constexpr int IG_BLOCK_M = 128;
+constexpr int IG_BLOCK_K = 64;   // bf16 elements = one 128-byte swizzle row
+constexpr int IG_UMMA_K = 16;
+constexpr int IG_THREADS = 192;  // 6 warps
+
+template <int BLOCK_N, bool SPLIT>
+struct IgemmCfg {
+  static constexpr int A_BYTES = IG_BLOCK_M * IG_BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * IG_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 512;  // 2 accumulator stages of <= 256 fp32 columns
+  static constexpr int ACC_STRIDE = 256;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024>>4 | version [46,48) = 1 | layout [61,64) = 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// tile index -> (n block, image, y0, x0).  N blocks vary fastest so that CTAs running
+// concurrently share the same activation tile in L2.
+__device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& nb, int& img, int& y0, int& x0) {
+  nb = tile % p.n_blocks;
+  int m = tile / p.n_blocks;
+  int tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  int ty = m % p.tiles_y;
+  img = m / p.tiles_y;
+  y0 = ty * p.th;
+  x0 = tx * p.tw;
+}
+
+template <int BLOCK_N, bool SPLIT>
+__global__ void __launch_bounds__(IG_THREADS, 1)
+igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ ConvParams p) {
+  using Cfg = IgemmCfg<BLOCK_N, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  // barrier layout: full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * Cfg::STAGES;
+  const uint32_t tfull_bar = empty_bar + 8 * Cfg::STAGES, tempty_bar = tfull_bar + 16;
+  volatile uint32_t* tmem_holder =
+      reinterpret_cast<volatile uint32_t*>(smem_al + Cfg::STAGES * Cfg::STAGE_BYTES + 16 * Cfg::STAGES + 32);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + 8 * i, 1);
+      mbar_init(tempty_bar + 8 * i, 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32((const void*)tmem_holder)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int k_chunks = p.Cin / IG_BLOCK_K;
+  const int num_kb = p.taps * k_chunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int nb, img, y0, x0;
+        tile_coords(p, tile, nb, img, y0, x0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / k_chunks;
+          const int c0 = (kb - tap * k_chunks) * IG_BLOCK_K;
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap], ai = img + p.tap_img[tap];
+          const int bk = tap * p.Cin + c0, bn = nb * BLOCK_N;
+          tma_load_4d(sa, &tmA, fb, c0, ax, ay, ai);
+          tma_load_4d(sa + Cfg::A_BYTES, &tmB, fb, bk, bn, 0, 0);
+          if (SPLIT) {
+            tma_load_4d(sa + Cfg::A_BYTES + Cfg::B_BYTES, &tmA, fb, c0, ax, ay, ai + p.a_lo_img);
+            tma_load_4d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmB, fb, bk, bn, 0, 1);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                             ((uint32_t)(IG_BLOCK_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t a_hi = umma_desc_sw128(sa);
+          const uint64_t b_hi = umma_desc_sw128(sa + Cfg::A_BYTES);
+          const uint64_t a_lo = umma_desc_sw128(sa + Cfg::A_BYTES + Cfg::B_BYTES);
+          const uint64_t b_lo = umma_desc_sw128(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
+            const uint64_t ko = (uint64_t)((k * IG_UMMA_K * 2) >> 4);  // advance start address inside the swizzle row
+            if (SPLIT) {
+              // small cross terms first, dominant term last
+              tcgen05_mma_bf16(d, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0);
+              tcgen05_mma_bf16(d, a_hi + ko, b_lo + ko, idesc, 1);
+              tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, 1);
+            } else {
+              tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, (kb | k) != 0);
+            }
+          }
+          tcgen05_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
+          if (kb == num_kb - 1) tcgen05_commit(tfull_bar + 8 * acc);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int nb, img, y0, x0;
+      tile_coords(p, tile, nb, img, y0, x0);
+      const int y = y0 + row / p.tw, x = x0 + row % p.tw;
+      const bool valid = (y < p.H) && (x < p.W);
+      long long orow = 0, rrow = 0;
+      if (valid) {
+        orow = out_row_offset(p, img, y, x);
+        if (p.res_mode != RES_NONE) rrow = res_row_offset(p, img, y, x);
+      }
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t0 = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < BLOCK_N; cc += 32) {
+        uint32_t r[32];
+        tmem_ld32(t0 + cc, r);
+        const int cbase = nb * BLOCK_N + cc;
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const int c = cbase + j;
+            if (c < p.Cout) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
+              epilogue_store8(p, orow, rrow, c, v);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------------
+// SIMT checker: the same contraction with plain fp32 FMAs on the same split inputs.
+// Used by the stage-wise parity tests to validate the tensor-core kernel and as the
+// engine's CALD_CONV=simt debugging path.  One thread = one pixel x 8 output channels.
+// --------------------------------------------------------------------------------
+struct SimtOperands {
+  const bf16* a_hi; const bf16* a_lo;   // [img'][H_in][W_in][Cin]
+  const bf16* b_hi; const bf16* b_lo;   // [Cout_pad][taps*Cin]
+  int H_in, W_in, n_img_in;             // input plane geometry (a_lo == null -> bf16 mode)
+};
+
+__global__ void conv_simt_kernel(ConvParams p, SimtOperands o) {
+  const int cgroups = (p.Cout + 7) / 8;
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)p.n_img * p.H * p.W * cgroups;
+  if (gid >= total) return;
+  int cg = (int)(gid % cgroups);
+  long long pix = gid / cgroups;
+  int x = (int)(pix % p.W);
+  int y = (int)((pix / p.W) % p.H);
+  int n = (int)(pix / ((long long)p.W * p.H));
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int ktot = p.taps * p.Cin;
+  for (int tap = 0; tap < p.taps; ++tap) {
+    int iy = y + p.tap_dy[tap], ix = x + p.tap_dx[tap], ii = n + p.tap_img[tap];
+    if (iy < 0 || iy >= o.H_in || ix < 0 || ix >= o.W_in) continue;
+    const long long abase = (((long long)ii * o.H_in + iy) * o.W_in + ix) * p.Cin;
+    for (int c = 0; c < p.Cin; ++c) {
+      float a = __bfloat162float(o.a_hi[abase + c]);
+      if (o.a_lo) a += __bfloat162float(o.a_lo[abase + c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long bi = (long long)(cg * 8 + j) * ktot + tap * p.Cin + c;
+        float b = __bfloat162float(o.b_hi[bi]);
+        if (o.b_lo) b += __bfloat162float(o.b_lo[bi]);
+        acc[j] = fmaf(a, b, acc[j]);
+      }
+    }
+  }
+  long long orow = out_row_offset(p, n, y, x);
+  long long rrow = p.res_mode != RES_NONE ? res_row_offset(p, n, y, x) : 0;
+  epilogue_store8(p, orow, rrow, cg * 8, acc);
+}
+
+}  // namespace cald

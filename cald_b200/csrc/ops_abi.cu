@@ -1,0 +1,130 @@
+// Stage-level C ABI (see include/cald_b200_ops.h).  Host buffers in, host buffers out.
+#include "layers.cuh"
+#include "../../include/cald_b200_ops.h"
+
+using namespace cald;
+
+static thread_local std::string g_ops_err;
+extern "C" const char* cald_ops_last_error(void) { return g_ops_err.c_str(); }
+
+#define OPS_TRY try {
+#define OPS_CATCH                                   \
+  }                                                 \
+  catch (const std::exception& e) {                 \
+    g_ops_err = e.what();                           \
+    cudaGetLastError();                             \
+    return -1;                                      \
+  }                                                 \
+  return 0;
+
+namespace cald {
+// Upload torch-layout weights [cout][cin][k][k] as [2][cout_pad][(r,s,cin)] split bf16 (+ fp32 bias).
+ConvW upload_conv_weight(const float* w, const float* bias, int cout, int cin, int k, bool split,
+                         const float* scale /*per-cout or null*/) {
+  ConvW cw;
+  cw.cout = cout;
+  cw.cout_pad = (cout + 7) / 8 * 8;
+  cw.cin = cin;
+  cw.taps = k * k;
+  size_t pe = cw.plane_elems();
+  std::vector<bf16> h(pe * (split ? 2 : 1));
+  for (auto& v : h) v = __float2bfloat16(0.f);
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < cin; ++c)
+      for (int r = 0; r < k; ++r)
+        for (int s = 0; s < k; ++s) {
+          float v = w[(((size_t)o * cin + c) * k + r) * k + s];
+          if (scale) v *= scale[o];
+          size_t idx = (size_t)o * cw.taps * cin + (size_t)(r * k + s) * cin + c;
+          bf16 hi, lo;
+          split_bf16(v, hi, lo);
+          h[idx] = hi;
+          if (split) h[pe + idx] = lo;
+        }
+  CALD_CUDA_CHECK(cudaMalloc((void**)&cw.w, h.size() * sizeof(bf16)));
+  CALD_CUDA_CHECK(cudaMemcpy(cw.w, h.data(), h.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  std::vector<float> b(cw.cout_pad, 0.f);
+  if (bias) for (int o = 0; o < cout; ++o) b[o] = bias[o];
+  CALD_CUDA_CHECK(cudaMalloc((void**)&cw.bias, b.size() * sizeof(float)));
+  CALD_CUDA_CHECK(cudaMemcpy(cw.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return cw;
+}
+void free_conv_weight(ConvW& w) {
+  if (w.w) cudaFree(w.w);
+  if (w.bias) cudaFree(w.bias);
+  w.w = nullptr; w.bias = nullptr;
+}
+}  // namespace cald
+
+extern "C" int cald_op_conv2d(const float* x, int n, int h, int w, int cin, const float* weight, const float* bias,
+                              int cout, int k, int stride, int relu, const float* res, int res_mode, int res_h,
+                              int res_w, int prec, int impl, int phase_out, int block_n, float* out) {
+  OPS_TRY
+  const bool split = (prec == 0);
+  cudaStream_t st = 0;
+  Arena ar;
+  size_t in_e = (size_t)n * h * w * cin;
+  int ho = (stride == 2) ? (h + 1) / 2 : h, wo = (stride == 2) ? (w + 1) / 2 : w;
+  size_t out_e = (size_t)n * ho * wo * ((cout + 7) / 8 * 8);
+  ar.init((in_e + out_e) * 16 + ((size_t)64 << 20) + (size_t)n * res_h * res_w * cout * 16);
+  ConvEngine eng;
+  int dev;
+  CALD_CUDA_CHECK(cudaGetDevice(&dev));
+  CALD_CUDA_CHECK(cudaDeviceGetAttribute(&eng.num_sms, cudaDevAttrMultiProcessorCount, dev));
+  eng.impl = impl ? CONV_SIMT : CONV_TC;
+  eng.split = split;
+  eng.force_block_n = block_n;
+  ConvW cw = upload_conv_weight(weight, bias, cout, cin, k, split, nullptr);
+  float* dx = (float*)ar.alloc(in_e * 4);
+  CALD_CUDA_CHECK(cudaMemcpy(dx, x, in_e * 4, cudaMemcpyHostToDevice));
+  Act a = alloc_act(ar, n, h, w, cin, split);
+  f32_to_split(dx, a, st);
+  Act rs;
+  if (res_mode) {
+    size_t re = (size_t)n * res_h * res_w * cw.cout_pad;
+    if (cw.cout_pad != cout) throw std::runtime_error("test op: residual needs cout % 8 == 0");
+    float* dr = (float*)ar.alloc(re * 4);
+    CALD_CUDA_CHECK(cudaMemcpy(dr, res, re * 4, cudaMemcpyHostToDevice));
+    rs = alloc_act(ar, n, res_h, res_w, cout, split);
+    f32_to_split(dr, rs, st);
+  }
+  Act in = a;
+  if (stride == 2) in = (k == 3) ? phase_split(ar, a, st) : subsample2(ar, a, st);
+  ConvOpts o;
+  o.relu = relu != 0;
+  o.stride = (k == 3) ? stride : 1;
+  o.res_mode = res_mode;
+  o.res = res_mode ? &rs : nullptr;
+  Act y;
+  if (phase_out) {
+    y = alloc_act(ar, n, (ho + 1) / 2, (wo + 1) / 2, cw.cout_pad, split, 4);
+    CALD_CUDA_CHECK(cudaMemsetAsync(y.hi, 0, y.bytes(), st));
+    o.out_phase = true;
+    o.full_h = ho;
+    o.full_w = wo;
+  } else {
+    y = alloc_act(ar, n, ho, wo, cw.cout_pad, split);
+  }
+  eng.run(in, cw, y, o, st);
+  std::vector<float> hy(y.plane_elems());
+  float* dy = (float*)ar.alloc(hy.size() * 4);
+  split_to_f32(y, dy, st);
+  CALD_CUDA_CHECK(cudaMemcpyAsync(hy.data(), dy, hy.size() * 4, cudaMemcpyDeviceToHost, st));
+  CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; ++i)
+    for (int yy = 0; yy < ho; ++yy)
+      for (int xx = 0; xx < wo; ++xx)
+        for (int c = 0; c < cout; ++c) {
+          size_t src;
+          if (phase_out) {
+            int ph = (yy & 1) * 2 + (xx & 1);
+            src = ((((size_t)ph * n + i) * y.h + (yy >> 1)) * y.w + (xx >> 1)) * cw.cout_pad + c;
+          } else {
+            src = (((size_t)i * ho + yy) * wo + xx) * cw.cout_pad + c;
+          }
+          out[(((size_t)i * ho + yy) * wo + xx) * cout + c] = hy[src];
+        }
+  free_conv_weight(cw);
+  ar.destroy();
+  OPS_CATCH
+}

@@ -1,0 +1,41 @@
+/* Stage-level entry points of libcald_b200.so.
+ *
+ * These expose single stages of the scoring pipeline on HOST buffers so that the
+ * stage-wise parity tests (tests/test_gpu_*.py) can compare each hand-written
+ * kernel with the CPU oracle in isolation ("parity must be
+ * asserted stage-wise").  They are not needed by a caller of cald_score().
+ *
+ * All functions return 0 on success, <0 on error; cald_ops_last_error() returns
+ * the message of the last failure on the calling thread.
+ */
+#ifndef CALD_B200_OPS_H
+#define CALD_B200_OPS_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* cald_ops_last_error(void);
+
+/* conv2d / linear on the implicit-GEMM engine.
+ * Replaces: torch.nn.functional.conv2d as used by torchvision resnet.py Bottleneck,
+ *           ops/feature_pyramid_network.py:172-204, models/detection/rpn.py:71-78 and
+ *           F.linear in models/detection/faster_rcnn.py:286-307 (a 1x1 conv on 1x1 maps).
+ * x:      [n][h][w][cin]  fp32 NHWC (cin multiple of 64)
+ * weight: [cout][cin][k][k] fp32 (torch layout), k in {1,3}; pad = k/2; stride in {1,2}
+ * bias:   [cout] or NULL
+ * res:    optional residual added before ReLU, NHWC fp32 [n][res_h][res_w][cout];
+ *         res_mode 0 none, 1 same shape, 2 nearest-upsampled to the output size
+ * prec:   0 = split-bf16 x3 (fp32-faithful), 1 = single-pass bf16
+ * impl:   0 = tcgen05 kernel, 1 = SIMT checker kernel
+ * phase_out: 1 = exercise the phase-split epilogue (output is re-assembled before return)
+ * out:    [n][ho][wo][cout] fp32
+ */
+int cald_op_conv2d(const float* x, int n, int h, int w, int cin, const float* weight, const float* bias, int cout,
+                   int k, int stride, int relu, const float* res, int res_mode, int res_h, int res_w, int prec,
+                   int impl, int phase_out, int block_n, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,99 @@
+"""Stage parity: implicit-GEMM conv / linear kernels vs torch CPU fp32 conv2d.
+
+Oracle for this stage = torch.nn.functional.conv2d on CPU in fp32 (the exact op the
+reference's CPU run executes: tv resnet.py / feature_pyramid_network.py / rpn.py).
+Tolerances: split-bf16 x3 mode carries ~16 mantissa bits per operand -> relative
+error ~2e-5 of the output scale; single-pass bf16 ~1e-2.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w, b, stride, relu, res=None, res_mode=0):
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+    y = F.conv2d(xt, torch.from_numpy(w), None if b is None else torch.from_numpy(b), stride=stride,
+                 padding=w.shape[-1] // 2)
+    if res is not None:
+        r = torch.from_numpy(res).permute(0, 3, 1, 2)
+        if res_mode == 2:
+            r = F.interpolate(r, size=y.shape[-2:], mode="nearest")
+        y = y + r
+    if relu:
+        y = F.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous().numpy()
+
+
+def _case(seed, n, h, w, cin, cout, k, stride=1, relu=True, bias=True, res_mode=0, res_hw=None):
+    rs = np.random.RandomState(seed)
+    x = rs.standard_normal((n, h, w, cin)).astype(np.float32)
+    wt = (rs.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (cin * k * k))).astype(np.float32)
+    b = rs.standard_normal(cout).astype(np.float32) if bias else None
+    ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
+    res = None
+    if res_mode == 1:
+        res = rs.standard_normal((n, ho, wo, cout)).astype(np.float32)
+    elif res_mode == 2:
+        res = rs.standard_normal((n,) + tuple(res_hw) + (cout,)).astype(np.float32)
+    return x, wt, b, res
+
+
+CASES = [
+    # n, h, w, cin, cout, k, stride, res_mode, res_hw
+    (1, 16, 16, 64, 64, 1, 1, 0, None),
+    (2, 19, 25, 64, 256, 1, 1, 1, None),
+    (1, 38, 50, 256, 64, 1, 1, 0, None),
+    (2, 20, 28, 64, 64, 3, 1, 0, None),
+    (1, 19, 25, 128, 128, 3, 1, 0, None),
+    (1, 25, 42, 256, 256, 3, 1, 0, None),
+    (2, 19, 25, 128, 128, 3, 2, 0, None),
+    (1, 20, 26, 256, 512, 1, 2, 0, None),
+    (1, 38, 50, 512, 256, 1, 1, 2, (19, 25)),
+    (1, 13, 21, 256, 16, 1, 1, 0, None),
+    (1, 10, 100, 1024, 112, 1, 1, 0, None),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("impl", [1, 0])
+def test_conv_split_matches_fp32(case, impl):
+    from cald_b200 import ops
+    n, h, w, cin, cout, k, stride, res_mode, res_hw = case
+    x, wt, b, res = _case(hash(case) % 1000, n, h, w, cin, cout, k, stride, True, True, res_mode, res_hw)
+    want = _ref(x, wt, b, stride, True, res, res_mode)
+    got = ops.conv2d(x, wt, b, stride=stride, relu=True, res=res, res_mode=res_mode, prec=0, impl=impl)
+    scale = np.abs(want).max()
+    err = np.abs(got - want).max()
+    assert err <= 3e-5 * scale + 1e-6, (err, scale)
+
+
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+def test_conv_block_n_variants(block_n):
+    from cald_b200 import ops
+    x, wt, b, _ = _case(7, 1, 24, 40, 128, 256, 3)
+    want = _ref(x, wt, b, 1, False)
+    for prec, tol in ((0, 3e-5), (1, 2e-2)):
+        got = ops.conv2d(x, wt, b, prec=prec, impl=0, block_n=block_n)
+        assert np.abs(got - want).max() <= tol * np.abs(want).max()
+
+
+def test_conv_phase_split_epilogue():
+    from cald_b200 import ops
+    x, wt, b, _ = _case(11, 2, 19, 25, 64, 128, 1)
+    a = ops.conv2d(x, wt, b, relu=True, prec=0, impl=0, phase_out=False)
+    p = ops.conv2d(x, wt, b, relu=True, prec=0, impl=0, phase_out=True)
+    assert np.array_equal(a, p)
+
+
+def test_conv_tc_equals_simt_large_k():
+    """fc6-like contraction: K = 12544, many k-blocks through the smem ring."""
+    from cald_b200 import ops
+    rs = np.random.RandomState(3)
+    x = rs.standard_normal((1, 1, 300, 12544)).astype(np.float32)
+    wt = (rs.standard_normal((128, 12544, 1, 1)) * 0.01).astype(np.float32)
+    want = _ref(x, wt, None, 1, False)
+    got = ops.conv2d(x, wt, None, prec=0, impl=0)
+    assert np.abs(got - want).max() <= 3e-5 * np.abs(want).max()
