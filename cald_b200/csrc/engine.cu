@@ -1,0 +1,1071 @@
+// Host side of the scoring engine: weight folding, the Faster R-CNN forward pass as a stream of
+// hand-written kernels, the CALD scoring loop, and the public C ABI (include/cald_b200.h).
+#include <map>
+#include <cmath>
+#include <algorithm>
+#include <memory>
+#include "layers.cuh"
+#include "det.cuh"
+#include "pre.cuh"
+#include "cons.cuh"
+#include "../../include/cald_b200.h"
+
+using namespace cald;
+
+namespace cald {
+ConvW upload_conv_weight(const float* w, const float* bias, int cout, int cin, int k, bool split, const float* scale);
+void free_conv_weight(ConvW& w);
+}
+
+namespace {
+
+struct HostTensor {
+  std::vector<float> v;
+  std::vector<int64_t> shape;
+};
+
+struct Block {
+  ConvW c1, c2, c3, ds;
+  bool has_ds = false;
+  int stride = 1;
+};
+
+// fixed-capacity detections of a set of views (device)
+struct ViewSet {
+  int V = 0;
+  DetOut det{};
+  float* scores = nullptr;    // [V][cap][C]
+  float* prob_max = nullptr;  // [V][cap] (per proposal)
+};
+
+static std::string g_create_err;
+
+}  // namespace
+
+struct cald_engine {
+  cald_config cfg;
+  std::string err;
+  cudaStream_t st = nullptr;
+  ConvEngine conv;
+  Arena arena;
+  bool split = true;
+  int C = 0;          // classes incl. background
+  int cap = 1000;     // proposals per view
+  int det_cap = 100;
+  long long launches = 0;
+
+  std::map<std::string, HostTensor> staged;
+  bool weights_ready = false;
+  ConvW stem;
+  std::vector<std::vector<Block>> layers;
+  ConvW fpn_inner[4], fpn_layer[4], rpn_conv, rpn_out, fc6, fc7, pred;
+  int head_ld = 0;
+
+  // device constants
+  int* d_lut = nullptr;  // [(det_cap+1)][50]
+  std::map<std::string, std::vector<float>> dbg;
+  std::map<long long, std::pair<int*, int*>> pil_cache;  // (in,out,filter) -> device bounds, kk
+  std::map<long long, int> pil_ksize;
+  std::vector<float> last_per_view;
+  int last_A = 0;
+
+  ~cald_engine() {
+    if (d_lut) cudaFree(d_lut);
+    for (auto& kv : pil_cache) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+    auto fw = [](ConvW& w) { free_conv_weight(w); };
+    fw(stem); fw(rpn_conv); fw(rpn_out); fw(fc6); fw(fc7); fw(pred);
+    for (int i = 0; i < 4; ++i) { fw(fpn_inner[i]); fw(fpn_layer[i]); }
+    for (auto& l : layers) for (auto& b : l) { fw(b.c1); fw(b.c2); fw(b.c3); if (b.has_ds) fw(b.ds); }
+    arena.destroy();
+    if (st) cudaStreamDestroy(st);
+  }
+};
+
+namespace {
+
+#define KLAUNCH(e) ((e)->launches++)
+
+const HostTensor& need(cald_engine* e, const std::string& name) {
+  auto it = e->staged.find(name);
+  if (it == e->staged.end()) throw std::runtime_error("missing weight tensor: " + name);
+  return it->second;
+}
+
+std::string canonical_key(const std::string& n) {
+  // torchvision 0.8.2 spellings (README.md:10-11 pin) -> current
+  if (n == "rpn.head.conv.weight") return "rpn.head.conv.0.0.weight";
+  if (n == "rpn.head.conv.bias") return "rpn.head.conv.0.0.bias";
+  for (const char* grp : {"backbone.fpn.inner_blocks.", "backbone.fpn.layer_blocks."}) {
+    std::string g(grp);
+    if (n.compare(0, g.size(), g) == 0) {
+      std::string rest = n.substr(g.size());  // "i.weight" or "i.0.weight"
+      size_t dot = rest.find('.');
+      if (dot != std::string::npos && (rest.substr(dot + 1) == "weight" || rest.substr(dot + 1) == "bias"))
+        return g + rest.substr(0, dot) + ".0." + rest.substr(dot + 1);
+    }
+  }
+  return n;
+}
+
+// conv + FrozenBatchNorm2d folded: scale = w_bn * rsqrt(var + eps), bias = b_bn - mean * scale (tv:ops/misc.py:54-63)
+ConvW fold_conv_bn(cald_engine* e, const std::string& conv, const std::string& bn) {
+  const HostTensor& w = need(e, conv + ".weight");
+  const HostTensor& g = need(e, bn + ".weight");
+  const HostTensor& b = need(e, bn + ".bias");
+  const HostTensor& m = need(e, bn + ".running_mean");
+  const HostTensor& v = need(e, bn + ".running_var");
+  int cout = (int)w.shape[0], cin = (int)w.shape[1], k = (int)w.shape[2];
+  std::vector<float> scale(cout), bias(cout);
+  for (int o = 0; o < cout; ++o) {
+    scale[o] = g.v[o] * (1.0f / sqrtf(v.v[o] + 1e-5f));
+    bias[o] = b.v[o] - m.v[o] * scale[o];
+  }
+  return upload_conv_weight(w.v.data(), bias.data(), cout, cin, k, e->split, scale.data());
+}
+
+ConvW plain_conv(cald_engine* e, const std::string& name) {
+  const HostTensor& w = need(e, name + ".weight");
+  const HostTensor& b = need(e, name + ".bias");
+  int k = w.shape.size() == 4 ? (int)w.shape[2] : 1;
+  return upload_conv_weight(w.v.data(), b.v.data(), (int)w.shape[0], (int)w.shape[1], k, e->split, nullptr);
+}
+
+void finalize_weights(cald_engine* e) {
+  const int depth = e->cfg.depth;
+  static const int blocks50[4] = {3, 4, 6, 3}, blocks101[4] = {3, 4, 23, 3};
+  const int* nb = depth == 101 ? blocks101 : blocks50;
+  // ---- stem: [64][3][7][7] with BN folded -> [64][192], k = r*24 + s*3 + c
+  {
+    const HostTensor& w = need(e, "backbone.body.conv1.weight");
+    const HostTensor& g = need(e, "backbone.body.bn1.weight");
+    const HostTensor& b = need(e, "backbone.body.bn1.bias");
+    const HostTensor& m = need(e, "backbone.body.bn1.running_mean");
+    const HostTensor& v = need(e, "backbone.body.bn1.running_var");
+    std::vector<float> w2((size_t)64 * STEM_K, 0.f), bias(64);
+    for (int o = 0; o < 64; ++o) {
+      float scale = g.v[o] * (1.0f / sqrtf(v.v[o] + 1e-5f));
+      bias[o] = b.v[o] - m.v[o] * scale;
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 7; ++r)
+          for (int s = 0; s < 7; ++s)
+            w2[(size_t)o * STEM_K + r * 24 + s * 3 + c] = w.v[(((size_t)o * 3 + c) * 7 + r) * 7 + s] * scale;
+    }
+    e->stem = upload_conv_weight(w2.data(), bias.data(), 64, STEM_K, 1, e->split, nullptr);
+  }
+  e->layers.assign(4, {});
+  for (int li = 0; li < 4; ++li) {
+    for (int bi = 0; bi < nb[li]; ++bi) {
+      Block blk;
+      std::string pre = "backbone.body.layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+      blk.c1 = fold_conv_bn(e, pre + ".conv1", pre + ".bn1");
+      blk.c2 = fold_conv_bn(e, pre + ".conv2", pre + ".bn2");
+      blk.c3 = fold_conv_bn(e, pre + ".conv3", pre + ".bn3");
+      blk.stride = (bi == 0 && li > 0) ? 2 : 1;
+      if (bi == 0) {
+        blk.has_ds = true;
+        blk.ds = fold_conv_bn(e, pre + ".downsample.0", pre + ".downsample.1");
+      }
+      e->layers[li].push_back(blk);
+    }
+  }
+  for (int i = 0; i < 4; ++i) {
+    e->fpn_inner[i] = plain_conv(e, "backbone.fpn.inner_blocks." + std::to_string(i) + ".0");
+    e->fpn_layer[i] = plain_conv(e, "backbone.fpn.layer_blocks." + std::to_string(i) + ".0");
+  }
+  e->rpn_conv = plain_conv(e, "rpn.head.conv.0.0");
+  {
+    // 1x1 -> 3 objectness + 1x1 -> 12 deltas fused into one [16][256] matrix (rows 0..2 logits, 3..14 deltas)
+    const HostTensor& wc = need(e, "rpn.head.cls_logits.weight");
+    const HostTensor& bc = need(e, "rpn.head.cls_logits.bias");
+    const HostTensor& wb = need(e, "rpn.head.bbox_pred.weight");
+    const HostTensor& bb = need(e, "rpn.head.bbox_pred.bias");
+    std::vector<float> w(15 * 256), b(15);
+    memcpy(w.data(), wc.v.data(), 3 * 256 * 4);
+    memcpy(w.data() + 3 * 256, wb.v.data(), 12 * 256 * 4);
+    for (int i = 0; i < 3; ++i) b[i] = bc.v[i];
+    for (int i = 0; i < 12; ++i) b[3 + i] = bb.v[i];
+    e->rpn_out = upload_conv_weight(w.data(), b.data(), 15, 256, 1, e->split, nullptr);
+  }
+  {
+    // fc6: torch flattens [256][7][7] as c*49 + ph*7 + pw; RoIAlign writes (ph*7+pw)*256 + c
+    const HostTensor& w = need(e, "roi_heads.box_head.fc6.weight");
+    const HostTensor& b = need(e, "roi_heads.box_head.fc6.bias");
+    int out = (int)w.shape[0];
+    std::vector<float> w2(w.v.size());
+    for (int o = 0; o < out; ++o)
+      for (int c = 0; c < 256; ++c)
+        for (int s = 0; s < 49; ++s) w2[(size_t)o * 12544 + s * 256 + c] = w.v[(size_t)o * 12544 + c * 49 + s];
+    e->fc6 = upload_conv_weight(w2.data(), b.v.data(), out, 12544, 1, e->split, nullptr);
+  }
+  e->fc7 = plain_conv(e, "roi_heads.box_head.fc7");
+  {
+    const HostTensor& wc = need(e, "roi_heads.box_predictor.cls_score.weight");
+    const HostTensor& bc = need(e, "roi_heads.box_predictor.cls_score.bias");
+    const HostTensor& wb = need(e, "roi_heads.box_predictor.bbox_pred.weight");
+    const HostTensor& bb = need(e, "roi_heads.box_predictor.bbox_pred.bias");
+    const int C = e->C;
+    if ((int)wc.shape[0] != C || (int)wb.shape[0] != 4 * C) throw std::runtime_error("box predictor: num_classes mismatch");
+    std::vector<float> w((size_t)5 * C * 1024), b(5 * C);
+    memcpy(w.data(), wc.v.data(), (size_t)C * 1024 * 4);
+    memcpy(w.data() + (size_t)C * 1024, wb.v.data(), (size_t)4 * C * 1024 * 4);
+    for (int i = 0; i < C; ++i) b[i] = bc.v[i];
+    for (int i = 0; i < 4 * C; ++i) b[C + i] = bb.v[i];
+    e->pred = upload_conv_weight(w.data(), b.data(), 5 * C, 1024, 1, e->split, nullptr);
+    e->head_ld = e->pred.cout_pad;
+  }
+  e->staged.clear();
+  e->weights_ready = true;
+}
+
+// torchvision cell anchors (tv:anchor_utils.py:58-75): fp32 sqrt, round-half-even
+void cell_anchors(float size, float out[3][4]) {
+  const float ratios[3] = {0.5f, 1.0f, 2.0f};
+  for (int i = 0; i < 3; ++i) {
+    float hr = sqrtf(ratios[i]);
+    float wr = 1.0f / hr;
+    float ws = wr * size, hs = hr * size;
+    out[i][0] = nearbyintf(-ws / 2.f);
+    out[i][1] = nearbyintf(-hs / 2.f);
+    out[i][2] = nearbyintf(ws / 2.f);
+    out[i][3] = nearbyintf(hs / 2.f);
+  }
+}
+
+void dbg_store_act(cald_engine* e, const char* name, const Act& a) {
+  if (!e->cfg.debug) return;
+  std::vector<float>& v = e->dbg[name];
+  v.resize(a.plane_elems());
+  float* tmp = (float*)e->arena.alloc(v.size() * 4);
+  split_to_f32(a, tmp, e->st);
+  CALD_CUDA_CHECK(cudaMemcpyAsync(v.data(), tmp, v.size() * 4, cudaMemcpyDeviceToHost, e->st));
+  CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  e->arena.free(tmp);
+}
+void dbg_store_f32(cald_engine* e, const char* name, const float* d, size_t n) {
+  if (!e->cfg.debug) return;
+  std::vector<float>& v = e->dbg[name];
+  v.resize(n);
+  CALD_CUDA_CHECK(cudaMemcpyAsync(v.data(), d, n * 4, cudaMemcpyDeviceToHost, e->st));
+  CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
+}
+
+Act conv(cald_engine* e, const Act& in, const ConvW& w, int n, int h, int wd, const ConvOpts& o) {
+  Act out = alloc_act(e->arena, n, h, wd, w.cout_pad, e->split, 1);
+  e->conv.run(in, w, out, o, e->st);
+  KLAUNCH(e);
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// One forward pass over V views that share the padded input size (Hp, Wp).
+// d_views / d_cuts / d_image_hw / d_ratio live on the device.  Results go to `vs` (local view order).
+// ------------------------------------------------------------------------------------------------------------
+void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views, const CutRects* d_cuts,
+                  const int* d_image_hw, const float* d_ratio, ViewSet& vs) {
+  cudaStream_t st = e->st;
+  Arena& ar = e->arena;
+  const bool split = e->split;
+  const int C = e->C, cap = e->cap;
+
+  // ---- transform: normalise + resize + pad (fused), fp32 NHWC3
+  float* img = (float*)ar.alloc((size_t)V * Hp * Wp * 3 * 4);
+  {
+    dim3 grid((Wp * 3 + 191) / 192, Hp, V);
+    view_preprocess_kernel<<<grid, 192, 0, st>>>(d_views, d_cuts, Hp, Wp, img);
+    CALD_CUDA_CHECK(cudaGetLastError());
+    KLAUNCH(e);
+  }
+  dbg_store_f32(e, "input", img, (size_t)V * Hp * Wp * 3);
+  // ---- stem: im2col + GEMM (+BN+ReLU) + maxpool
+  Act col = stem_im2col(ar, img, V, Hp, Wp, split, st);
+  KLAUNCH(e);
+  ar.free(img);
+  ConvOpts relu_o;
+  relu_o.relu = true;
+  Act x = conv(e, col, e->stem, V, col.h, col.w, relu_o);
+  free_act(ar, col);
+  Act xp = maxpool3x3s2(ar, x, st);
+  KLAUNCH(e);
+  free_act(ar, x);
+  x = xp;
+  // ---- residual stages
+  Act cfeat[4];
+  for (int li = 0; li < 4; ++li) {
+    for (size_t bi = 0; bi < e->layers[li].size(); ++bi) {
+      const Block& b = e->layers[li][bi];
+      const int ho = b.stride == 2 ? (x.h + 1) / 2 : x.h, wo = b.stride == 2 ? (x.w + 1) / 2 : x.w;
+      Act idt;
+      if (b.has_ds) {
+        ConvOpts o;
+        if (b.stride == 2) {
+          Act xs = subsample2(ar, x, st);
+          e->launches += split ? 2 : 1;
+          idt = conv(e, xs, b.ds, V, ho, wo, o);
+          free_act(ar, xs);
+        } else {
+          idt = conv(e, x, b.ds, V, ho, wo, o);
+        }
+      }
+      Act t1;
+      if (b.stride == 2) {
+        t1 = alloc_act(ar, V, ho, wo, b.c1.cout_pad, split, 4);
+        if ((x.h & 1) || (x.w & 1)) {
+          CALD_CUDA_CHECK(cudaMemsetAsync(t1.hi, 0, t1.bytes(), st));
+        }
+        ConvOpts o;
+        o.relu = true;
+        o.out_phase = true;
+        o.full_h = x.h;
+        o.full_w = x.w;
+        e->conv.run(x, b.c1, t1, o, st);
+        KLAUNCH(e);
+      } else {
+        t1 = conv(e, x, b.c1, V, x.h, x.w, relu_o);
+      }
+      ConvOpts o2;
+      o2.relu = true;
+      o2.stride = b.stride;
+      Act t2 = conv(e, t1, b.c2, V, ho, wo, o2);
+      free_act(ar, t1);
+      ConvOpts o3;
+      o3.relu = true;
+      o3.res_mode = RES_SAME;
+      o3.res = b.has_ds ? &idt : &x;
+      Act y = conv(e, t2, b.c3, V, ho, wo, o3);
+      free_act(ar, t2);
+      if (b.has_ds) free_act(ar, idt);
+      const bool keep_x = (bi == 0 && li > 0);  // x is the previous stage's output (C2..C4), needed by the FPN
+      if (!keep_x) free_act(ar, x);
+      x = y;
+    }
+    cfeat[li] = x;
+  }
+  if (e->cfg.debug) {
+    dbg_store_act(e, "c2", cfeat[0]); dbg_store_act(e, "c3", cfeat[1]);
+    dbg_store_act(e, "c4", cfeat[2]); dbg_store_act(e, "c5", cfeat[3]);
+  }
+  // ---- FPN (tv:ops/feature_pyramid_network.py:172-221)
+  Act pf[5];
+  {
+    ConvOpts o;
+    Act last = conv(e, cfeat[3], e->fpn_inner[3], V, cfeat[3].h, cfeat[3].w, o);
+    pf[3] = conv(e, last, e->fpn_layer[3], V, last.h, last.w, o);
+    for (int i = 2; i >= 0; --i) {
+      ConvOpts oi;
+      oi.res_mode = RES_NEAREST;
+      oi.res = &last;
+      Act inner = conv(e, cfeat[i], e->fpn_inner[i], V, cfeat[i].h, cfeat[i].w, oi);
+      free_act(ar, last);
+      last = inner;
+      pf[i] = conv(e, last, e->fpn_layer[i], V, last.h, last.w, o);
+    }
+    free_act(ar, last);
+    for (int i = 0; i < 4; ++i) free_act(ar, cfeat[i]);
+    pf[4] = subsample2(ar, pf[3], st);  // LastLevelMaxPool: kernel 1, stride 2
+    e->launches += split ? 2 : 1;
+  }
+  if (e->cfg.debug) {
+    const char* nm[5] = {"p2", "p3", "p4", "p5", "p6"};
+    for (int i = 0; i < 5; ++i) dbg_store_act(e, nm[i], pf[i]);
+  }
+  // ---- RPN head (tv:rpn.py:71-78): 3x3+ReLU then fused 1x1 -> 15 (+1 pad) fp32
+  RpnLevels L;
+  memset(&L, 0, sizeof(L));
+  float* rpn_raw[5];
+  static const float sizes[5] = {32.f, 64.f, 128.f, 256.f, 512.f};
+  int off = 0;
+  for (int l = 0; l < 5; ++l) {
+    Act t = conv(e, pf[l], e->rpn_conv, V, pf[l].h, pf[l].w, relu_o);
+    rpn_raw[l] = (float*)ar.alloc((size_t)V * pf[l].h * pf[l].w * 16 * 4);
+    Act dummy;
+    dummy.n = V; dummy.h = pf[l].h; dummy.w = pf[l].w; dummy.c = 16; dummy.split = split; dummy.hi = nullptr;
+    ConvOpts o;
+    o.out_f32 = rpn_raw[l];
+    o.no_bf16_out = true;
+    e->conv.run(t, e->rpn_out, dummy, o, st);
+    KLAUNCH(e);
+    free_act(ar, t);
+    RpnLevel& lv = L.lv[l];
+    lv.out = rpn_raw[l];
+    lv.h = pf[l].h; lv.w = pf[l].w;
+    lv.stride_h = Hp / pf[l].h; lv.stride_w = Wp / pf[l].w;
+    cell_anchors(sizes[l], lv.base);
+    lv.n = pf[l].h * pf[l].w * 3;
+    lv.off = off;
+    off += lv.n;
+    if (e->cfg.debug) {
+      std::string nm = "rpn" + std::to_string(l);
+      dbg_store_f32(e, nm.c_str(), rpn_raw[l], (size_t)V * pf[l].h * pf[l].w * 16);
+    }
+  }
+  L.total = off;
+  free_act(ar, pf[4]);
+  // ---- proposals (tv:rpn.py:242-297)
+  const int G = V * RPN_LEVELS;
+  unsigned long long* keys = (unsigned long long*)ar.alloc((size_t)V * L.total * 8);
+  unsigned long long* sel = (unsigned long long*)ar.alloc((size_t)G * TOPK_MAX * 8);
+  int* sel_count = (int*)ar.alloc((size_t)G * 4);
+  float4* lv_boxes = (float4*)ar.alloc((size_t)G * TOPK_MAX * 16);
+  float* lv_scores = (float*)ar.alloc((size_t)G * TOPK_MAX * 4);
+  int* lv_count = (int*)ar.alloc((size_t)G * 4);
+  int* keep_idx = (int*)ar.alloc((size_t)G * TOPK_MAX * 4);
+  int* keep_count = (int*)ar.alloc((size_t)G * 4);
+  float4* props = (float4*)ar.alloc((size_t)V * cap * 16);
+  float* prop_scores = (float*)ar.alloc((size_t)V * cap * 4);
+  int* prop_count = (int*)ar.alloc((size_t)V * 4);
+  {
+    long long tot = (long long)V * L.total;
+    rpn_keys_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(L, V, keys);
+    TopkGroups tg;
+    memset(&tg, 0, sizeof(tg));
+    tg.keys = keys;
+    tg.stride_outer = L.total;
+    tg.inner = RPN_LEVELS;
+    for (int l = 0; l < 5; ++l) { tg.inner_off[l] = L.lv[l].off; tg.inner_n[l] = L.lv[l].n; }
+    tg.k = std::min(e->cfg.rpn_pre_nms_top_n, TOPK_MAX);
+    topk_select_kernel<<<G, 1024, 0, st>>>(tg, sel, sel_count);
+    rpn_decode_kernel<<<G, 1024, 0, st>>>(L, sel, sel_count, d_image_hw, 1e-3f, lv_boxes, lv_scores, lv_count);
+    nms_groups_kernel<<<G, 1024, NMS_SMEM, st>>>(lv_boxes, lv_count, (double)e->cfg.rpn_nms_thresh, keep_idx,
+                                                 keep_count);
+    rpn_merge_kernel<<<V, 1024, MERGE_CAP * 8, st>>>(lv_boxes, lv_scores, keep_idx, keep_count,
+                                                     std::min(e->cfg.rpn_post_nms_top_n, cap), props, prop_scores,
+                                                     prop_count, cap);
+    CALD_CUDA_CHECK(cudaGetLastError());
+    e->launches += 5;
+  }
+  if (e->cfg.debug) {
+    dbg_store_f32(e, "proposals", (const float*)props, (size_t)V * cap * 4);
+    std::vector<int> pc(V);
+    CALD_CUDA_CHECK(cudaMemcpyAsync(pc.data(), prop_count, V * 4, cudaMemcpyDeviceToHost, st));
+    CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<float>& v = e->dbg["proposal_count"];
+    v.assign(pc.begin(), pc.end());
+  }
+  for (int l = 0; l < 5; ++l) ar.free(rpn_raw[l]);
+  ar.free(keys); ar.free(sel); ar.free(sel_count); ar.free(lv_boxes); ar.free(lv_scores); ar.free(lv_count);
+  ar.free(keep_idx); ar.free(keep_count);
+  // ---- RoIAlign on P2..P5 -> [V*cap][49*256]
+  Act roi = alloc_act(ar, 1, 1, V * cap, 49 * 256, split, 1);
+  {
+    RoiFeats F;
+    for (int l = 0; l < 4; ++l) {
+      F.hi[l] = pf[l].hi; F.lo[l] = pf[l].lo();
+      F.h[l] = pf[l].h; F.w[l] = pf[l].w;
+      // tv:ops/poolers.py _infer_scale: 2 ** round(log2(feat / padded_input))
+      F.scale[l] = (float)std::pow(2.0, std::round(std::log2((double)pf[l].h / (double)Hp)));
+    }
+    F.C = 256;
+    roialign_kernel<<<dim3(cap, V), 256, 0, st>>>(F, props, prop_count, cap, roi.hi, roi.lo());
+    CALD_CUDA_CHECK(cudaGetLastError());
+    KLAUNCH(e);
+  }
+  dbg_store_act(e, "pooled", roi);
+  for (int l = 0; l < 4; ++l) free_act(ar, pf[l]);
+  // ---- box head (tv:faster_rcnn.py:286-307, 347-372)
+  Act f6 = conv(e, roi, e->fc6, 1, 1, V * cap, relu_o);
+  free_act(ar, roi);
+  Act f7 = conv(e, f6, e->fc7, 1, 1, V * cap, relu_o);
+  free_act(ar, f6);
+  float* head = (float*)ar.alloc((size_t)V * cap * e->head_ld * 4);
+  {
+    Act dummy;
+    dummy.n = 1; dummy.h = 1; dummy.w = V * cap; dummy.c = e->head_ld; dummy.split = split; dummy.hi = nullptr;
+    ConvOpts o;
+    o.out_f32 = head;
+    o.no_bf16_out = true;
+    e->conv.run(f7, e->pred, dummy, o, st);
+    KLAUNCH(e);
+  }
+  free_act(ar, f7);
+  dbg_store_f32(e, "head", head, (size_t)V * cap * e->head_ld);
+  // ---- postprocess_detections (frcnn_la.py:32-87) + transform.postprocess (292-315)
+  {
+    long long rows = (long long)V * cap;
+    softmax_rows_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(head, e->head_ld, C, rows, vs.scores,
+                                                                             vs.prob_max);
+    const int kept_cap = (C - 1) * cap;
+    unsigned long long* kept = (unsigned long long*)ar.alloc((size_t)V * kept_cap * 8);
+    int* kept_count = (int*)ar.alloc((size_t)V * 4);
+    unsigned long long* top = (unsigned long long*)ar.alloc((size_t)V * TOPK_MAX * 8);
+    int* top_count = (int*)ar.alloc((size_t)V * 4);
+    CALD_CUDA_CHECK(cudaMemsetAsync(kept_count, 0, V * 4, st));
+    det_class_nms_kernel<<<dim3(C - 1, V), 1024, NMS_SMEM + TOPK_MAX * 8 + TOPK_MAX * 4, st>>>(
+        head, e->head_ld, C, vs.scores, props, prop_count, cap, d_image_hw, e->cfg.box_score_thresh,
+        (double)e->cfg.box_nms_thresh, kept, kept_count, kept_cap);
+    TopkGroups tg;
+    memset(&tg, 0, sizeof(tg));
+    tg.keys = kept;
+    tg.stride_outer = kept_cap;
+    tg.inner = 1;
+    tg.dyn_n = kept_count;
+    tg.k = e->det_cap;
+    topk_select_kernel<<<V, 1024, 0, st>>>(tg, top, top_count);
+    det_gather_kernel<<<V, 128, 0, st>>>(top, top_count, head, e->head_ld, C, vs.scores, vs.prob_max, props, cap,
+                                         d_image_hw, d_ratio, e->det_cap, vs.det);
+    CALD_CUDA_CHECK(cudaGetLastError());
+    e->launches += 4;
+    ar.free(kept); ar.free(kept_count); ar.free(top); ar.free(top_count);
+  }
+  ar.free(head); ar.free(props); ar.free(prop_scores); ar.free(prop_count);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+ViewSet alloc_viewset(cald_engine* e, int V) {
+  Arena& ar = e->arena;
+  ViewSet vs;
+  vs.V = V;
+  const int dc = e->det_cap;
+  vs.det.count = (int*)ar.alloc((size_t)V * 4);
+  vs.det.boxes = (float4*)ar.alloc((size_t)V * dc * 16);
+  vs.det.props = (float4*)ar.alloc((size_t)V * dc * 16);
+  vs.det.scores = (float*)ar.alloc((size_t)V * dc * 4);
+  vs.det.prob_max = (float*)ar.alloc((size_t)V * dc * 4);
+  vs.det.labels = (int*)ar.alloc((size_t)V * dc * 4);
+  vs.det.prop_idx = (int*)ar.alloc((size_t)V * dc * 4);
+  vs.scores = (float*)ar.alloc((size_t)V * e->cap * e->C * 4);
+  vs.prob_max = (float*)ar.alloc((size_t)V * e->cap * 4);
+  return vs;
+}
+void free_viewset(cald_engine* e, ViewSet& vs) {
+  Arena& ar = e->arena;
+  ar.free(vs.det.count); ar.free(vs.det.boxes); ar.free(vs.det.props); ar.free(vs.det.scores);
+  ar.free(vs.det.prob_max); ar.free(vs.det.labels); ar.free(vs.det.prop_idx); ar.free(vs.scores);
+  ar.free(vs.prob_max);
+}
+
+// host description of one view before upload
+struct HostView {
+  const uint8_t* src;
+  int sh, sw;
+  int flip;
+  int cut_slot;
+};
+
+void resized_hw(const cald_config& c, int h, int w, int& rh, int& rw) {
+  // tv:transform.py:57-62 + F.interpolate(recompute_scale_factor=True): python doubles
+  double s = std::min((double)c.min_size / (double)std::min(h, w), (double)c.max_size / (double)std::max(h, w));
+  rh = (int)std::floor((double)h * s);
+  rw = (int)std::floor((double)w * s);
+}
+inline int pad32(int v) { return (int)(std::ceil((double)v / 32.0) * 32.0); }
+
+// Run the detector over `views` (any mix of sizes): group by padded shape, forward each group, results in view order.
+void detect_views(cald_engine* e, const std::vector<HostView>& views, const CutRects* d_cuts, ViewSet& out) {
+  const int V = (int)views.size();
+  std::vector<ViewDesc> vd(V);
+  std::vector<int> hw(V * 2), php(V), pwp(V);
+  std::vector<float> ratio(V * 2);
+  for (int i = 0; i < V; ++i) {
+    int rh, rw;
+    resized_hw(e->cfg, views[i].sh, views[i].sw, rh, rw);
+    vd[i] = ViewDesc{views[i].src, views[i].sh, views[i].sw, rh, rw, views[i].flip, views[i].cut_slot};
+    hw[i * 2] = rh; hw[i * 2 + 1] = rw;
+    ratio[i * 2] = (float)((double)views[i].sh / (double)rh);
+    ratio[i * 2 + 1] = (float)((double)views[i].sw / (double)rw);
+    php[i] = pad32(rh); pwp[i] = pad32(rw);
+  }
+  // order views by (Hp, Wp) groups
+  std::vector<int> order(V);
+  for (int i = 0; i < V; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return php[a] != php[b] ? php[a] < php[b] : pwp[a] < pwp[b];
+  });
+  Arena& ar = e->arena;
+  cudaStream_t st = e->st;
+  const int maxv = e->cfg.max_views_per_pass > 0 ? e->cfg.max_views_per_pass : 8;
+  int pos = 0;
+  while (pos < V) {
+    int end = pos + 1;
+    while (end < V && end - pos < maxv && php[order[end]] == php[order[pos]] && pwp[order[end]] == pwp[order[pos]]) ++end;
+    const int n = end - pos;
+    std::vector<ViewDesc> lvd(n);
+    std::vector<int> lhw(n * 2);
+    std::vector<float> lr(n * 2);
+    for (int j = 0; j < n; ++j) {
+      int g = order[pos + j];
+      lvd[j] = vd[g];
+      lhw[j * 2] = hw[g * 2]; lhw[j * 2 + 1] = hw[g * 2 + 1];
+      lr[j * 2] = ratio[g * 2]; lr[j * 2 + 1] = ratio[g * 2 + 1];
+    }
+    ViewDesc* d_vd = (ViewDesc*)ar.alloc(n * sizeof(ViewDesc));
+    int* d_hw = (int*)ar.alloc(n * 8);
+    float* d_r = (float*)ar.alloc(n * 8);
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d_vd, lvd.data(), n * sizeof(ViewDesc), cudaMemcpyHostToDevice, st));
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d_hw, lhw.data(), n * 8, cudaMemcpyHostToDevice, st));
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d_r, lr.data(), n * 8, cudaMemcpyHostToDevice, st));
+    CALD_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors go out of scope below
+    ViewSet local = alloc_viewset(e, n);
+    forward_pass(e, n, php[order[pos]], pwp[order[pos]], d_vd, d_cuts, d_hw, d_r, local);
+    // scatter to global view slots
+    const int dc = e->det_cap;
+    const size_t srow = (size_t)e->cap * e->C * 4;
+    for (int j = 0; j < n; ++j) {
+      int g = order[pos + j];
+      auto cp = [&](void* dst, const void* src, size_t bytes) {
+        CALD_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+      };
+      cp(out.det.count + g, local.det.count + j, 4);
+      cp(out.det.boxes + (size_t)g * dc, local.det.boxes + (size_t)j * dc, dc * 16);
+      cp(out.det.props + (size_t)g * dc, local.det.props + (size_t)j * dc, dc * 16);
+      cp(out.det.scores + (size_t)g * dc, local.det.scores + (size_t)j * dc, dc * 4);
+      cp(out.det.prob_max + (size_t)g * dc, local.det.prob_max + (size_t)j * dc, dc * 4);
+      cp(out.det.labels + (size_t)g * dc, local.det.labels + (size_t)j * dc, dc * 4);
+      cp(out.det.prop_idx + (size_t)g * dc, local.det.prop_idx + (size_t)j * dc, dc * 4);
+      cp((char*)out.scores + (size_t)g * srow, (char*)local.scores + (size_t)j * srow, srow);
+      cp(out.prob_max + (size_t)g * e->cap, local.prob_max + (size_t)j * e->cap, (size_t)e->cap * 4);
+    }
+    free_viewset(e, local);
+    ar.free(d_vd); ar.free(d_hw); ar.free(d_r);
+    pos = end;
+  }
+}
+
+// Pillow-exact resize of a device u8 image (horizontal pass then vertical pass).
+uint8_t* pil_resize_device(cald_engine* e, const uint8_t* src, int h, int w, int oh, int ow, int filter) {
+  Arena& ar = e->arena;
+  cudaStream_t st = e->st;
+  auto coeffs = [&](int in, int out, int*& d_bounds, int*& d_kk, int& ksize) {
+    long long key = ((long long)in << 34) | ((long long)out << 4) | filter;
+    auto it = e->pil_cache.find(key);
+    if (it == e->pil_cache.end()) {
+      PilCoeffs pc = pil_precompute(in, out, filter);
+      int *b, *k;
+      CALD_CUDA_CHECK(cudaMalloc((void**)&b, pc.bounds.size() * 4));
+      CALD_CUDA_CHECK(cudaMalloc((void**)&k, pc.kk.size() * 4));
+      CALD_CUDA_CHECK(cudaMemcpy(b, pc.bounds.data(), pc.bounds.size() * 4, cudaMemcpyHostToDevice));
+      CALD_CUDA_CHECK(cudaMemcpy(k, pc.kk.data(), pc.kk.size() * 4, cudaMemcpyHostToDevice));
+      e->pil_cache[key] = {b, k};
+      e->pil_ksize[key] = pc.ksize;
+      it = e->pil_cache.find(key);
+    }
+    d_bounds = it->second.first;
+    d_kk = it->second.second;
+    ksize = e->pil_ksize[key];
+  };
+  const uint8_t* cur = src;
+  uint8_t* tmp = nullptr;
+  if (ow != w) {
+    int *b, *k, ks;
+    coeffs(w, ow, b, k, ks);
+    tmp = (uint8_t*)ar.alloc((size_t)h * ow * 3);
+    pil_resample_h_kernel<<<dim3((ow * 3 + 255) / 256, h), 256, 0, st>>>(cur, tmp, h, w, ow, b, k, ks);
+    KLAUNCH(e);
+    cur = tmp;
+  }
+  uint8_t* out = (uint8_t*)ar.alloc((size_t)oh * ow * 3);
+  if (oh != h) {
+    int *b, *k, ks;
+    coeffs(h, oh, b, k, ks);
+    pil_resample_v_kernel<<<dim3((ow * 3 + 255) / 256, oh), 256, 0, st>>>(cur, out, h, oh, ow, b, k, ks);
+    KLAUNCH(e);
+  } else {
+    CALD_CUDA_CHECK(cudaMemcpyAsync(out, cur, (size_t)oh * ow * 3, cudaMemcpyDeviceToDevice, st));
+  }
+  CALD_CUDA_CHECK(cudaGetLastError());
+  if (tmp) ar.free(tmp);
+  return out;
+}
+
+// The affine of cald_helper.rotate's box transform (cald_helper.py:146-195): float64 math, then .float()
+void rotate_box_geom(int w, int h, double angle_deg, int rot_w, int rot_h, AugGeom& g) {
+  const double PI = 3.14159265358979323846;
+  double ang = angle_deg * PI / 180.0;  // np.radians
+  double alpha = cos(ang), beta = sin(ang);
+  double cx = w / 2.0, cy = h / 2.0;
+  double m[6] = {alpha, beta, (1 - alpha) * cx - beta * cy, -beta, alpha, beta * cx + (1 - alpha) * cy};
+  double c = fabs(m[0]), s = fabs(m[1]);
+  int nW = (int)((h * s) + (w * c));
+  int nH = (int)((h * c) + (w * s));
+  m[2] += (nW / 2.0) - cx;
+  m[5] += (nH / 2.0) - cy;
+  for (int i = 0; i < 6; ++i) g.m[i] = (float)m[i];
+  g.sx = (float)((double)rot_w / w);
+  g.sy = (float)((double)rot_h / h);
+}
+
+void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const int* hs, const int* ws,
+                 const std::vector<int>& augs, double bp, const double* d_u, int n_u, int* d_cursor,
+                 double* out_cons, double* out_cls) {
+  Arena& ar = e->arena;
+  cudaStream_t st = e->st;
+  const int A = (int)augs.size();
+  const int C = e->C, ncls1 = C - 1, dc = e->det_cap;
+  // ---------------- reference views
+  std::vector<HostView> rv(B);
+  for (int b = 0; b < B; ++b) rv[b] = HostView{d_images[b], hs[b], ws[b], 0, -1};
+  ViewSet ref = alloc_viewset(e, B);
+  detect_views(e, rv, nullptr, ref);
+  // ---------------- reference sub-sample, class vectors, cutout rects, boxes in aug coordinates
+  RefSet rs;
+  rs.n = (int*)ar.alloc(B * 4);
+  rs.n_det = (int*)ar.alloc(B * 4);
+  rs.boxes = (float4*)ar.alloc((size_t)B * REF_CAP * 16);
+  rs.prob_max = (float*)ar.alloc((size_t)B * REF_CAP * 4);
+  rs.prop_idx = (int*)ar.alloc((size_t)B * REF_CAP * 4);
+  float* d_cls = (float*)ar.alloc((size_t)B * (1 + A) * ncls1 * 4);  // [B] ref rows, then [B*A] aug rows
+  ref_prepare_kernel<<<B, 64, 0, st>>>(ref.det, dc, e->d_lut, rs);
+  class_max_kernel<<<B, 128, ncls1 * 4, st>>>(ref.det, dc, ncls1, e->d_lut, 1, d_cls);
+  e->launches += 2;
+  CutRects* d_cuts = (CutRects*)ar.alloc((size_t)B * sizeof(CutRects));
+  CALD_CUDA_CHECK(cudaMemsetAsync(d_cuts, 0, (size_t)B * sizeof(CutRects), st));
+  std::vector<int> img_hw(B * 2);
+  for (int b = 0; b < B; ++b) { img_hw[b * 2] = hs[b]; img_hw[b * 2 + 1] = ws[b]; }
+  int* d_img_hw = (int*)ar.alloc(B * 8);
+  CALD_CUDA_CHECK(cudaMemcpyAsync(d_img_hw, img_hw.data(), B * 8, cudaMemcpyHostToDevice, st));
+  bool has_cut = false;
+  for (int a : augs) has_cut |= (a == CALD_AUG_CUTOUT);
+  if (has_cut) {
+    cutout_kernel<<<1, 64, 0, st>>>(rs, d_img_hw, B, 2, d_u, n_u, d_cuts, d_cursor);
+    KLAUNCH(e);
+  }
+  // ---------------- augmented views
+  std::vector<HostView> av((size_t)B * A);
+  std::vector<AugGeom> geom((size_t)B * A);
+  std::vector<uint8_t*> temps;
+  for (int b = 0; b < B; ++b) {
+    for (int a = 0; a < A; ++a) {
+      AugGeom& g = geom[(size_t)b * A + a];
+      memset(&g, 0, sizeof(g));
+      g.w = (float)ws[b]; g.h = (float)hs[b];
+      HostView hv{d_images[b], hs[b], ws[b], 0, -1};
+      switch (augs[a]) {
+        case CALD_AUG_FLIP: g.kind = AUG_FLIP; hv.flip = 1; break;
+        case CALD_AUG_CUTOUT: g.kind = AUG_CUTOUT; hv.cut_slot = b; break;
+        case CALD_AUG_SMALLER_RESIZE: {
+          g.kind = AUG_RESIZE;
+          g.ratio = 0.8f;
+          int ow = (int)(ws[b] * 0.8), oh = (int)(hs[b] * 0.8);
+          uint8_t* t = pil_resize_device(e, d_images[b], hs[b], ws[b], oh, ow, 0);
+          temps.push_back(t);
+          hv.src = t; hv.sh = oh; hv.sw = ow;
+          break;
+        }
+        case CALD_AUG_ROTATION: {
+          g.kind = AUG_ROTATE;
+          RotateGeom rg = pil_rotate_geom(ws[b], hs[b], 5.0);
+          uint8_t* r = (uint8_t*)ar.alloc((size_t)rg.nh * rg.nw * 3);
+          pil_rotate_nearest_kernel<<<dim3((rg.nw + 127) / 128, rg.nh), 128, 0, st>>>(d_images[b], r, ws[b], hs[b], rg);
+          KLAUNCH(e);
+          uint8_t* t = pil_resize_device(e, r, rg.nh, rg.nw, hs[b], ws[b], 1);
+          ar.free(r);
+          temps.push_back(t);
+          hv.src = t;
+          rotate_box_geom(ws[b], hs[b], 5.0, rg.nw, rg.nh, g);
+          break;
+        }
+        default: throw std::runtime_error("unsupported augmentation kind");
+      }
+      av[(size_t)b * A + a] = hv;
+    }
+  }
+  ViewSet aug;
+  float* d_cons = nullptr;
+  if (A > 0) {
+    AugGeom* d_geom = (AugGeom*)ar.alloc(geom.size() * sizeof(AugGeom));
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d_geom, geom.data(), geom.size() * sizeof(AugGeom), cudaMemcpyHostToDevice, st));
+    float4* d_augb = (float4*)ar.alloc((size_t)B * A * REF_CAP * 16);
+    aug_boxes_kernel<<<B * A, 64, 0, st>>>(rs, d_geom, A, d_augb);
+    KLAUNCH(e);
+    aug = alloc_viewset(e, B * A);
+    detect_views(e, av, d_cuts, aug);
+    class_max_kernel<<<B * A, 128, ncls1 * 4, st>>>(aug.det, dc, ncls1, e->d_lut, 0, d_cls + (size_t)B * ncls1);
+    d_cons = (float*)ar.alloc((size_t)B * A * 4);
+    ConsArgs ca;
+    ca.ref = rs; ca.aug_boxes = d_augb; ca.det = aug.det; ca.det_cap = dc;
+    ca.ref_scores = ref.scores; ca.aug_scores = aug.scores; ca.cap = e->cap; ca.C = C; ca.A = A;
+    ca.bp = (float)bp; ca.out = d_cons;
+    consistency_kernel<<<dim3(A, B), 32 * CONS_WARPS, 0, st>>>(ca);
+    CALD_CUDA_CHECK(cudaGetLastError());
+    e->launches += 2;
+    ar.free(d_geom);
+    ar.free(d_augb);
+  }
+  // ---------------- results to host; final means in double as numpy does (cald_train.py:225-228)
+  std::vector<float> h_cons((size_t)B * std::max(A, 1)), h_cls((size_t)B * (1 + A) * ncls1);
+  std::vector<int> h_ndet(B);
+  if (A > 0) CALD_CUDA_CHECK(cudaMemcpyAsync(h_cons.data(), d_cons, (size_t)B * A * 4, cudaMemcpyDeviceToHost, st));
+  CALD_CUDA_CHECK(cudaMemcpyAsync(h_cls.data(), d_cls, h_cls.size() * 4, cudaMemcpyDeviceToHost, st));
+  CALD_CUDA_CHECK(cudaMemcpyAsync(h_ndet.data(), rs.n_det, B * 4, cudaMemcpyDeviceToHost, st));
+  CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b) {
+    double* cls = out_cls + (size_t)b * ncls1;
+    if (h_ndet[b] == 0 || A == 0) {
+      // empty reference prediction: consistency 0.0, class vector = the (all-zero) reference row (cald_train.py:118-121)
+      out_cons[b] = 0.0;
+      for (int c = 0; c < ncls1; ++c) cls[c] = (double)h_cls[(size_t)b * ncls1 + c];
+      for (int a = 0; a < A; ++a) e->last_per_view.push_back(0.f);
+      continue;
+    }
+    double s = 0.0;
+    for (int a = 0; a < A; ++a) { s += (double)h_cons[(size_t)b * A + a]; e->last_per_view.push_back(h_cons[(size_t)b * A + a]); }
+    out_cons[b] = s / A;
+    for (int c = 0; c < ncls1; ++c) {
+      double t = (double)h_cls[(size_t)b * ncls1 + c];
+      for (int a = 0; a < A; ++a) t += (double)h_cls[((size_t)B + (size_t)b * A + a) * ncls1 + c];
+      cls[c] = t / (1 + A);
+    }
+  }
+  if (A > 0) { free_viewset(e, aug); ar.free(d_cons); }
+  for (uint8_t* t : temps) ar.free(t);
+  ar.free(d_img_hw); ar.free(d_cuts); ar.free(d_cls);
+  ar.free(rs.n); ar.free(rs.n_det); ar.free(rs.boxes); ar.free(rs.prob_max); ar.free(rs.prop_idx);
+  free_viewset(e, ref);
+}
+
+// upload host images into one device slab; returns device pointers
+struct DeviceImages {
+  uint8_t* slab = nullptr;
+  std::vector<const uint8_t*> ptr;
+};
+DeviceImages upload_images(cald_engine* e, int n, const uint8_t* const* images, const int* hs, const int* ws) {
+  DeviceImages d;
+  size_t total = 0;
+  std::vector<size_t> off(n);
+  for (int i = 0; i < n; ++i) { off[i] = total; total += ((size_t)hs[i] * ws[i] * 3 + 255) & ~(size_t)255; }
+  d.slab = (uint8_t*)e->arena.alloc(total);
+  d.ptr.resize(n);
+  for (int i = 0; i < n; ++i) {
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d.slab + off[i], images[i], (size_t)hs[i] * ws[i] * 3, cudaMemcpyHostToDevice, e->st));
+    d.ptr[i] = d.slab + off[i];
+  }
+  return d;
+}
+
+void check_ready(cald_engine* e) {
+  if (!e->weights_ready) throw std::runtime_error("cald_load_weights has not been called");
+  CALD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+}
+
+}  // namespace
+
+#define API_TRY(e) try {
+#define API_CATCH(e)                                  \
+  }                                                   \
+  catch (const std::exception& ex) {                  \
+    (e)->err = ex.what();                             \
+    cudaGetLastError();                               \
+    return -1;                                        \
+  }                                                   \
+  return 0;
+
+extern "C" {
+
+int cald_config_default(cald_config* cfg, int arch, int depth, int num_classes, int min_size, int max_size) {
+  if (!cfg) return -1;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->arch = arch; cfg->depth = depth; cfg->num_classes = num_classes;
+  cfg->min_size = min_size; cfg->max_size = max_size;
+  cfg->rpn_pre_nms_top_n = 1000; cfg->rpn_post_nms_top_n = 1000; cfg->rpn_nms_thresh = 0.7f;
+  cfg->box_score_thresh = 0.05f; cfg->box_nms_thresh = 0.5f; cfg->box_detections_per_img = 100;
+  cfg->device = 0; cfg->precision = CALD_PREC_BF16X3; cfg->conv_impl = CALD_CONV_TCGEN05;
+  cfg->max_views_per_pass = 0; cfg->workspace_bytes = 0; cfg->debug = 0;
+  return 0;
+}
+
+const char* cald_last_error(const cald_engine* e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+int cald_create(const cald_config* cfg, cald_engine** out) {
+  if (!cfg || !out) return -1;
+  cald_engine* e = nullptr;
+  try {
+    if (cfg->arch != CALD_ARCH_FRCNN) throw std::runtime_error("only CALD_ARCH_FRCNN is implemented in this build");
+    if (cfg->depth != 50 && cfg->depth != 101) throw std::runtime_error("depth must be 50 or 101");
+    if (cfg->box_detections_per_img > 128 || cfg->rpn_post_nms_top_n > 1000 || cfg->rpn_pre_nms_top_n > 1000)
+      throw std::runtime_error("capacity limits: detections <= 128, rpn top-n <= 1000");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+      throw std::runtime_error("no CUDA device: the CALD B200 engine has no CPU fallback");
+    CALD_CUDA_CHECK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CALD_CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) throw std::runtime_error("this library contains sm_100a code only (Blackwell B200 required)");
+    e = new cald_engine();
+    e->cfg = *cfg;
+    e->split = cfg->precision == CALD_PREC_BF16X3;
+    e->C = cfg->num_classes;
+    e->cap = 1000;
+    e->det_cap = cfg->box_detections_per_img;
+    CALD_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    e->conv.num_sms = prop.multiProcessorCount;
+    e->conv.impl = cfg->conv_impl == CALD_CONV_SIMT ? CONV_SIMT : CONV_TC;
+    e->conv.split = e->split;
+    size_t ws = cfg->workspace_bytes;
+    if (!ws) {
+      size_t fr = 0, tot = 0;
+      CALD_CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
+      ws = std::min<size_t>(fr / 2, (size_t)64 << 30);
+    }
+    e->arena.init(ws);
+    CALD_CUDA_CHECK(cudaFuncSetAttribute(nms_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM));
+    CALD_CUDA_CHECK(cudaFuncSetAttribute(det_class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         NMS_SMEM + TOPK_MAX * 12));
+    CALD_CUDA_CHECK(cudaFuncSetAttribute(rpn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_CAP * 8));
+    // sub-sampling LUT: np.round(np.linspace(0, n-1, 50)).astype(int) (cald_train.py:110-111)
+    std::vector<int> lut((size_t)(e->det_cap + 1) * 50, 0);
+    for (int n = 41; n <= e->det_cap; ++n) {
+      double step = (double)(n - 1) / 49.0;
+      for (int i = 0; i < 50; ++i) {
+        double y = (i == 49) ? (double)(n - 1) : (double)i * step;
+        lut[(size_t)n * 50 + i] = (int)nearbyint(y);
+      }
+    }
+    CALD_CUDA_CHECK(cudaMalloc((void**)&e->d_lut, lut.size() * 4));
+    CALD_CUDA_CHECK(cudaMemcpy(e->d_lut, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice));
+    *out = e;
+    return 0;
+  } catch (const std::exception& ex) {
+    g_create_err = ex.what();
+    delete e;
+    return -1;
+  }
+}
+
+void cald_destroy(cald_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  delete e;
+}
+
+int cald_load_weights(cald_engine* e, int n, const char* const* names, const float* const* data, const int* ndim,
+                      const int64_t* shapes) {
+  API_TRY(e)
+  CALD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  for (int i = 0; i < n; ++i) {
+    HostTensor t;
+    size_t cnt = 1;
+    for (int d = 0; d < ndim[i]; ++d) { t.shape.push_back(shapes[i * 4 + d]); cnt *= (size_t)shapes[i * 4 + d]; }
+    t.v.assign(data[i], data[i] + cnt);
+    e->staged[canonical_key(names[i])] = std::move(t);
+  }
+  finalize_weights(e);
+  API_CATCH(e)
+}
+
+static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, bool on_device, const int* heights,
+                      const int* widths, int n_augs, const int* aug_kinds, double bp, const double* rng_uniforms,
+                      int n_uniforms, int* uniforms_consumed, double* out_consistency, double* out_cls) {
+  API_TRY(e)
+  check_ready(e);
+  e->arena.reset();
+  e->last_per_view.clear();
+  e->last_A = n_augs;
+  std::vector<int> augs(aug_kinds, aug_kinds + n_augs);
+  double* d_u = nullptr;
+  int* d_cursor = (int*)e->arena.alloc(4);
+  CALD_CUDA_CHECK(cudaMemsetAsync(d_cursor, 0, 4, e->st));
+  if (n_uniforms > 0 && rng_uniforms) {
+    d_u = (double*)e->arena.alloc((size_t)n_uniforms * 8);
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d_u, rng_uniforms, (size_t)n_uniforms * 8, cudaMemcpyHostToDevice, e->st));
+  } else {
+    n_uniforms = 0;
+  }
+  const int maxv = e->cfg.max_views_per_pass > 0 ? e->cfg.max_views_per_pass : 8;
+  const int Bmax = std::max(1, maxv / std::max(1, n_augs));
+  for (int pos = 0; pos < n_images; pos += Bmax) {
+    const int B = std::min(Bmax, n_images - pos);
+    DeviceImages di;
+    const uint8_t* const* dptr;
+    if (on_device) {
+      dptr = imgs + pos;
+    } else {
+      di = upload_images(e, B, imgs + pos, heights + pos, widths + pos);
+      dptr = di.ptr.data();
+    }
+    score_chunk(e, B, dptr, heights + pos, widths + pos, augs, bp, d_u, n_uniforms, d_cursor,
+                out_consistency + pos, out_cls + (size_t)pos * (e->C - 1));
+    if (di.slab) e->arena.free(di.slab);
+  }
+  int consumed = 0;
+  CALD_CUDA_CHECK(cudaMemcpyAsync(&consumed, d_cursor, 4, cudaMemcpyDeviceToHost, e->st));
+  CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  if (uniforms_consumed) *uniforms_consumed = consumed;
+  API_CATCH(e)
+}
+
+int cald_score(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
+               int n_augs, const int* aug_kinds, double bp, const double* rng_uniforms, int n_uniforms,
+               int* uniforms_consumed, double* out_consistency, double* out_cls) {
+  return score_impl(e, n_images, images, false, heights, widths, n_augs, aug_kinds, bp, rng_uniforms, n_uniforms,
+                    uniforms_consumed, out_consistency, out_cls);
+}
+int cald_score_device(cald_engine* e, int n_images, const uint8_t* const* d_images, const int* heights,
+                      const int* widths, int n_augs, const int* aug_kinds, double bp, const double* rng_uniforms,
+                      int n_uniforms, int* uniforms_consumed, double* out_consistency, double* out_cls) {
+  return score_impl(e, n_images, d_images, true, heights, widths, n_augs, aug_kinds, bp, rng_uniforms, n_uniforms,
+                    uniforms_consumed, out_consistency, out_cls);
+}
+
+int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
+                int* counts, float* boxes, float* scores, int64_t* labels, float* props, float* prob_max,
+                float* scores_cls) {
+  API_TRY(e)
+  check_ready(e);
+  e->arena.reset();
+  const int dc = e->det_cap, C = e->C;
+  const int maxv = e->cfg.max_views_per_pass > 0 ? e->cfg.max_views_per_pass : 8;
+  for (int pos = 0; pos < n_images; pos += maxv) {
+    const int B = std::min(maxv, n_images - pos);
+    DeviceImages di = upload_images(e, B, images + pos, heights + pos, widths + pos);
+    std::vector<HostView> hv(B);
+    for (int b = 0; b < B; ++b) hv[b] = HostView{di.ptr[b], heights[pos + b], widths[pos + b], 0, -1};
+    ViewSet vs = alloc_viewset(e, B);
+    detect_views(e, hv, nullptr, vs);
+    std::vector<int> h_count(B), h_labels((size_t)B * dc), h_pidx((size_t)B * dc);
+    std::vector<float> h_scores_all;
+    cudaStream_t st = e->st;
+    CALD_CUDA_CHECK(cudaMemcpyAsync(h_count.data(), vs.det.count, B * 4, cudaMemcpyDeviceToHost, st));
+    CALD_CUDA_CHECK(cudaMemcpyAsync(h_labels.data(), vs.det.labels, (size_t)B * dc * 4, cudaMemcpyDeviceToHost, st));
+    CALD_CUDA_CHECK(cudaMemcpyAsync(h_pidx.data(), vs.det.prop_idx, (size_t)B * dc * 4, cudaMemcpyDeviceToHost, st));
+    if (boxes) CALD_CUDA_CHECK(cudaMemcpyAsync(boxes + (size_t)pos * dc * 4, vs.det.boxes, (size_t)B * dc * 16, cudaMemcpyDeviceToHost, st));
+    if (props) CALD_CUDA_CHECK(cudaMemcpyAsync(props + (size_t)pos * dc * 4, vs.det.props, (size_t)B * dc * 16, cudaMemcpyDeviceToHost, st));
+    if (scores) CALD_CUDA_CHECK(cudaMemcpyAsync(scores + (size_t)pos * dc, vs.det.scores, (size_t)B * dc * 4, cudaMemcpyDeviceToHost, st));
+    if (prob_max) CALD_CUDA_CHECK(cudaMemcpyAsync(prob_max + (size_t)pos * dc, vs.det.prob_max, (size_t)B * dc * 4, cudaMemcpyDeviceToHost, st));
+    if (scores_cls) {
+      h_scores_all.resize((size_t)B * e->cap * C);
+      CALD_CUDA_CHECK(cudaMemcpyAsync(h_scores_all.data(), vs.scores, h_scores_all.size() * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int b = 0; b < B; ++b) {
+      if (counts) counts[pos + b] = h_count[b];
+      for (int i = 0; i < dc; ++i) {
+        if (labels) labels[(size_t)(pos + b) * dc + i] = h_labels[(size_t)b * dc + i];
+        if (scores_cls) {
+          float* dst = scores_cls + ((size_t)(pos + b) * dc + i) * C;
+          if (i < h_count[b]) memcpy(dst, &h_scores_all[((size_t)b * e->cap + h_pidx[(size_t)b * dc + i]) * C], (size_t)C * 4);
+          else memset(dst, 0, (size_t)C * 4);
+        }
+      }
+    }
+    free_viewset(e, vs);
+    e->arena.free(di.slab);
+  }
+  API_CATCH(e)
+}
+
+int cald_last_per_view(cald_engine* e, float* out, int capacity) {
+  if (!e || !out) return -1;
+  int n = (int)e->last_per_view.size();
+  if (n > capacity) n = capacity;
+  memcpy(out, e->last_per_view.data(), (size_t)n * 4);
+  return n;
+}
+
+long long cald_debug_fetch(cald_engine* e, const char* name, float* buf, long long capacity) {
+  if (!e) return -1;
+  auto it = e->dbg.find(name);
+  if (it == e->dbg.end()) { e->err = std::string("no debug tensor named ") + name; return -1; }
+  long long n = (long long)it->second.size();
+  if (buf) memcpy(buf, it->second.data(), (size_t)std::min(n, capacity) * 4);
+  return n;
+}
+
+int cald_counters(cald_engine* e, long long* kernel_launches, double* conv_flops) {
+  if (!e) return -1;
+  if (kernel_launches) *kernel_launches = e->launches;
+  if (conv_flops) *conv_flops = e->conv.flops;
+  return 0;
+}
+
+}  // extern "C"

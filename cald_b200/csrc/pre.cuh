@@ -1,0 +1,212 @@
+// Image-side kernels (HBM-bound byte/float work):
+//   * view_preprocess_kernel: u8 HWC source -> [flip] -> [cutout] -> /255 -> normalise -> bilinear resize
+//     (ATen upsample_bilinear2d, align_corners=False) -> zero-pad to /32, fp32 NHWC3.  One fused pass.
+//     Reference: torchvision F.to_tensor (cald_train.py:107), cald/cald_helper.py:23-30 (flip), 88-132
+//     (cutout fill), tv:models/detection/transform.py:119-255.
+//   * Pillow-exact u8 resampling (libImaging/Resample.c two-pass fixed point) and nearest affine rotate
+//     (libImaging/Geometry.c affine_fixed) for cald_helper.resize / rotate (cald_helper.py:47-53,135-223).
+#pragma once
+#include <cmath>
+#include <vector>
+#include "common.cuh"
+
+namespace cald {
+
+constexpr int MAX_CUT = 4;
+
+struct ViewDesc {
+  const uint8_t* src;   // u8 [sh][sw][3]
+  int sh, sw;           // source size
+  int rh, rw;           // size after the detector's resize
+  int flip;             // horizontal flip of the source
+  int n_cut_slot;       // index into the device cutout-rect table, or -1
+};
+
+struct CutRects {       // per image
+  int n;
+  int rect[MAX_CUT][4]; // l, t, r, b (half-open), in source pixels
+};
+
+__device__ __forceinline__ float src_pixel(const ViewDesc& d, const CutRects* cut, int c, int y, int x,
+                                           float mean, float stdv) {
+  // pixel of the augmented [0,1] image, then (x - mean) / std
+  float v;
+  bool zero = false;
+  if (cut) {
+    for (int k = 0; k < cut->n; ++k)
+      zero |= (x >= cut->rect[k][0] && x < cut->rect[k][2] && y >= cut->rect[k][1] && y < cut->rect[k][3]);
+  }
+  int sx = d.flip ? (d.sw - 1 - x) : x;
+  v = zero ? 0.f : ((float)d.src[((long long)y * d.sw + sx) * 3 + c] / 255.f);
+  return (v - mean) / stdv;
+}
+
+// grid: (ceil(Wp/64), Hp, V), block 64*3? -> one thread per (x, c) pair, 192 threads.
+__global__ void view_preprocess_kernel(const ViewDesc* __restrict__ views, const CutRects* __restrict__ cuts,
+                                       int Hp, int Wp, float* __restrict__ out /*[V][Hp][Wp][3]*/) {
+  const int v = blockIdx.z, oy = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ox = t / 3, c = t % 3;
+  if (ox >= Wp) return;
+  const ViewDesc d = views[v];
+  const CutRects* cut = d.n_cut_slot >= 0 ? &cuts[d.n_cut_slot] : nullptr;
+  const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+  const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+  float val = 0.f;
+  if (oy < d.rh && ox < d.rw) {
+    // ATen area_pixel_compute_source_index, scale = in / out in float (recompute_scale_factor=True)
+    const float sh = (float)d.sh / (float)d.rh, sw = (float)d.sw / (float)d.rw;
+    float fy = sh * ((float)oy + 0.5f) - 0.5f;
+    if (fy < 0.f) fy = 0.f;
+    float fx = sw * ((float)ox + 0.5f) - 0.5f;
+    if (fx < 0.f) fx = 0.f;
+    int y0 = (int)fy, x0 = (int)fx;
+    int y1 = y0 + ((y0 < d.sh - 1) ? 1 : 0), x1 = x0 + ((x0 < d.sw - 1) ? 1 : 0);
+    float ly = fy - (float)y0, lx = fx - (float)x0;
+    float hy = 1.f - ly, hx = 1.f - lx;
+    float p00 = src_pixel(d, cut, c, y0, x0, mean, stdv), p01 = src_pixel(d, cut, c, y0, x1, mean, stdv);
+    float p10 = src_pixel(d, cut, c, y1, x0, mean, stdv), p11 = src_pixel(d, cut, c, y1, x1, mean, stdv);
+    val = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
+  }
+  out[(((long long)v * Hp + oy) * Wp + ox) * 3 + c] = val;
+}
+
+// ---------------------------------------------------------------- Pillow-exact resampling
+constexpr int PIL_PRECISION_BITS = 32 - 8 - 2;
+
+struct PilCoeffs {          // host-built (double arithmetic as in Resample.c), uploaded once per (in,out,filter)
+  int in_size, out_size, ksize;
+  std::vector<int> bounds;  // [out][2] xmin, xcnt
+  std::vector<int> kk;      // [out][ksize]
+};
+
+inline double pil_bilinear(double x) { if (x < 0.0) x = -x; return x < 1.0 ? 1.0 - x : 0.0; }
+inline double pil_bicubic(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+// filter: 0 bilinear (support 1), 1 bicubic (support 2)
+inline PilCoeffs pil_precompute(int in_size, int out_size, int filter) {
+  PilCoeffs pc;
+  pc.in_size = in_size; pc.out_size = out_size;
+  double support = filter == 0 ? 1.0 : 2.0;
+  double scale = (double)in_size / out_size;
+  double filterscale = scale < 1.0 ? 1.0 : scale;
+  support = support * filterscale;
+  int ksize = (int)ceil(support) * 2 + 1;
+  pc.ksize = ksize;
+  pc.bounds.assign((size_t)out_size * 2, 0);
+  pc.kk.assign((size_t)out_size * ksize, 0);
+  std::vector<double> k(ksize);
+  double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    double center = (xx + 0.5) * scale;
+    double ww = 0.0;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    for (int x = 0; x < xmax; ++x) {
+      double w = (filter == 0 ? pil_bilinear : pil_bicubic)((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x) if (ww != 0.0) k[x] /= ww;
+    for (int x = 0; x < xmax; ++x) {
+      double s = k[x] * (1 << PIL_PRECISION_BITS);
+      pc.kk[(size_t)xx * ksize + x] = (int)(k[x] < 0 ? -0.5 + s : 0.5 + s);
+    }
+    pc.bounds[xx * 2] = xmin;
+    pc.bounds[xx * 2 + 1] = xmax;
+  }
+  return pc;
+}
+
+__device__ __forceinline__ uint8_t pil_clip8(int v) {
+  v >>= PIL_PRECISION_BITS;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+// horizontal pass: in [h][iw][3] -> out [h][ow][3]
+__global__ void pil_resample_h_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int h, int iw, int ow,
+                                      const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (t >= ow * 3) return;
+  int xx = t / 3, c = t % 3;
+  int xmin = bounds[xx * 2], n = bounds[xx * 2 + 1];
+  int acc = 1 << (PIL_PRECISION_BITS - 1);
+  const uint8_t* row = in + (long long)y * iw * 3;
+  for (int x = 0; x < n; ++x) acc += (int)row[(xmin + x) * 3 + c] * kk[xx * ksize + x];
+  out[((long long)y * ow + xx) * 3 + c] = pil_clip8(acc);
+}
+// vertical pass: in [ih][w][3] -> out [oh][w][3]
+__global__ void pil_resample_v_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int ih, int oh, int w,
+                                      const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int yy = blockIdx.y;
+  if (t >= w * 3) return;
+  int ymin = bounds[yy * 2], n = bounds[yy * 2 + 1];
+  int acc = 1 << (PIL_PRECISION_BITS - 1);
+  for (int y = 0; y < n; ++y) acc += (int)in[(long long)(ymin + y) * w * 3 + t] * kk[yy * ksize + y];
+  out[(long long)yy * w * 3 + t] = pil_clip8(acc);
+}
+
+// PIL Image.rotate(angle, expand=True) geometry (PIL/Image.py) + Geometry.c affine_fixed coefficients
+struct RotateGeom { int nw, nh; int a0, a1, a2, a3, a4, a5; };
+inline double py_round15(double v) { return std::round(v * 1e15) / 1e15; }
+inline RotateGeom pil_rotate_geom(int w, int h, double angle_deg) {
+  // note: python's round(x, 15) is correctly-rounded decimal; for cos/sin of 5 degrees the value
+  // has no representable neighbour within 1e-15 that changes the 16.16 fixed-point result.
+  const double PI = 3.14159265358979323846;
+  double ang = -(angle_deg * PI / 180.0);
+  double m[6] = {py_round15(cos(ang)), py_round15(sin(ang)), 0.0, py_round15(-sin(ang)), py_round15(cos(ang)), 0.0};
+  double cx = w / 2.0, cy = h / 2.0;
+  auto tf = [&](double x, double y, double& ox, double& oy) {
+    ox = m[0] * x + m[1] * y + m[2];
+    oy = m[3] * x + m[4] * y + m[5];
+  };
+  double t2, t5;
+  tf(-cx, -cy, t2, t5);
+  m[2] = t2 + cx;
+  m[5] = t5 + cy;
+  double xs[4], ys[4];
+  double px[4] = {0, (double)w, (double)w, 0}, py[4] = {0, 0, (double)h, (double)h};
+  for (int i = 0; i < 4; ++i) tf(px[i], py[i], xs[i], ys[i]);
+  double xmin = xs[0], xmax = xs[0], ymin = ys[0], ymax = ys[0];
+  for (int i = 1; i < 4; ++i) {
+    xmin = std::min(xmin, xs[i]); xmax = std::max(xmax, xs[i]);
+    ymin = std::min(ymin, ys[i]); ymax = std::max(ymax, ys[i]);
+  }
+  RotateGeom g;
+  g.nw = (int)(ceil(xmax) - floor(xmin));
+  g.nh = (int)(ceil(ymax) - floor(ymin));
+  tf(-(g.nw - w) / 2.0, -(g.nh - h) / 2.0, t2, t5);
+  m[2] = t2;
+  m[5] = t5;
+  auto fix = [](double v) { return (int)floor(v * 65536.0 + 0.5); };
+  g.a0 = fix(m[0]); g.a1 = fix(m[1]); g.a3 = fix(m[3]); g.a4 = fix(m[4]);
+  g.a2 = fix(m[2] + m[0] * 0.5 + m[1] * 0.5);
+  g.a5 = fix(m[5] + m[3] * 0.5 + m[4] * 0.5);
+  return g;
+}
+__global__ void pil_rotate_nearest_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int w, int h,
+                                          RotateGeom g) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= g.nw) return;
+  long long xx = (long long)g.a2 + (long long)g.a1 * y + (long long)g.a0 * x;
+  long long yy = (long long)g.a5 + (long long)g.a4 * y + (long long)g.a3 * x;
+  int xin = (int)(xx >> 16), yin = (int)(yy >> 16);
+  uint8_t r = 0, gg = 0, b = 0;
+  if (xin >= 0 && xin < w && yin >= 0 && yin < h) {
+    const uint8_t* p = in + ((long long)yin * w + xin) * 3;
+    r = p[0]; gg = p[1]; b = p[2];
+  }
+  uint8_t* o = out + ((long long)y * g.nw + x) * 3;
+  o[0] = r; o[1] = gg; o[2] = b;
+}
+
+}  // namespace cald

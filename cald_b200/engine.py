@@ -1,0 +1,193 @@
+"""ctypes binding of the public C ABI (include/cald_b200.h) -- one Engine per GPU."""
+import ctypes
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_size_t, c_uint8, c_void_p
+
+import numpy as np
+
+from . import arch
+from ._lib import CaldError, lib
+
+ARCH_FRCNN, ARCH_RETINANET = 0, 1
+PREC_BF16X3, PREC_BF16 = 0, 1
+CONV_TCGEN05, CONV_SIMT = 0, 1
+AUG_FLIP, AUG_CUTOUT, AUG_SMALLER_RESIZE, AUG_ROTATION = 0, 1, 2, 3
+
+# reference augmentation names (cald_train.py:93-94) -> engine kinds, in the order get_uncertainty appends them
+AUG_ORDER = (("flip", AUG_FLIP), ("cut_out", AUG_CUTOUT), ("smaller_resize", AUG_SMALLER_RESIZE),
+             ("rotation", AUG_ROTATION))
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("arch", c_int), ("depth", c_int), ("num_classes", c_int), ("min_size", c_int),
+                ("max_size", c_int), ("rpn_pre_nms_top_n", c_int), ("rpn_post_nms_top_n", c_int),
+                ("rpn_nms_thresh", c_float), ("box_score_thresh", c_float), ("box_nms_thresh", c_float),
+                ("box_detections_per_img", c_int), ("device", c_int), ("precision", c_int),
+                ("conv_impl", c_int), ("max_views_per_pass", c_int), ("workspace_bytes", c_size_t),
+                ("debug", c_int)]
+
+
+def _u8_list(images):
+    imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+    for im in imgs:
+        if im.ndim != 3 or im.shape[2] != 3:
+            raise ValueError("images must be HxWx3 uint8 (RGB)")
+    n = len(imgs)
+    ptrs = (POINTER(c_uint8) * n)(*[im.ctypes.data_as(POINTER(c_uint8)) for im in imgs])
+    hs = (c_int * n)(*[im.shape[0] for im in imgs])
+    ws = (c_int * n)(*[im.shape[1] for im in imgs])
+    return imgs, ptrs, hs, ws
+
+
+class Engine:
+    """The scoring engine for one detector on one GPU."""
+
+    def __init__(self, depth=50, num_classes=21, min_size=600, max_size=1000, device=0, precision=PREC_BF16X3,
+                 conv_impl=CONV_TCGEN05, max_views_per_pass=0, workspace_bytes=0, debug=False,
+                 arch_id=ARCH_FRCNN, **overrides):
+        L = lib()
+        L.cald_create.argtypes = [POINTER(Config), POINTER(c_void_p)]
+        L.cald_last_error.restype = c_char_p
+        L.cald_last_error.argtypes = [c_void_p]
+        L.cald_destroy.argtypes = [c_void_p]
+        cfg = Config()
+        L.cald_config_default(ctypes.byref(cfg), arch_id, depth, num_classes, min_size, max_size)
+        cfg.device, cfg.precision, cfg.conv_impl = device, precision, conv_impl
+        cfg.max_views_per_pass, cfg.workspace_bytes, cfg.debug = max_views_per_pass, workspace_bytes, int(debug)
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.num_classes = num_classes
+        self.depth = depth
+        self._h = c_void_p()
+        self._L = L
+        if L.cald_create(ctypes.byref(cfg), ctypes.byref(self._h)) != 0:
+            raise CaldError(L.cald_last_error(None).decode())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CaldError(self._L.cald_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cald_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict):
+        """state_dict: torchvision-keyed mapping name -> tensor / ndarray (checkpoint['model'])."""
+        names, arrays = [], []
+        for k, v in state_dict.items():
+            if hasattr(v, "detach"):
+                v = v.detach().cpu().numpy()
+            a = np.ascontiguousarray(v, dtype=np.float32)
+            if a.ndim > 4:
+                raise ValueError("tensor %s has rank %d" % (k, a.ndim))
+            names.append(arch.canonical_key(k).encode())
+            arrays.append(a)
+        n = len(names)
+        c_names = (c_char_p * n)(*names)
+        c_data = (POINTER(c_float) * n)(*[a.ctypes.data_as(POINTER(c_float)) for a in arrays])
+        c_ndim = (c_int * n)(*[a.ndim for a in arrays])
+        shp = np.ones((n, 4), dtype=np.int64)
+        for i, a in enumerate(arrays):
+            shp[i, :a.ndim] = a.shape
+        self._L.cald_load_weights.argtypes = [c_void_p, c_int, POINTER(c_char_p), POINTER(POINTER(c_float)),
+                                              POINTER(c_int), POINTER(c_int64)]
+        self._check(self._L.cald_load_weights(self._h, n, c_names, c_data, c_ndim,
+                                              shp.ctypes.data_as(POINTER(c_int64))))
+
+    # ------------------------------------------------------------------ scoring
+    def score(self, images, aug_kinds, bp=1.3, uniforms=None):
+        """-> (consistency float64[n], cls float64[n, C-1], uniforms_consumed)."""
+        imgs, ptrs, hs, ws = _u8_list(images)
+        n = len(imgs)
+        a = (c_int * len(aug_kinds))(*aug_kinds)
+        u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
+        nu = 0 if u is None else u.size
+        consumed = c_int(0)
+        cons = np.zeros(n, dtype=np.float64)
+        cls = np.zeros((n, self.num_classes - 1), dtype=np.float64)
+        self._L.cald_score.argtypes = [c_void_p, c_int, POINTER(POINTER(c_uint8)), POINTER(c_int), POINTER(c_int),
+                                       c_int, POINTER(c_int), c_double, POINTER(c_double), c_int, POINTER(c_int),
+                                       POINTER(c_double), POINTER(c_double)]
+        self._check(self._L.cald_score(self._h, n, ptrs, hs, ws, len(aug_kinds), a, float(bp),
+                                       None if u is None else u.ctypes.data_as(POINTER(c_double)), nu,
+                                       ctypes.byref(consumed), cons.ctypes.data_as(POINTER(c_double)),
+                                       cls.ctypes.data_as(POINTER(c_double))))
+        return cons, cls, consumed.value
+
+    def score_device(self, d_ptrs, hs, ws, aug_kinds, bp=1.3, uniforms=None):
+        """Like score() but images are already resident in HBM (list of device pointers)."""
+        n = len(d_ptrs)
+        ptrs = (POINTER(c_uint8) * n)(*[ctypes.cast(int(p), POINTER(c_uint8)) for p in d_ptrs])
+        chs = (c_int * n)(*hs)
+        cws = (c_int * n)(*ws)
+        a = (c_int * len(aug_kinds))(*aug_kinds)
+        u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
+        consumed = c_int(0)
+        cons = np.zeros(n, dtype=np.float64)
+        cls = np.zeros((n, self.num_classes - 1), dtype=np.float64)
+        self._L.cald_score_device.argtypes = [c_void_p, c_int, POINTER(POINTER(c_uint8)), POINTER(c_int),
+                                              POINTER(c_int), c_int, POINTER(c_int), c_double, POINTER(c_double),
+                                              c_int, POINTER(c_int), POINTER(c_double), POINTER(c_double)]
+        self._check(self._L.cald_score_device(self._h, n, ptrs, chs, cws, len(aug_kinds), a, float(bp),
+                                              None if u is None else u.ctypes.data_as(POINTER(c_double)),
+                                              0 if u is None else u.size, ctypes.byref(consumed),
+                                              cons.ctypes.data_as(POINTER(c_double)),
+                                              cls.ctypes.data_as(POINTER(c_double))))
+        return cons, cls, consumed.value
+
+    def last_per_view(self, n_images, n_augs):
+        out = np.zeros(n_images * n_augs, dtype=np.float32)
+        self._L.cald_last_per_view.argtypes = [c_void_p, POINTER(c_float), c_int]
+        k = self._L.cald_last_per_view(self._h, out.ctypes.data_as(POINTER(c_float)), out.size)
+        return out[:k].reshape(-1, n_augs) if n_augs else out[:0]
+
+    def detect(self, images):
+        """List of per-image dicts with the reference's output schema (frcnn_la.py:131-141)."""
+        imgs, ptrs, hs, ws = _u8_list(images)
+        n = len(imgs)
+        cap, C = self.cfg.box_detections_per_img, self.num_classes
+        counts = np.zeros(n, dtype=np.int32)
+        boxes = np.zeros((n, cap, 4), dtype=np.float32)
+        props = np.zeros((n, cap, 4), dtype=np.float32)
+        scores = np.zeros((n, cap), dtype=np.float32)
+        pmax = np.zeros((n, cap), dtype=np.float32)
+        labels = np.zeros((n, cap), dtype=np.int64)
+        scls = np.zeros((n, cap, C), dtype=np.float32)
+        fp = POINTER(c_float)
+        self._L.cald_detect.argtypes = [c_void_p, c_int, POINTER(POINTER(c_uint8)), POINTER(c_int), POINTER(c_int),
+                                        POINTER(c_int), fp, fp, POINTER(c_int64), fp, fp, fp]
+        self._check(self._L.cald_detect(self._h, n, ptrs, hs, ws, counts.ctypes.data_as(POINTER(c_int)),
+                                        boxes.ctypes.data_as(fp), scores.ctypes.data_as(fp),
+                                        labels.ctypes.data_as(POINTER(c_int64)), props.ctypes.data_as(fp),
+                                        pmax.ctypes.data_as(fp), scls.ctypes.data_as(fp)))
+        out = []
+        for i in range(n):
+            k = int(counts[i])
+            out.append({"boxes": boxes[i, :k], "labels": labels[i, :k], "scores": scores[i, :k],
+                        "props": props[i, :k], "prob_max": pmax[i, :k], "scores_cls": scls[i, :k]})
+        return out
+
+    def debug_fetch(self, name):
+        self._L.cald_debug_fetch.restype = c_longlong
+        self._L.cald_debug_fetch.argtypes = [c_void_p, c_char_p, POINTER(c_float), c_longlong]
+        n = self._L.cald_debug_fetch(self._h, name.encode(), None, 0)
+        if n < 0:
+            raise CaldError(self._L.cald_last_error(self._h).decode())
+        buf = np.zeros(n, dtype=np.float32)
+        self._L.cald_debug_fetch(self._h, name.encode(), buf.ctypes.data_as(POINTER(c_float)), n)
+        return buf
+
+    def counters(self):
+        k = c_longlong(0)
+        f = c_double(0)
+        self._L.cald_counters.argtypes = [c_void_p, POINTER(c_longlong), POINTER(c_double)]
+        self._L.cald_counters(self._h, ctypes.byref(k), ctypes.byref(f))
+        return k.value, f.value

@@ -1,0 +1,103 @@
+/* libcald_b200.so -- C ABI of the B200-native CALD unlabeled-pool scoring engine.
+ *
+ * The reference (we1pingyu/CALD) is pure Python and has no FFI; the boundary this
+ * library replaces is the body of
+ *     get_uncertainty(task_model, unlabeled_loader, augs, num_cls)      cald_train.py:91-231
+ * i.e. for every image: 1 reference forward of the detector (detection/frcnn_la.py:237-275),
+ * A augmented forwards (cald/cald_helper.py:23-243), and the paired-prediction reduction
+ * (cald_train.py:189-228).  The host-side mirror of the reference signature lives in
+ * cald_b200/api.py and binds these entry points with ctypes.
+ *
+ * Conventions: every call returns 0 on success and <0 on error with the
+ * message available from cald_last_error(); no exception crosses the boundary; all buffers
+ * are caller-owned HOST memory unless stated, and the engine copies what it keeps; one
+ * handle per GPU; a handle is not thread-safe, independent handles are; calls are
+ * synchronous at return.
+ */
+#ifndef CALD_B200_H
+#define CALD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cald_engine cald_engine;
+
+enum { CALD_ARCH_FRCNN = 0, CALD_ARCH_RETINANET = 1 };
+enum { CALD_PREC_BF16X3 = 0, CALD_PREC_BF16 = 1 };
+enum { CALD_CONV_TCGEN05 = 0, CALD_CONV_SIMT = 1 };
+/* augmentation kinds, in the order cald_train.py:123-183 appends them */
+enum { CALD_AUG_FLIP = 0, CALD_AUG_CUTOUT = 1, CALD_AUG_SMALLER_RESIZE = 2, CALD_AUG_ROTATION = 3 };
+
+typedef struct {
+  int arch;                  /* CALD_ARCH_*: FRCNN_Feature (frcnn_la.py:146) */
+  int depth;                 /* 50 | 101 (resnet_fpn_backbone) */
+  int num_classes;           /* incl. background: 21 VOC / 91 COCO (detection/train.py:43-46) */
+  int min_size, max_size;    /* GeneralizedRCNNTransform: 600/1000 VOC, 800/1333 COCO (cald_train.py:340-347) */
+  int rpn_pre_nms_top_n;     /* 1000 (frcnn_la.py:154) */
+  int rpn_post_nms_top_n;    /* 1000 */
+  float rpn_nms_thresh;      /* 0.7 */
+  float box_score_thresh;    /* 0.05 (frcnn_la.py:161) */
+  float box_nms_thresh;      /* 0.5 */
+  int box_detections_per_img;/* 100 */
+  int device;                /* CUDA ordinal */
+  int precision;             /* CALD_PREC_* */
+  int conv_impl;             /* CALD_CONV_* */
+  int max_views_per_pass;    /* views batched through one forward pass (0 = auto) */
+  size_t workspace_bytes;    /* device arena (0 = auto from free memory) */
+  int debug;                 /* 1: keep host copies of stage tensors for cald_debug_fetch */
+} cald_config;
+
+/* Fill cfg with the reference defaults for (arch, depth, num_classes, min_size, max_size). */
+int cald_config_default(cald_config* cfg, int arch, int depth, int num_classes, int min_size, int max_size);
+
+int cald_create(const cald_config* cfg, cald_engine** out);
+void cald_destroy(cald_engine* e);
+const char* cald_last_error(const cald_engine* e); /* e may be NULL: last create() error */
+
+/* Weights: the torchvision-keyed state_dict the reference saves / loads
+ * (cald_train.py:351-356, 420-426), fp32 host tensors.  Both the torchvision 0.8.2 and the
+ * current key spellings are accepted.  FrozenBatchNorm is folded into the preceding conv
+ * (tv:ops/misc.py:54-63, eps 1e-5).  Must be called once with ALL tensors before scoring. */
+int cald_load_weights(cald_engine* e, int n, const char* const* names, const float* const* data,
+                      const int* ndim, const int64_t* shapes /* [n][4], unused dims = 1 */);
+
+/* get_uncertainty over n images (cald_train.py:91-231).
+ * images[i]: u8 RGB, HWC contiguous, heights[i] x widths[i]  (what F.to_tensor(PIL) reads, cald_train.py:107).
+ * aug_kinds: the augmentation list in reference order; bp: args.bp (cald_train.py:220, default 1.3).
+ * rng_uniforms: raw random.random() doubles from python's generator (4 per cutout try, drawn in stream order);
+ *   uniforms_consumed returns how many the scoring consumed so the caller can advance its generator exactly as
+ *   cald_helper.cutout would have (cald_helper.py:106-114).
+ * out_consistency[n]: np.mean(consistency_aug) per image; out_cls[n][num_classes-1]: mean class-max vector. */
+int cald_score(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
+               int n_augs, const int* aug_kinds, double bp, const double* rng_uniforms, int n_uniforms,
+               int* uniforms_consumed, double* out_consistency, double* out_cls);
+
+/* One detector forward per image: task_model([F.to_tensor(img)])[0] (frcnn_la.py:131-141).
+ * Outputs are fixed-capacity [n][cap] with counts[n]; cap = box_detections_per_img.
+ * scores_cls is [n][cap][num_classes].  Any output pointer may be NULL. */
+int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
+                int* counts, float* boxes, float* scores, int64_t* labels, float* props, float* prob_max,
+                float* scores_cls);
+
+/* Per-view consistency of the last cald_score() call: out[n_images][n_augs] (cald_train.py:223). */
+int cald_last_per_view(cald_engine* e, float* out, int capacity);
+
+/* Stage tensors of the LAST forward pass (debug=1): returns element count, or <0.  With buf == NULL only the size
+ * is returned.  Names: "input", "c2".."c5", "p2".."p6", "rpn0".."rpn4", "proposals", "proposal_count", "pooled", "head". */
+long long cald_debug_fetch(cald_engine* e, const char* name, float* buf, long long capacity);
+
+/* Counters since creation: kernels launched by this engine, algorithmic conv/GEMM FLOPs (2*MAC),
+ * and device milliseconds spent inside tcgen05 conv kernels when timing is enabled. */
+int cald_counters(cald_engine* e, long long* kernel_launches, double* conv_flops);
+
+/* Same as cald_score but the u8 images already live in device memory (device pointers). */
+int cald_score_device(cald_engine* e, int n_images, const uint8_t* const* d_images, const int* heights,
+                      const int* widths, int n_augs, const int* aug_kinds, double bp, const double* rng_uniforms,
+                      int n_uniforms, int* uniforms_consumed, double* out_consistency, double* out_cls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
