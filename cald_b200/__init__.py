@@ -1,0 +1,12 @@
+"""cald_b200 -- B200-native engine for CALD's unlabeled-pool consistency scoring.
+
+Public surface (mirrors we1pingyu/CALD cald_train.py):
+    get_uncertainty(task_model, unlabeled_loader, augs, num_cls) -> (consistency_all, cls_all)
+    select(uncertainty, cls_corrs, subset, labeled_loader, budget_num, ...)
+    cls_kldiv(labeled_loader, cls_corrs, budget, cycle)
+Everything below these calls runs in hand-written sm_100a CUDA behind libcald_b200.so.
+"""
+from .api import get_uncertainty, select, cls_kldiv, score_images, engine_for  # noqa: F401
+from .engine import Engine  # noqa: F401
+
+__all__ = ["get_uncertainty", "select", "cls_kldiv", "score_images", "engine_for", "Engine"]

@@ -1,0 +1,157 @@
+"""Host-side mirror of the reference's scoring API.
+
+``get_uncertainty(task_model, unlabeled_loader, augs, num_cls)`` has the signature and the
+return value of cald_train.py:91-231 and ``select(...)`` / ``cls_kldiv(...)`` reproduce the
+selection code at cald_train.py:234-271 and 439-457, so the active-learning cycle can call
+them unchanged.  Underneath, every image is scored by the CUDA engine through the C ABI
+(include/cald_b200.h); there is no torch op and no CPU fallback on the scoring path.  torch
+is only used to read ``task_model.state_dict()`` and (multi-GPU) for the final all-gather.
+"""
+import random
+
+import numpy as np
+
+from . import engine as _eng
+
+_AUG_WHITELIST = ['flip', 'multi_ga', 'color_adjust', 'color_swap', 'multi_color_adjust', 'multi_sp', 'cut_out',
+                  'multi_cut_out', 'multi_resize', 'larger_resize', 'smaller_resize', 'rotation', 'ga', 'sp']
+_ENGINE_AUGS = dict(_eng.AUG_ORDER)
+
+# the reference reads a module-global ``args`` (cald_train.py:220, 254); mirror it as module state
+bp = 1.3
+uniform = False
+mr = 1.2
+
+_engine_cache = {}
+
+
+def _aug_kinds(augs):
+    """Reference order (cald_train.py:123-183), restricted to what the engine implements."""
+    for a in augs:
+        if a not in _AUG_WHITELIST:
+            print('{} is not in the pre-set augmentations!'.format(a))  # cald_train.py:95
+    kinds = []
+    for name, kind in _eng.AUG_ORDER:
+        if name in augs:
+            kinds.append(kind)
+    unsupported = [a for a in augs if a in _AUG_WHITELIST and a not in _ENGINE_AUGS]
+    if unsupported:
+        raise NotImplementedError("augmentations not implemented by the B200 engine yet: %s" % unsupported)
+    return kinds
+
+
+def _model_config(task_model, num_cls):
+    """Read depth / sizes from a torchvision-style detector (FRCNN_Feature, frcnn_la.py:146-235)."""
+    t = getattr(task_model, "transform", None)
+    min_size = int(t.min_size[-1]) if t is not None else 800
+    max_size = int(t.max_size) if t is not None else 1333
+    sd = task_model.state_dict()
+    depth = 101 if any(k.startswith("backbone.body.layer3.22.") for k in sd) else 50
+    return depth, min_size, max_size, sd
+
+
+def engine_for(task_model, num_cls, device=0, **kw):
+    """Build (or reuse) the engine for this model object; weights are re-read on every call of
+    get_uncertainty because the AL cycle retrains the model in between (cald_train.py:409-411)."""
+    depth, mn, mx, sd = _model_config(task_model, num_cls)
+    key = (depth, num_cls, mn, mx, device, tuple(sorted(kw.items())))
+    eng = _engine_cache.get(key)
+    if eng is None:
+        eng = _eng.Engine(depth=depth, num_classes=num_cls, min_size=mn, max_size=mx, device=device, **kw)
+        _engine_cache[key] = eng
+    eng.load_state_dict(sd)
+    return eng
+
+
+def _to_u8(image):
+    """PIL RGB image (what dataset_aug yields, cald_train.py:289) or HxWx3 u8 array -> contiguous u8."""
+    a = np.asarray(image)
+    if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError("expected an RGB PIL image / HxWx3 uint8 array")
+    return np.ascontiguousarray(a)
+
+
+def score_images(eng, images, augs, chunk=64):
+    """Score u8 images with an existing engine; consumes python's global ``random`` stream exactly as
+    cald_helper.cutout would (4 uniforms per try, data-dependent number of tries)."""
+    kinds = _aug_kinds(augs)
+    needs_rng = _eng.AUG_CUTOUT in kinds
+    cons_all, cls_all = [], []
+    for pos in range(0, len(images), chunk):
+        batch = images[pos:pos + chunk]
+        u = None
+        if needs_rng:
+            state = random.getstate()
+            u = np.array([random.random() for _ in range(200 * len(batch))], dtype=np.float64)
+        cons, cls, used = eng.score(batch, kinds, bp, u)
+        if needs_rng:
+            random.setstate(state)
+            for _ in range(used):
+                random.random()
+        cons_all.extend(float(c) for c in cons)
+        cls_all.extend(np.array(r, dtype=np.float64) for r in cls)
+    return cons_all, cls_all
+
+
+def get_uncertainty(task_model, unlabeled_loader, augs, num_cls, device=0, **engine_kw):
+    """Drop-in for cald_train.get_uncertainty (cald_train.py:91-231).
+
+    unlabeled_loader yields ``(tuple_of_PIL_images, tuple_of_targets)`` with batch size 1
+    (cald_train.py:370-371).  Returns ``(consistency_all, cls_all)``: list of float and list
+    of float64 arrays of shape (num_cls - 1,), in loader order.
+    """
+    eng = engine_for(task_model, num_cls, device, **engine_kw)
+    images = []
+    for imgs, _ in unlabeled_loader:
+        for image in imgs:
+            images.append(_to_u8(image))
+    return score_images(eng, images, augs)
+
+
+def cls_kldiv(labeled_loader, cls_corrs, budget, cycle=0):
+    """cald_train.py:234-271 (class-balance stage); host-side, O(budget * candidates * classes)."""
+    import torch
+    from torch import nn
+    cls_inds = []
+    result = []
+    for _, targets in labeled_loader:
+        for target in targets:
+            cls_corr = [0] * cls_corrs[0].shape[0]
+            for l in target['labels']:
+                cls_corr[l - 1] += 1
+            result.append(cls_corr)
+    for a in list(np.where(np.sum(cls_corrs, axis=1) == 0)[0]):
+        cls_inds.append(a)
+    while len(cls_inds) < budget:
+        kld = nn.KLDivLoss(reduction='none')
+        _cls_corrs = torch.tensor(np.array(cls_corrs))
+        _result = torch.tensor(np.mean(np.array(result), axis=0)).unsqueeze(0)
+        if uniform:
+            p = torch.nn.functional.softmax(_result + _cls_corrs, -1)
+            q = torch.nn.functional.softmax(torch.ones(_result.shape) / len(_result), -1)
+            log_mean = ((p + q) / 2).log()
+            jsdiv = torch.sum(kld(log_mean, p), dim=1) / 2 + torch.sum(kld(log_mean, q), dim=1) / 2
+            jsdiv[cls_inds] = 100
+            cls_inds.append(torch.argmin(jsdiv).item())
+        else:
+            p = torch.nn.functional.softmax(_result, -1)
+            q = torch.nn.functional.softmax(_cls_corrs, -1)
+            log_mean = ((p + q) / 2).log()
+            jsdiv = torch.sum(kld(log_mean, p), dim=1) / 2 + torch.sum(kld(log_mean, q), dim=1) / 2
+            jsdiv[cls_inds] = -1
+            cls_inds.append(torch.argmax(jsdiv).item())
+    return cls_inds
+
+
+def select(uncertainty, cls_corrs, subset, labeled_loader, budget_num, cycle=0, mutual=True):
+    """The inline selection of cald_train.py:439-448 (mutual) / 452-455 (--no-mutual).
+
+    Returns the dataset indices to move from the unlabeled to the labeled set.
+    """
+    import torch
+    arg = np.argsort(np.array(uncertainty))
+    if not mutual:
+        return list(torch.tensor(subset)[arg][:budget_num].numpy())
+    cand = arg[:int(mr * budget_num)]
+    picked = cls_kldiv(labeled_loader, [cls_corrs[i] for i in cand], budget_num, cycle)
+    return list(torch.tensor(subset)[arg][picked].numpy())

@@ -83,6 +83,7 @@ struct ConvParams {
   int ldc;             // channel stride of the output row (>= Cout)
   int res_ld;
   int out_H2, out_W2;  // OUT_PHASE: ceil(H/2), ceil(W/2)
+  int kc;              // chunked accumulation: k-blocks per TMEM accumulation chunk
 };
 
 // ATen nearest-neighbour source index (UpSampleKernel: nearest_idx), float scale.

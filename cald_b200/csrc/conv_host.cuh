@@ -89,20 +89,50 @@ struct ConvEngine {
   ConvImpl impl = CONV_TC;
   bool split = true;       // false: single-pass bf16 (hi plane only)
   int force_block_n = 0;   // 0 = auto
+  int kc = 8;              // split mode: k-blocks (of 64) per accumulation chunk; 0 = never chunk
   long long launches = 0;  // kernels launched (bench's gpu_launches)
   double flops = 0;        // algorithmic 2*MAC of the launches
+  // optional per-launch timing with CUDA events on the launching stream (bench.py roofline)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  double prof_flops = 0;
+  long long prof_launches = 0;
+  cudaEvent_t next_event() {
+    if (ev_used == ev.size()) {
+      cudaEvent_t e;
+      CALD_CUDA_CHECK(cudaEventCreate(&e));
+      ev.push_back(e);
+    }
+    return ev[ev_used++];
+  }
+  // sum of kernel durations (ms) since the last call; the stream must be idle
+  double drain_profile(double* fl, long long* n) {
+    double ms = 0;
+    for (size_t i = 0; i + 1 < ev_used; i += 2) {
+      float t = 0;
+      CALD_CUDA_CHECK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+      ms += t;
+    }
+    if (fl) *fl = prof_flops;
+    if (n) *n = prof_launches;
+    ev_used = 0; prof_flops = 0; prof_launches = 0;
+    return ms;
+  }
 
-  template <int BN, bool SP>
+  template <int BN, bool SP, bool CH>
   void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
     using Cfg = IgemmCfg<BN, SP>;
     static bool attr_set = false;
     if (!attr_set) {
-      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<BN, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<BN, SP, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
       attr_set = true;
     }
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    igemm_tc_kernel<BN, SP><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
+    igemm_tc_kernel<BN, SP, CH><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
     CALD_CUDA_CHECK(cudaGetLastError());
   }
 
@@ -182,7 +212,9 @@ struct ConvEngine {
     p.out_H2 = out.h;
     p.out_W2 = out.w;
     launches++;
-    flops += 2.0 * (double)p.n_img * p.H * p.W * (double)w.cout * w.taps * w.cin;
+    const double fl = 2.0 * (double)p.n_img * p.H * p.W * (double)w.cout * w.taps * w.cin;
+    flops += fl;
+    if (profiling && impl == CONV_TC) { prof_flops += fl; prof_launches++; }
 
     if (impl == CONV_SIMT) {
       SimtOperands so;
@@ -202,14 +234,17 @@ struct ConvEngine {
     else
       ta = make_tmap(in.hi, in.c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);
     tb = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, split ? 2 : 1, BN, 1);
+    const int num_kb = w.taps * (w.cin / 64);
+    const bool chunked = split && kc > 0 && num_kb > kc && BN <= 128;
+    p.kc = chunked ? kc : num_kb;
     if (split) {
-      if (BN == 64) launch_tc<64, true>(ta, tb, p, st);
-      else if (BN == 128) launch_tc<128, true>(ta, tb, p, st);
-      else launch_tc<256, true>(ta, tb, p, st);
+      if (BN == 64) { if (chunked) launch_tc<64, true, true>(ta, tb, p, st); else launch_tc<64, true, false>(ta, tb, p, st); }
+      else if (BN == 128) { if (chunked) launch_tc<128, true, true>(ta, tb, p, st); else launch_tc<128, true, false>(ta, tb, p, st); }
+      else launch_tc<256, true, false>(ta, tb, p, st);
     } else {
-      if (BN == 64) launch_tc<64, false>(ta, tb, p, st);
-      else if (BN == 128) launch_tc<128, false>(ta, tb, p, st);
-      else launch_tc<256, false>(ta, tb, p, st);
+      if (BN == 64) launch_tc<64, false, false>(ta, tb, p, st);
+      else if (BN == 128) launch_tc<128, false, false>(ta, tb, p, st);
+      else launch_tc<256, false, false>(ta, tb, p, st);
     }
   }
 };

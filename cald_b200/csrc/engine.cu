@@ -68,6 +68,7 @@ struct cald_engine {
   std::map<long long, int> pil_ksize;
   std::vector<float> last_per_view;
   int last_A = 0;
+  cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   ~cald_engine() {
     if (d_lut) cudaFree(d_lut);
@@ -1059,6 +1060,42 @@ long long cald_debug_fetch(cald_engine* e, const char* name, float* buf, long lo
   long long n = (long long)it->second.size();
   if (buf) memcpy(buf, it->second.data(), (size_t)std::min(n, capacity) * 4);
   return n;
+}
+
+int cald_profile(cald_engine* e, int enable) {
+  if (!e) return -1;
+  e->conv.profiling = enable != 0;
+  e->conv.ev_used = 0; e->conv.prof_flops = 0; e->conv.prof_launches = 0;
+  return 0;
+}
+
+int cald_profile_read(cald_engine* e, double* conv_ms, long long* conv_launches, double* conv_flops) {
+  API_TRY(e)
+  CALD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  double fl = 0;
+  long long n = 0;
+  double ms = e->conv.drain_profile(&fl, &n);
+  if (conv_ms) *conv_ms = ms;
+  if (conv_launches) *conv_launches = n;
+  if (conv_flops) *conv_flops = fl;
+  API_CATCH(e)
+}
+
+int cald_event_record(cald_engine* e, int slot) {
+  API_TRY(e)
+  if (slot < 0 || slot >= 8) throw std::runtime_error("event slot out of range");
+  CALD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  if (!e->user_ev[slot]) CALD_CUDA_CHECK(cudaEventCreate(&e->user_ev[slot]));
+  CALD_CUDA_CHECK(cudaEventRecord(e->user_ev[slot], e->st));
+  API_CATCH(e)
+}
+
+int cald_event_elapsed_ms(cald_engine* e, int slot_a, int slot_b, float* ms) {
+  API_TRY(e)
+  CALD_CUDA_CHECK(cudaEventSynchronize(e->user_ev[slot_b]));
+  CALD_CUDA_CHECK(cudaEventElapsedTime(ms, e->user_ev[slot_a], e->user_ev[slot_b]));
+  API_CATCH(e)
 }
 
 int cald_counters(cald_engine* e, long long* kernel_launches, double* conv_flops) {

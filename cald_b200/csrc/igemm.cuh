@@ -108,7 +108,11 @@ __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& 
   x0 = tx * p.tw;
 }
 
-template <int BLOCK_N, bool SPLIT>
+// CHUNKED: the tensor core adds into the TMEM accumulator with truncation (measured: relative bias ~6e-8 per
+// accumulate, toward zero), which at K = 12544 (fc6) costs 6e-5.  In chunked mode the MMA warp restarts the
+// accumulator every p.kc k-blocks and the epilogue warps sum the partial tiles in fp32 registers (round to nearest),
+// using the two TMEM stages as a ring, so the bias is bounded by the chunk length instead of K.
+template <int BLOCK_N, bool SPLIT, bool CHUNKED>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvParams p) {
@@ -194,11 +198,16 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const int kc = CHUNKED ? p.kc : num_kb;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d = tmem_base + acc * Cfg::ACC_STRIDE;
+        uint32_t d = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
+          const int kin = kb % kc;  // position inside the accumulation chunk
+          if (kin == 0) {
+            mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+            tcgen05_fence_after();
+            d = tmem_base + acc * Cfg::ACC_STRIDE;
+          }
           mbar_wait(full_bar + 8 * stage, phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -211,18 +220,20 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint64_t ko = (uint64_t)((k * IG_UMMA_K * 2) >> 4);  // advance start address inside the swizzle row
             if (SPLIT) {
               // small cross terms first, dominant term last
-              tcgen05_mma_bf16(d, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0);
+              tcgen05_mma_bf16(d, a_lo + ko, b_hi + ko, idesc, (kin | k) != 0);
               tcgen05_mma_bf16(d, a_hi + ko, b_lo + ko, idesc, 1);
               tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, 1);
             } else {
-              tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, (kb | k) != 0);
+              tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, (kin | k) != 0);
             }
           }
           tcgen05_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
-          if (kb == num_kb - 1) tcgen05_commit(tfull_bar + 8 * acc);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (kin == kc - 1 || kb == num_kb - 1) {
+            tcgen05_commit(tfull_bar + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -241,31 +252,70 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         orow = out_row_offset(p, img, y, x);
         if (p.res_mode != RES_NONE) rrow = res_row_offset(p, img, y, x);
       }
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      tcgen05_fence_after();
-      const uint32_t t0 = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+      if (!CHUNKED) {
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        tcgen05_fence_after();
+        const uint32_t t0 = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-      for (int cc = 0; cc < BLOCK_N; cc += 32) {
-        uint32_t r[32];
-        tmem_ld32(t0 + cc, r);
-        const int cbase = nb * BLOCK_N + cc;
+        for (int cc = 0; cc < BLOCK_N; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32(t0 + cc, r);
+          const int cbase = nb * BLOCK_N + cc;
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const int c = cbase + j;
+              if (c < p.Cout) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
+                epilogue_store8(p, orow, rrow, c, v);
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      } else {
+        constexpr int NACC = BLOCK_N <= 128 ? BLOCK_N : 1;  // chunked mode is only instantiated for BLOCK_N <= 128
+        float accv[NACC];
+        const int chunks = (num_kb + p.kc - 1) / p.kc;
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(tfull_bar + 8 * acc, acc_phase);
+          tcgen05_fence_after();
+          const uint32_t t0 = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+          for (int cc = 0; cc < NACC; cc += 32) {
+            uint32_t r[32];
+            tmem_ld32(t0 + cc, r);
+            if (ch == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) accv[cc + i] = __uint_as_float(r[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) accv[cc + i] += __uint_as_float(r[i]);
+            }
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int c = cbase + j;
+          for (int j = 0; j < NACC; j += 8) {
+            const int c = nb * BLOCK_N + j;
             if (c < p.Cout) {
               float v[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
+              for (int i = 0; i < 8; ++i) v[i] = accv[j + i];
               epilogue_store8(p, orow, rrow, c, v);
             }
           }
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 

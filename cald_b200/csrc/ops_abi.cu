@@ -58,7 +58,7 @@ void free_conv_weight(ConvW& w) {
 
 extern "C" int cald_op_conv2d(const float* x, int n, int h, int w, int cin, const float* weight, const float* bias,
                               int cout, int k, int stride, int relu, const float* res, int res_mode, int res_h,
-                              int res_w, int prec, int impl, int phase_out, int block_n, float* out) {
+                              int res_w, int prec, int impl, int phase_out, int block_n, int kc, float* out) {
   OPS_TRY
   const bool split = (prec == 0);
   cudaStream_t st = 0;
@@ -74,6 +74,7 @@ extern "C" int cald_op_conv2d(const float* x, int n, int h, int w, int cin, cons
   eng.impl = impl ? CONV_SIMT : CONV_TC;
   eng.split = split;
   eng.force_block_n = block_n;
+  if (kc >= 0) eng.kc = kc;
   ConvW cw = upload_conv_weight(weight, bias, cout, cin, k, split, nullptr);
   float* dx = (float*)ar.alloc(in_e * 4);
   CALD_CUDA_CHECK(cudaMemcpy(dx, x, in_e * 4, cudaMemcpyHostToDevice));

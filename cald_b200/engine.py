@@ -191,3 +191,25 @@ class Engine:
         self._L.cald_counters.argtypes = [c_void_p, POINTER(c_longlong), POINTER(c_double)]
         self._L.cald_counters(self._h, ctypes.byref(k), ctypes.byref(f))
         return k.value, f.value
+
+    # ------------------------------------------------------------------ measurement hooks
+    def profile(self, enable=True):
+        self._L.cald_profile.argtypes = [c_void_p, c_int]
+        self._L.cald_profile(self._h, int(enable))
+
+    def profile_read(self):
+        """-> (conv kernel ms, conv launches, conv algorithmic FLOPs) since the last read."""
+        ms, n, fl = c_double(0), c_longlong(0), c_double(0)
+        self._L.cald_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_longlong), POINTER(c_double)]
+        self._check(self._L.cald_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
+        return ms.value, n.value, fl.value
+
+    def event_record(self, slot):
+        self._L.cald_event_record.argtypes = [c_void_p, c_int]
+        self._check(self._L.cald_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = c_float(0)
+        self._L.cald_event_elapsed_ms.argtypes = [c_void_p, c_int, c_int, POINTER(c_float)]
+        self._check(self._L.cald_event_elapsed_ms(self._h, a, b, ctypes.byref(ms)))
+        return ms.value

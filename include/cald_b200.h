@@ -92,6 +92,14 @@ long long cald_debug_fetch(cald_engine* e, const char* name, float* buf, long lo
  * and device milliseconds spent inside tcgen05 conv kernels when timing is enabled. */
 int cald_counters(cald_engine* e, long long* kernel_launches, double* conv_flops);
 
+/* Measurement hooks (bench.py).  cald_profile(e,1) brackets every tcgen05 conv/GEMM launch with CUDA events on
+ * the engine's stream; cald_profile_read() synchronises and returns the summed kernel time, launch count and
+ * algorithmic FLOPs since the last read.  cald_event_record/elapsed time whole regions on the same stream. */
+int cald_profile(cald_engine* e, int enable);
+int cald_profile_read(cald_engine* e, double* conv_ms, long long* conv_launches, double* conv_flops);
+int cald_event_record(cald_engine* e, int slot /* 0..7 */);
+int cald_event_elapsed_ms(cald_engine* e, int slot_a, int slot_b, float* ms);
+
 /* Same as cald_score but the u8 images already live in device memory (device pointers). */
 int cald_score_device(cald_engine* e, int n_images, const uint8_t* const* d_images, const int* heights,
                       const int* widths, int n_augs, const int* aug_kinds, double bp, const double* rng_uniforms,

@@ -28,12 +28,13 @@ const char* cald_ops_last_error(void);
  *         res_mode 0 none, 1 same shape, 2 nearest-upsampled to the output size
  * prec:   0 = split-bf16 x3 (fp32-faithful), 1 = single-pass bf16
  * impl:   0 = tcgen05 kernel, 1 = SIMT checker kernel
+ * kc:     k-blocks per accumulation chunk in split mode (-1 = engine default, 0 = never chunk)
  * phase_out: 1 = exercise the phase-split epilogue (output is re-assembled before return)
  * out:    [n][ho][wo][cout] fp32
  */
 int cald_op_conv2d(const float* x, int n, int h, int w, int cin, const float* weight, const float* bias, int cout,
                    int k, int stride, int relu, const float* res, int res_mode, int res_h, int res_w, int prec,
-                   int impl, int phase_out, int block_n, float* out);
+                   int impl, int phase_out, int block_n, int kc, float* out);
 
 #ifdef __cplusplus
 }

@@ -88,12 +88,22 @@ def test_conv_phase_split_epilogue():
     assert np.array_equal(a, p)
 
 
-def test_conv_tc_equals_simt_large_k():
-    """fc6-like contraction: K = 12544, many k-blocks through the smem ring."""
+def test_conv_large_k_chunked_accumulation():
+    """fc6-like contraction (K = 12544).  The tensor core truncates when adding into the TMEM accumulator; the
+    chunked-accumulation epilogue bounds that bias.  Unchunked error is reported for the record."""
     from cald_b200 import ops
     rs = np.random.RandomState(3)
     x = rs.standard_normal((1, 1, 300, 12544)).astype(np.float32)
     wt = (rs.standard_normal((128, 12544, 1, 1)) * 0.01).astype(np.float32)
     want = _ref(x, wt, None, 1, False)
-    got = ops.conv2d(x, wt, None, prec=0, impl=0)
-    assert np.abs(got - want).max() <= 3e-5 * np.abs(want).max()
+    scale = np.abs(want).max()
+    errs = {}
+    for kc in (0, 16, 8, 4, 2, 1):
+        got = ops.conv2d(x, wt, None, prec=0, impl=0, kc=kc)
+        errs[kc] = float(np.abs(got - want).max() / scale)
+    simt = ops.conv2d(x, wt, None, prec=0, impl=1)
+    errs["simt"] = float(np.abs(simt - want).max() / scale)
+    print("relative error by chunk length (k-blocks of 64):", errs)
+    assert errs[4] <= 1e-5, errs
+    got = ops.conv2d(x, wt, None, prec=0, impl=0)  # engine default
+    assert np.abs(got - want).max() <= 1e-5 * scale
