@@ -1,0 +1,88 @@
+"""CPU-side checks of the boundary: the shared library loads, exports every declared symbol, and the
+host logic (weight key mapping, shard arithmetic, augmentation ordering) behaves.  No GPU compute."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    so = os.path.join(ROOT, "cald_b200", "libcald_b200.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["bash", os.path.join(ROOT, "build.sh")])
+    return so
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cald_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = ctypes.CDLL(built)
+    names = _declared("cald_b200.h") + _declared("cald_b200_ops.h")
+    assert "cald_score" in names and "cald_create" in names and "cald_op_conv2d" in names
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_create_fails_loudly_without_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cald_b200.engine import Engine
+    from cald_b200._lib import CaldError
+    with pytest.raises(CaldError):
+        Engine(depth=50, num_classes=21)
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions(built):
+    out = subprocess.run(["cuobjdump", "-sass", built], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out and "UTMALDG" in out and "LDTM" in out
+
+
+def test_weight_key_aliases():
+    from cald_b200 import arch
+    assert arch.canonical_key("rpn.head.conv.weight") == "rpn.head.conv.0.0.weight"
+    assert arch.canonical_key("backbone.fpn.inner_blocks.2.bias") == "backbone.fpn.inner_blocks.2.0.bias"
+    assert arch.canonical_key("backbone.fpn.layer_blocks.0.0.weight") == "backbone.fpn.layer_blocks.0.0.weight"
+    assert len(arch.frcnn_params(50, 21)) == 295 and len(arch.frcnn_params(101, 21)) == 550
+    assert len(arch.retinanet_params(50, 21)) == 301
+
+
+def test_planted_weights_are_deterministic_and_complete():
+    from cald_b200 import arch, synth
+    a = synth.planted_frcnn_weights(50, 21, 0)
+    b = synth.planted_frcnn_weights(50, 21, 0)
+    shapes = arch.frcnn_params(50, 21)
+    assert list(a.keys()) == list(shapes.keys())
+    for k in a:
+        assert a[k].shape == tuple(shapes[k]) and a[k].dtype == np.float32 and np.array_equal(a[k], b[k])
+
+
+def test_aug_order_follows_reference():
+    from cald_b200 import api
+    from cald_b200 import engine as E
+    assert api._aug_kinds(['rotation', 'flip', 'cut_out', 'smaller_resize']) == \
+        [E.AUG_FLIP, E.AUG_CUTOUT, E.AUG_SMALLER_RESIZE, E.AUG_ROTATION]
+    with pytest.raises(NotImplementedError):
+        api._aug_kinds(['ga'])
+
+
+def test_shard_partition_covers_pool_in_order():
+    from cald_b200 import shard
+    for n in (0, 1, 7, 100, 10001):
+        for world in (1, 2, 3, 8):
+            parts = [shard.shard_indices(n, r, world) for r in range(world)]
+            flat = np.concatenate(parts) if parts else np.zeros(0, int)
+            assert sorted(flat.tolist()) == list(range(n))
+            merged = shard.merge_shards([np.asarray(p, float) * 2 for p in parts], n, world)
+            assert np.array_equal(merged, np.arange(n) * 2.0)
