@@ -84,6 +84,8 @@ struct ConvParams {
   int res_ld;
   int out_H2, out_W2;  // OUT_PHASE: ceil(H/2), ceil(W/2)
   int kc;              // chunked accumulation: k-blocks per TMEM accumulation chunk
+  int tma_store;       // 1: epilogue stages 64-channel groups in smem and stores them with TMA (NHWC bf16 outputs)
+  int c_lo_img;        // image-index offset of the lo plane in the output tensor map
 };
 
 // ATen nearest-neighbour source index (UpSampleKernel: nearest_idx), float scale.

@@ -89,6 +89,7 @@ struct ConvEngine {
   ConvImpl impl = CONV_TC;
   bool split = true;       // false: single-pass bf16 (hi plane only)
   int force_block_n = 0;   // 0 = auto
+  bool use_tma_store = true;  // false: always use the direct (per-thread) store epilogue
   int kc = 8;              // split mode: k-blocks (of 64) per accumulation chunk; 0 = never chunk
   long long launches = 0;  // kernels launched (bench's gpu_launches)
   double flops = 0;        // algorithmic 2*MAC of the launches
@@ -121,7 +122,8 @@ struct ConvEngine {
   }
 
   template <int BN, bool SP, bool CH>
-  void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
+  void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const ConvParams& p,
+                 cudaStream_t st) {
     using Cfg = IgemmCfg<BN, SP>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -131,7 +133,7 @@ struct ConvEngine {
     }
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
-    igemm_tc_kernel<BN, SP, CH><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    igemm_tc_kernel<BN, SP, CH><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, p);
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
     CALD_CUDA_CHECK(cudaGetLastError());
   }
@@ -234,17 +236,30 @@ struct ConvEngine {
     else
       ta = make_tmap(in.hi, in.c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);
     tb = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, split ? 2 : 1, BN, 1);
+    // epilogue output path: TMA store for plain NHWC bf16 outputs whose channel count is a multiple of 64
+    CUtensorMap tc = tb;
+    p.tma_store = (!o.out_phase && !o.no_bf16_out && o.out_f32 == nullptr && (w.cout_pad % 64) == 0 &&
+                   out.c == w.cout_pad && use_tma_store) ? 1 : 0;
+    if (p.tma_store) {
+      if (spatial) {
+        tc = make_tmap(out.hi, out.c, out.w, out.h, (uint64_t)out.n * (split ? 2 : 1), p.tw, p.th);
+        p.c_lo_img = out.n;
+      } else {
+        tc = make_tmap(out.hi, out.c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);
+        p.c_lo_img = 1;
+      }
+    }
     const int num_kb = w.taps * (w.cin / 64);
     const bool chunked = split && kc > 0 && num_kb > kc && BN <= 128;
     p.kc = chunked ? kc : num_kb;
     if (split) {
-      if (BN == 64) { if (chunked) launch_tc<64, true, true>(ta, tb, p, st); else launch_tc<64, true, false>(ta, tb, p, st); }
-      else if (BN == 128) { if (chunked) launch_tc<128, true, true>(ta, tb, p, st); else launch_tc<128, true, false>(ta, tb, p, st); }
-      else launch_tc<256, true, false>(ta, tb, p, st);
+      if (BN == 64) { if (chunked) launch_tc<64, true, true>(ta, tb, tc, p, st); else launch_tc<64, true, false>(ta, tb, tc, p, st); }
+      else if (BN == 128) { if (chunked) launch_tc<128, true, true>(ta, tb, tc, p, st); else launch_tc<128, true, false>(ta, tb, tc, p, st); }
+      else launch_tc<256, true, false>(ta, tb, tc, p, st);
     } else {
-      if (BN == 64) launch_tc<64, false, false>(ta, tb, p, st);
-      else if (BN == 128) launch_tc<128, false, false>(ta, tb, p, st);
-      else launch_tc<256, false, false>(ta, tb, p, st);
+      if (BN == 64) launch_tc<64, false, false>(ta, tb, tc, p, st);
+      else if (BN == 128) launch_tc<128, false, false>(ta, tb, tc, p, st);
+      else launch_tc<256, false, false>(ta, tb, tc, p, st);
     }
   }
 };

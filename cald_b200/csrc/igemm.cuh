@@ -25,8 +25,11 @@ struct IgemmCfg {
   static constexpr int A_BYTES = IG_BLOCK_M * IG_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * IG_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int OUT_STAGE_BYTES = (SPLIT ? 2 : 1) * A_BYTES;  // epilogue staging: 128 rows x 64 ch per plane
+  static constexpr int BAR_BYTES = 1024;                              // barriers + tmem pointer (keeps staging aligned)
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - BAR_BYTES - OUT_STAGE_BYTES;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + OUT_STAGE_BYTES + 1024;
   static constexpr int TMEM_COLS = 512;  // 2 accumulator stages of <= 256 fp32 columns
   static constexpr int ACC_STRIDE = 256;
 };
@@ -95,6 +98,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// 64 residual channels of one output row (8 x 16 B per plane) into registers
+__device__ __forceinline__ void load_res64(const ConvParams& p, long long rrow, int c, uint4* rh, uint4* rl) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) rh[q] = *reinterpret_cast<const uint4*>(p.res_hi + rrow + c + q * 8);
+  if (p.res_lo) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) rl[q] = *reinterpret_cast<const uint4*>(p.res_lo + rrow + c + q * 8);
+  }
+}
+
 // tile index -> (n block, image, y0, x0).  N blocks vary fastest so that CTAs running
 // concurrently share the same activation tile in L2.
 __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& nb, int& img, int& y0, int& x0) {
@@ -115,7 +133,7 @@ __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& 
 template <int BLOCK_N, bool SPLIT, bool CHUNKED>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ ConvParams p) {
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ ConvParams p) {
   using Cfg = IgemmCfg<BLOCK_N, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
@@ -134,6 +152,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -240,8 +259,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
+    const bool leader = (threadIdx.x == 64);
+    const uint32_t stage_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;  // 1024-aligned
+    bool store_pending = false;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int num_chunks = CHUNKED ? (num_kb + p.kc - 1) / p.kc : 1;
+    constexpr int NACC = CHUNKED ? (BLOCK_N <= 128 ? BLOCK_N : 32) : 32;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int nb, img, y0, x0;
       tile_coords(p, tile, nb, img, y0, x0);
@@ -252,37 +276,14 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         orow = out_row_offset(p, img, y, x);
         if (p.res_mode != RES_NONE) rrow = res_row_offset(p, img, y, x);
       }
-      if (!CHUNKED) {
-        mbar_wait(tfull_bar + 8 * acc, acc_phase);
-        tcgen05_fence_after();
-        const uint32_t t0 = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-        for (int cc = 0; cc < BLOCK_N; cc += 32) {
-          uint32_t r[32];
-          tmem_ld32(t0 + cc, r);
-          const int cbase = nb * BLOCK_N + cc;
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const int c = cbase + j;
-              if (c < p.Cout) {
-                float v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
-                epilogue_store8(p, orow, rrow, c, v);
-              }
-            }
-          }
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      } else {
-        constexpr int NACC = BLOCK_N <= 128 ? BLOCK_N : 1;  // chunked mode is only instantiated for BLOCK_N <= 128
-        float accv[NACC];
-        const int chunks = (num_kb + p.kc - 1) / p.kc;
-        for (int ch = 0; ch < chunks; ++ch) {
+      // residual of the first 64-channel group is requested before the accumulator is ready
+      uint4 rh[8], rl[8];
+      const bool res_on = (p.res_mode != RES_NONE) && valid;
+      if (p.tma_store && res_on) load_res64(p, rrow, nb * BLOCK_N, rh, rl);
+
+      float accv[NACC];
+      if (CHUNKED) {
+        for (int ch = 0; ch < num_chunks; ++ch) {
           mbar_wait(tfull_bar + 8 * acc, acc_phase);
           tcgen05_fence_after();
           const uint32_t t0 = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
@@ -303,20 +304,103 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (valid) {
+      } else {
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        tcgen05_fence_after();
+      }
+      const uint32_t t0 = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+
 #pragma unroll
-          for (int j = 0; j < NACC; j += 8) {
-            const int c = nb * BLOCK_N + j;
-            if (c < p.Cout) {
-              float v[8];
+      for (int g = 0; g < BLOCK_N / 64; ++g) {
+        const int c0 = nb * BLOCK_N + g * 64;
+        float v[64];
+        if (CHUNKED) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = accv[j + i];
-              epilogue_store8(p, orow, rrow, c, v);
-            }
+          for (int i = 0; i < 64; ++i) v[i] = accv[(g * 64 + i) % NACC];
+        } else {
+          uint32_t r[32];
+          tmem_ld32(t0 + g * 64, r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          tmem_ld32(t0 + g * 64 + 32, r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
+          if (g == BLOCK_N / 64 - 1) {  // accumulator fully drained: hand the TMEM stage back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
           }
         }
+        if (!p.tma_store) {
+          // direct path: fp32 head outputs, phase-split outputs, Cout not a multiple of 64
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 8) {
+              if (c0 + j < p.Cout) epilogue_store8(p, orow, rrow, c0 + j, &v[j]);
+            }
+          }
+          continue;
+        }
+        if (c0 >= p.Cout) continue;  // uniform across the CTA
+        // ---- bias + residual + ReLU in registers
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + c0 + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (res_on) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const bf16* h = reinterpret_cast<const bf16*>(&rh[q]);
+            const bf16* l = reinterpret_cast<const bf16*>(&rl[q]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[q * 8 + i] += SPLIT ? join_bf16(h[i], l[i]) : __bfloat162float(h[i]);
+          }
+          // request the next group's residual now; it lands while this group is being stored
+          if (g + 1 < BLOCK_N / 64 && c0 + 64 < p.Cout) load_res64(p, rrow, c0 + 64, rh, rl);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        // ---- wait until the previous TMA store has finished reading the staging buffer
+        if (store_pending) {
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        // ---- split to bf16 planes and write this row's 8 x 16-byte chunks at their 128B-swizzled positions
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          bf16 hh[8], ll[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_bf16(v[q * 8 + i], hh[i], ll[i]);
+          const uint32_t off = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_base + off),
+                       "r"(pack_bf16x2(hh[0], hh[1])), "r"(pack_bf16x2(hh[2], hh[3])), "r"(pack_bf16x2(hh[4], hh[5])),
+                       "r"(pack_bf16x2(hh[6], hh[7]))
+                       : "memory");
+          if (SPLIT)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_base + Cfg::A_BYTES + off),
+                         "r"(pack_bf16x2(ll[0], ll[1])), "r"(pack_bf16x2(ll[2], ll[3])),
+                         "r"(pack_bf16x2(ll[4], ll[5])), "r"(pack_bf16x2(ll[6], ll[7]))
+                         : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          tma_store_4d(&tmC, stage_base, c0, x0, y0, img);
+          if (SPLIT) tma_store_4d(&tmC, stage_base + Cfg::A_BYTES, c0, x0, y0, img + p.c_lo_img);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        store_pending = true;
+      }
+      if (!CHUNKED) {
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+    if (leader && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tcgen05_fence_before();
