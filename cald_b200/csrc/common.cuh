@@ -44,6 +44,20 @@ __device__ __forceinline__ float join_bf16(bf16 hi, bf16 lo) {
   return __bfloat162float(hi) + __bfloat162float(lo);
 }
 
+// Two floats -> packed (hi plane, lo plane) bf16x2 words with 6 instructions (cvt.rn.bf16x2.f32 packs a pair).
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+// packed bf16x2 (hi, lo planes) -> two floats
+__device__ __forceinline__ void join_pack2(uint32_t hi, uint32_t lo, float& a, float& b) {
+  a = __uint_as_float(hi << 16) + __uint_as_float(lo << 16);
+  b = __uint_as_float(hi & 0xffff0000u) + __uint_as_float(lo & 0xffff0000u);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }

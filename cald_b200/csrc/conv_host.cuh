@@ -35,6 +35,10 @@ struct ConvOpts {
   int full_h = 0, full_w = 0;   // out_phase: logical (full-resolution) output size
   float* out_f32 = nullptr;     // fp32 NHWC output instead of / in addition to split bf16
   bool no_bf16_out = false;
+  // stem mode: `in` is the padded space-to-depth image [n][Ho+3][Wo+3][16]; the 7x7/s2 conv is a 4x4/s1 conv whose
+  // k-block `dy` is the 64-element window (4 pixels x 16 ch) starting at pixel (oy + dy, ox): an overlapping-stride
+  // tensor map (pixel stride 32 B, box width 128 B) lets TMA gather it without an im2col buffer.
+  bool stem_window = false;
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -68,6 +72,27 @@ inline CUtensorMap make_tmap(const void* base, uint64_t d0, uint64_t d1, uint64_
     char b[256];
     snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu,%llu,%llu box=%u,%u", (int)r,
              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)d3, b1, b2);
+    throw std::runtime_error(b);
+  }
+  return tm;
+}
+
+// Same, with explicit byte strides for dims 1..3 (used by the stem's overlapping sliding-window view).
+inline CUtensorMap make_tmap_strided(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                                     uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b1, uint32_t b2) {
+  CUtensorMap tm;
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {s1, s2, s3};
+  cuuint32_t box[4] = {64, b1, b2, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = get_encode_tiled()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                                  box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[256];
+    snprintf(b, sizeof(b), "cuTensorMapEncodeTiled(strided) failed (%d) dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu",
+             (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)d3,
+             (unsigned long long)s1, (unsigned long long)s2, (unsigned long long)s3);
     throw std::runtime_error(b);
   }
   return tm;
@@ -140,11 +165,15 @@ struct ConvEngine {
 
   // out must be pre-shaped by the caller (n, h, w, c = cout_pad or larger ldc).
   void run(const Act& in, const ConvW& w, Act& out, const ConvOpts& o, cudaStream_t st) {
-    if (in.c != w.cin || (w.cin % 64) != 0) throw std::runtime_error("conv: Cin mismatch or not a multiple of 64");
+    if (o.stem_window) {
+      if (in.c != 16 || w.cin != 64 || w.taps != 4) throw std::runtime_error("conv: bad stem operands");
+    } else if (in.c != w.cin || (w.cin % 64) != 0) {
+      throw std::runtime_error("conv: Cin mismatch or not a multiple of 64");
+    }
     if (in.split != split) throw std::runtime_error("conv: activation precision mode mismatch");
     ConvParams p;
     memset(&p, 0, sizeof(p));
-    const bool spatial = (w.taps == 9) || o.out_phase || o.res_mode == RES_NEAREST;
+    const bool spatial = (w.taps == 9) || o.out_phase || o.res_mode == RES_NEAREST || o.stem_window;
     p.Cin = w.cin;
     p.taps = w.taps;
     p.Cout = w.cout_pad;
@@ -154,7 +183,9 @@ struct ConvEngine {
       p.H = o.out_phase ? o.full_h : out.h;
       p.W = o.out_phase ? o.full_w : out.w;
       n_img_in = in.n;
-      if (w.taps == 1) {
+      if (o.stem_window) {
+        for (int t = 0; t < 4; ++t) { p.tap_dy[t] = t; p.tap_dx[t] = 0; p.tap_img[t] = 0; }
+      } else if (w.taps == 1) {
         if (in.phases != 1) throw std::runtime_error("conv: 1x1 needs a plain input");
         p.tap_dy[0] = p.tap_dx[0] = p.tap_img[0] = 0;
       } else if (o.stride == 2) {
@@ -214,7 +245,8 @@ struct ConvEngine {
     p.out_H2 = out.h;
     p.out_W2 = out.w;
     launches++;
-    const double fl = 2.0 * (double)p.n_img * p.H * p.W * (double)w.cout * w.taps * w.cin;
+    // algorithmic FLOPs of the reference op (the stem's 4x4x16 window holds the 7x7x3 = 147 real taps)
+    const double fl = 2.0 * (double)p.n_img * p.H * p.W * (double)w.cout * (o.stem_window ? 147.0 : (double)w.taps * w.cin);
     flops += fl;
     if (profiling && impl == CONV_TC) { prof_flops += fl; prof_launches++; }
 
@@ -224,6 +256,8 @@ struct ConvEngine {
       so.b_hi = w.w; so.b_lo = split ? w.w + w.plane_elems() : nullptr;
       if (spatial) { so.H_in = in.h; so.W_in = in.w; } else { so.H_in = 1; so.W_in = p.W; }
       so.n_img_in = n_img_in;
+      so.pix_stride = o.stem_window ? 16 : w.cin;
+      so.w_limit = o.stem_window ? in.w - 3 : so.W_in;
       long long total = (long long)p.n_img * p.H * p.W * ((p.Cout + 7) / 8);
       int blocks = (int)((total + 127) / 128);
       conv_simt_kernel<<<blocks, 128, 0, st>>>(p, so);
@@ -231,7 +265,10 @@ struct ConvEngine {
       return;
     }
     CUtensorMap ta, tb;
-    if (spatial)
+    if (o.stem_window)
+      ta = make_tmap_strided(in.hi, 64, (uint64_t)in.w - 3, in.h, (uint64_t)in.n * (split ? 2 : 1), 32,
+                             (uint64_t)in.w * 32, (uint64_t)in.h * in.w * 32, p.tw, p.th);
+    else if (spatial)
       ta = make_tmap(in.hi, in.c, in.w, in.h, (uint64_t)in.phases * in.n * (split ? 2 : 1), p.tw, p.th);
     else
       ta = make_tmap(in.hi, in.c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);

@@ -135,23 +135,34 @@ void finalize_weights(cald_engine* e) {
   const int depth = e->cfg.depth;
   static const int blocks50[4] = {3, 4, 6, 3}, blocks101[4] = {3, 4, 23, 3};
   const int* nb = depth == 101 ? blocks101 : blocks50;
-  // ---- stem: [64][3][7][7] with BN folded -> [64][192], k = r*24 + s*3 + c
+  // ---- stem: [64][3][7][7] with BN folded -> 4x4 conv over the space-to-depth image:
+  //      k = dy*64 + dx*16 + (py*2+px)*3 + c  with  r = 2*dy + py - 1,  s = 2*dx + px - 1  (zero where r, s fall outside 0..6)
   {
     const HostTensor& w = need(e, "backbone.body.conv1.weight");
     const HostTensor& g = need(e, "backbone.body.bn1.weight");
     const HostTensor& b = need(e, "backbone.body.bn1.bias");
     const HostTensor& m = need(e, "backbone.body.bn1.running_mean");
     const HostTensor& v = need(e, "backbone.body.bn1.running_var");
-    std::vector<float> w2((size_t)64 * STEM_K, 0.f), bias(64);
+    std::vector<float> w2((size_t)64 * 256, 0.f), bias(64);
     for (int o = 0; o < 64; ++o) {
       float scale = g.v[o] * (1.0f / sqrtf(v.v[o] + 1e-5f));
       bias[o] = b.v[o] - m.v[o] * scale;
-      for (int c = 0; c < 3; ++c)
-        for (int r = 0; r < 7; ++r)
-          for (int s = 0; s < 7; ++s)
-            w2[(size_t)o * STEM_K + r * 24 + s * 3 + c] = w.v[(((size_t)o * 3 + c) * 7 + r) * 7 + s] * scale;
+      for (int dy = 0; dy < 4; ++dy)
+        for (int dx = 0; dx < 4; ++dx)
+          for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+              int r = 2 * dy + py - 1, s2 = 2 * dx + px - 1;
+              if (r < 0 || r > 6 || s2 < 0 || s2 > 6) continue;
+              for (int c = 0; c < 3; ++c)
+                w2[(size_t)o * 256 + dy * 64 + dx * 16 + (py * 2 + px) * 3 + c] =
+                    w.v[(((size_t)o * 3 + c) * 7 + r) * 7 + s2] * scale;
+            }
     }
-    e->stem = upload_conv_weight(w2.data(), bias.data(), 64, STEM_K, 1, e->split, nullptr);
+    // upload as a "4-tap" conv with Cin = 64: layout [o][tap][64] == [o][256]
+    ConvW cw = upload_conv_weight(w2.data(), bias.data(), 64, 256, 1, e->split, nullptr);
+    cw.cin = 64;
+    cw.taps = 4;
+    e->stem = cw;
   }
   e->layers.assign(4, {});
   for (int li = 0; li < 4; ++li) {
@@ -268,23 +279,33 @@ void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views
   const bool split = e->split;
   const int C = e->C, cap = e->cap;
 
-  // ---- transform: normalise + resize + pad (fused), fp32 NHWC3
-  float* img = (float*)ar.alloc((size_t)V * Hp * Wp * 3 * 4);
+  // ---- transform (normalise + resize + pad) fused with the stem's space-to-depth layout
+  const int Ho = Hp / 2, Wo = Wp / 2;
+  Act sin = alloc_act(ar, V, Ho + 3, Wo + 3, 16, split, 1);
   {
-    dim3 grid((Wp * 3 + 191) / 192, Hp, V);
-    view_preprocess_kernel<<<grid, 192, 0, st>>>(d_views, d_cuts, Hp, Wp, img);
+    dim3 grid((Wo + 3 + 127) / 128, Ho + 3, V);
+    view_stem_input_kernel<<<grid, 128, 0, st>>>(d_views, d_cuts, Ho + 3, Wo + 3, sin.hi, sin.lo());
     CALD_CUDA_CHECK(cudaGetLastError());
     KLAUNCH(e);
   }
-  dbg_store_f32(e, "input", img, (size_t)V * Hp * Wp * 3);
-  // ---- stem: im2col + GEMM (+BN+ReLU) + maxpool
-  Act col = stem_im2col(ar, img, V, Hp, Wp, split, st);
-  KLAUNCH(e);
-  ar.free(img);
+  if (e->cfg.debug) {
+    float* img = (float*)ar.alloc((size_t)V * Hp * Wp * 3 * 4);
+    dim3 grid((Wp * 3 + 191) / 192, Hp, V);
+    view_preprocess_kernel<<<grid, 192, 0, st>>>(d_views, d_cuts, Hp, Wp, img);
+    dbg_store_f32(e, "input", img, (size_t)V * Hp * Wp * 3);
+    ar.free(img);
+  }
+  // ---- stem: 7x7/2 conv (+BN+ReLU) as a windowed 4x4 implicit GEMM, then maxpool
   ConvOpts relu_o;
   relu_o.relu = true;
-  Act x = conv(e, col, e->stem, V, col.h, col.w, relu_o);
-  free_act(ar, col);
+  Act x;
+  {
+    ConvOpts so;
+    so.relu = true;
+    so.stem_window = true;
+    x = conv(e, sin, e->stem, V, Ho, Wo, so);
+  }
+  free_act(ar, sin);
   Act xp = maxpool3x3s2(ar, x, st);
   KLAUNCH(e);
   free_act(ar, x);
@@ -309,17 +330,12 @@ void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views
       }
       Act t1;
       if (b.stride == 2) {
-        t1 = alloc_act(ar, V, ho, wo, b.c1.cout_pad, split, 4);
-        if ((x.h & 1) || (x.w & 1)) {
-          CALD_CUDA_CHECK(cudaMemsetAsync(t1.hi, 0, t1.bytes(), st));
-        }
-        ConvOpts o;
-        o.relu = true;
-        o.out_phase = true;
-        o.full_h = x.h;
-        o.full_w = x.w;
-        e->conv.run(x, b.c1, t1, o, st);
-        KLAUNCH(e);
+        // conv1 at full resolution through the TMA-store epilogue, then one HBM pass re-lays it out as the four
+        // stride-2 phases the 3x3 reads (cheaper than the per-thread phase-split store path)
+        Act full = conv(e, x, b.c1, V, x.h, x.w, relu_o);
+        t1 = phase_split(ar, full, st);
+        e->launches += split ? 2 : 1;
+        free_act(ar, full);
       } else {
         t1 = conv(e, x, b.c1, V, x.h, x.w, relu_o);
       }
@@ -593,13 +609,34 @@ void detect_views(cald_engine* e, const std::vector<HostView>& views, const CutR
     float* d_r = (float*)ar.alloc(n * 8);
     CALD_CUDA_CHECK(cudaMemcpyAsync(d_vd, lvd.data(), n * sizeof(ViewDesc), cudaMemcpyHostToDevice, st));
     CALD_CUDA_CHECK(cudaMemcpyAsync(d_hw, lhw.data(), n * 8, cudaMemcpyHostToDevice, st));
+    // (pageable-host cudaMemcpyAsync stages the source before returning, so the vectors may go out of scope)
     CALD_CUDA_CHECK(cudaMemcpyAsync(d_r, lr.data(), n * 8, cudaMemcpyHostToDevice, st));
-    CALD_CUDA_CHECK(cudaStreamSynchronize(st));  // host vectors go out of scope below
+    const int dc = e->det_cap;
+    const size_t srow = (size_t)e->cap * e->C * 4;
+    bool contiguous = true;
+    for (int j = 0; j < n; ++j) contiguous &= (order[pos + j] == order[pos] + j);
+    if (contiguous) {
+      // the group occupies consecutive global slots: let the pass write its results in place
+      const int g0 = order[pos];
+      ViewSet sub;
+      sub.V = n;
+      sub.det.count = out.det.count + g0;
+      sub.det.boxes = out.det.boxes + (size_t)g0 * dc;
+      sub.det.props = out.det.props + (size_t)g0 * dc;
+      sub.det.scores = out.det.scores + (size_t)g0 * dc;
+      sub.det.prob_max = out.det.prob_max + (size_t)g0 * dc;
+      sub.det.labels = out.det.labels + (size_t)g0 * dc;
+      sub.det.prop_idx = out.det.prop_idx + (size_t)g0 * dc;
+      sub.scores = out.scores + (size_t)g0 * e->cap * e->C;
+      sub.prob_max = out.prob_max + (size_t)g0 * e->cap;
+      forward_pass(e, n, php[order[pos]], pwp[order[pos]], d_vd, d_cuts, d_hw, d_r, sub);
+      ar.free(d_vd); ar.free(d_hw); ar.free(d_r);
+      pos = end;
+      continue;
+    }
     ViewSet local = alloc_viewset(e, n);
     forward_pass(e, n, php[order[pos]], pwp[order[pos]], d_vd, d_cuts, d_hw, d_r, local);
     // scatter to global view slots
-    const int dc = e->det_cap;
-    const size_t srow = (size_t)e->cap * e->C * 4;
     for (int j = 0; j < n; ++j) {
       int g = order[pos + j];
       auto cp = [&](void* dst, const void* src, size_t bytes) {

@@ -353,10 +353,20 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (res_on) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const bf16* h = reinterpret_cast<const bf16*>(&rh[q]);
-            const bf16* l = reinterpret_cast<const bf16*>(&rl[q]);
+            const uint32_t* h = reinterpret_cast<const uint32_t*>(&rh[q]);
+            const uint32_t* l = reinterpret_cast<const uint32_t*>(&rl[q]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[q * 8 + i] += SPLIT ? join_bf16(h[i], l[i]) : __bfloat162float(h[i]);
+            for (int i = 0; i < 4; ++i) {
+              float a, b;
+              if (SPLIT) {
+                join_pack2(h[i], l[i], a, b);
+              } else {
+                a = __uint_as_float(h[i] << 16);
+                b = __uint_as_float(h[i] & 0xffff0000u);
+              }
+              v[q * 8 + 2 * i] += a;
+              v[q * 8 + 2 * i + 1] += b;
+            }
           }
           // request the next group's residual now; it lands while this group is being stored
           if (g + 1 < BLOCK_N / 64 && c0 + 64 < p.Cout) load_res64(p, rrow, c0 + 64, rh, rl);
@@ -373,18 +383,16 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ---- split to bf16 planes and write this row's 8 x 16-byte chunks at their 128B-swizzled positions
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          bf16 hh[8], ll[8];
+          uint32_t ph[4], pl[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) split_bf16(v[q * 8 + i], hh[i], ll[i]);
+          for (int i = 0; i < 4; ++i) split_pack2(v[q * 8 + 2 * i], v[q * 8 + 2 * i + 1], ph[i], pl[i]);
           const uint32_t off = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_base + off),
-                       "r"(pack_bf16x2(hh[0], hh[1])), "r"(pack_bf16x2(hh[2], hh[3])), "r"(pack_bf16x2(hh[4], hh[5])),
-                       "r"(pack_bf16x2(hh[6], hh[7]))
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_base + off), "r"(ph[0]), "r"(ph[1]),
+                       "r"(ph[2]), "r"(ph[3])
                        : "memory");
           if (SPLIT)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_base + Cfg::A_BYTES + off),
-                         "r"(pack_bf16x2(ll[0], ll[1])), "r"(pack_bf16x2(ll[2], ll[3])),
-                         "r"(pack_bf16x2(ll[4], ll[5])), "r"(pack_bf16x2(ll[6], ll[7]))
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_base + Cfg::A_BYTES + off), "r"(pl[0]),
+                         "r"(pl[1]), "r"(pl[2]), "r"(pl[3])
                          : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -422,6 +430,8 @@ struct SimtOperands {
   const bf16* a_hi; const bf16* a_lo;   // [img'][H_in][W_in][Cin]
   const bf16* b_hi; const bf16* b_lo;   // [Cout_pad][taps*Cin]
   int H_in, W_in, n_img_in;             // input plane geometry (a_lo == null -> bf16 mode)
+  int pix_stride;                       // elements between consecutive pixels (Cin, or 16 for the stem window)
+  int w_limit;                          // number of valid window start columns (W_in, or W_in - 3 for the stem)
 };
 
 __global__ void conv_simt_kernel(ConvParams p, SimtOperands o) {
@@ -438,8 +448,8 @@ __global__ void conv_simt_kernel(ConvParams p, SimtOperands o) {
   const int ktot = p.taps * p.Cin;
   for (int tap = 0; tap < p.taps; ++tap) {
     int iy = y + p.tap_dy[tap], ix = x + p.tap_dx[tap], ii = n + p.tap_img[tap];
-    if (iy < 0 || iy >= o.H_in || ix < 0 || ix >= o.W_in) continue;
-    const long long abase = (((long long)ii * o.H_in + iy) * o.W_in + ix) * p.Cin;
+    if (iy < 0 || iy >= o.H_in || ix < 0 || ix >= o.w_limit) continue;
+    const long long abase = (((long long)ii * o.H_in + iy) * o.W_in + ix) * o.pix_stride;
     for (int c = 0; c < p.Cin; ++c) {
       float a = __bfloat162float(o.a_hi[abase + c]);
       if (o.a_lo) a += __bfloat162float(o.a_lo[abase + c]);

@@ -71,6 +71,58 @@ __global__ void view_preprocess_kernel(const ViewDesc* __restrict__ views, const
   out[(((long long)v * Hp + oy) * Wp + ox) * 3 + c] = val;
 }
 
+// Value of the normalised / resized / zero-padded detector input at integer position (c, iy, ix) of view d.
+__device__ __forceinline__ float view_input_value(const ViewDesc& d, const CutRects* cut, int c, int oy, int ox) {
+  if (oy < 0 || ox < 0 || oy >= d.rh || ox >= d.rw) return 0.f;
+  const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+  const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+  const float sh = (float)d.sh / (float)d.rh, sw = (float)d.sw / (float)d.rw;
+  float fy = sh * ((float)oy + 0.5f) - 0.5f;
+  if (fy < 0.f) fy = 0.f;
+  float fx = sw * ((float)ox + 0.5f) - 0.5f;
+  if (fx < 0.f) fx = 0.f;
+  int y0 = (int)fy, x0 = (int)fx;
+  int y1 = y0 + ((y0 < d.sh - 1) ? 1 : 0), x1 = x0 + ((x0 < d.sw - 1) ? 1 : 0);
+  float ly = fy - (float)y0, lx = fx - (float)x0;
+  if (ly == 0.f && lx == 0.f) return src_pixel(d, cut, c, y0, x0, mean, stdv);  // identity resize: exact copy
+  float hy = 1.f - ly, hx = 1.f - lx;
+  float p00 = src_pixel(d, cut, c, y0, x0, mean, stdv), p01 = src_pixel(d, cut, c, y0, x1, mean, stdv);
+  float p10 = src_pixel(d, cut, c, y1, x0, mean, stdv), p11 = src_pixel(d, cut, c, y1, x1, mean, stdv);
+  return hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
+}
+
+// Fused transform + space-to-depth for the stem: writes the padded phase image
+//   S[v][pr][pc][(py*2+px)*3 + c] = input(c, 2*(pr-2)+py, 2*(pc-2)+px)   (channels 12..15 = 0), split bf16,
+// with pr in [0, Ho+3), pc in [0, Wo+3).  One thread per (pr, pc): 2 x 32-byte stores.
+__global__ void view_stem_input_kernel(const ViewDesc* __restrict__ views, const CutRects* __restrict__ cuts, int Hs,
+                                       int Ws, bf16* __restrict__ ohi, bf16* __restrict__ olo) {
+  const int v = blockIdx.z, pr = blockIdx.y;
+  const int pc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pc >= Ws) return;
+  const ViewDesc d = views[v];
+  const CutRects* cut = d.n_cut_slot >= 0 ? &cuts[d.n_cut_slot] : nullptr;
+  float val[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int iy = 2 * (pr - 2) + (q >> 1), ix = 2 * (pc - 2) + (q & 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) val[q * 3 + c] = view_input_value(d, cut, c, iy, ix);
+  }
+  val[12] = val[13] = val[14] = val[15] = 0.f;
+  uint32_t ph[8], pl[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_pack2(val[2 * i], val[2 * i + 1], ph[i], pl[i]);
+  const long long off = (((long long)v * Hs + pr) * Ws + pc) * 16;
+  uint4* dh = reinterpret_cast<uint4*>(ohi + off);
+  dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+  if (olo) {
+    uint4* dl = reinterpret_cast<uint4*>(olo + off);
+    dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+  }
+}
+
 // ---------------------------------------------------------------- Pillow-exact resampling
 constexpr int PIL_PRECISION_BITS = 32 - 8 - 2;
 
