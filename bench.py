@@ -152,8 +152,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
@@ -188,8 +188,11 @@ def main():
     B = args.batch
     n_steps_total = args.warmup + args.steps
     # every rank scores its own shard of the pool (distinct images per step; weak scaling)
-    pool = [synth.synth_image(rank * 100000 + i, H, W, 0) for i in range(B * min(n_steps_total, 4))]
-    dev_pool = [torch.from_numpy(im).cuda() for im in pool]
+    # host pool in page-locked memory (the e2e leg copies from it every step); device copy for the resident leg
+    pinned = [torch.from_numpy(synth.synth_image(rank * 100000 + i, H, W, 0)).pin_memory()
+              for i in range(B * min(n_steps_total, 4))]
+    pool = [t.numpy() for t in pinned]
+    dev_pool = [t.cuda() for t in pinned]
 
     def step_images(s):
         idx = [(s * B + j) % len(pool) for j in range(B)]
@@ -241,6 +244,11 @@ def main():
 
     # ---------------- end-to-end run through the public API with host buffers
     barrier()
+    for s in range(min(2, args.warmup)):  # warm the host-buffer path (pinned staging, first-touch)
+        random.seed(1000 + s)
+        api.score_images(eng, [pool[i] for i in step_images(s)], AUGS, chunk=B)
+    barrier()
+    t_wall = time.time()
     eng.event_record(2)
     for s in range(args.warmup, n_steps_total):
         idx = step_images(s)
@@ -248,7 +256,8 @@ def main():
         api.score_images(eng, [pool[i] for i in idx], AUGS, chunk=B)
     eng.event_record(3)
     barrier()
-    ms_e2e = eng.event_elapsed_ms(2, 3)
+    t_wall = time.time() - t_wall
+    ms_e2e = max(eng.event_elapsed_ms(2, 3), 1000.0 * t_wall)  # the call is synchronous: wall clock bounds it too
     if world > 1:
         t = torch.tensor([ms_e2e], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

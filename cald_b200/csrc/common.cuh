@@ -77,7 +77,8 @@ struct ConvParams {
   int tap_dy[9], tap_dx[9], tap_img[9];  // per tap: input offset and image-index offset (phase planes)
   int a_lo_img;        // image-index offset of the lo plane in the A tensor map
   // ---- tiling
-  int tw, th;          // spatial tile, tw * th == 128
+  int tw, th;          // spatial tile, tw * th <= 128 (rows beyond tw*th of the MMA tile are dead)
+  int a_bytes;         // bytes one A-tile TMA box delivers per plane = th * tw * 128
   int tiles_x, tiles_y;
   int n_blocks;        // ceil(Cout / BLOCK_N)
   int num_tiles;
@@ -100,6 +101,8 @@ struct ConvParams {
   int kc;              // chunked accumulation: k-blocks per TMEM accumulation chunk
   int tma_store;       // 1: epilogue stages 64-channel groups in smem and stores them with TMA (NHWC bf16 outputs)
   int c_lo_img;        // image-index offset of the lo plane in the output tensor map
+  int res_kb;          // residual-as-MMA: extra identity k-blocks per tile (BLOCK_N / 64), else 0
+  int r_lo_img;        // image-index offset of the lo plane in the residual tensor map
 };
 
 // ATen nearest-neighbour source index (UpSampleKernel: nearest_idx), float scale.

@@ -98,12 +98,20 @@ inline CUtensorMap make_tmap_strided(const void* base, uint64_t d0, uint64_t d1,
   return tm;
 }
 
+// Spatial tile (th x tw <= 128 output pixels).  TMA boxes need not be powers of two, so pick the shape that wastes
+// the fewest of the 128 MMA rows (e.g. 3 x 42 = 126 rows on an 84-wide map instead of 4 x 32 with 14 % padding).
 inline void choose_tile(int H, int W, int& th, int& tw) {
-  static const int cand[8][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {64, 2}, {1, 128}, {128, 1}};
-  long long best = -1;
-  for (auto& c : cand) {
-    long long area = (long long)((H + c[0] - 1) / c[0]) * c[0] * ((W + c[1] - 1) / c[1]) * c[1];
-    if (best < 0 || area < best) { best = area; th = c[0]; tw = c[1]; }
+  double best = -1;
+  th = 8; tw = 16;
+  for (int w = 1; w <= 128 && w <= W; ++w) {
+    int h = 128 / w;
+    if (h > H) h = H;
+    if (h < 1) continue;
+    long long tiles = (long long)((H + h - 1) / h) * ((W + w - 1) / w);
+    double eff = (double)H * W / ((double)tiles * 128.0);
+    // tie-break towards squarer tiles (better halo reuse in L2 for 3x3 taps)
+    double score = eff - 1e-6 * std::abs(h - w);
+    if (score > best) { best = score; th = h; tw = w; }
   }
 }
 
@@ -115,6 +123,22 @@ struct ConvEngine {
   bool split = true;       // false: single-pass bf16 (hi plane only)
   int force_block_n = 0;   // 0 = auto
   bool use_tma_store = true;  // false: always use the direct (per-thread) store epilogue
+  bool use_res_mma = true;    // false: add residuals in the epilogue registers
+  bool force_pow2_tiles = false;  // true: restrict spatial tiles to power-of-two shapes
+  bf16* ident[3] = {nullptr, nullptr, nullptr};  // identity B tiles for BLOCK_N = 64 / 128 / 256
+  // I[j][n][k] = (n == j*64 + k): block j routes residual channels [j*64, j*64+64) to accumulator columns
+  const bf16* identity(int BN) {
+    int slot = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
+    if (!ident[slot]) {
+      std::vector<bf16> h((size_t)(BN / 64) * BN * 64);
+      for (int j = 0; j < BN / 64; ++j)
+        for (int n = 0; n < BN; ++n)
+          for (int k = 0; k < 64; ++k) h[((size_t)j * BN + n) * 64 + k] = __float2bfloat16(n == j * 64 + k ? 1.f : 0.f);
+      CALD_CUDA_CHECK(cudaMalloc((void**)&ident[slot], h.size() * sizeof(bf16)));
+      CALD_CUDA_CHECK(cudaMemcpy(ident[slot], h.data(), h.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    }
+    return ident[slot];
+  }
   int kc = 8;              // split mode: k-blocks (of 64) per accumulation chunk; 0 = never chunk
   long long launches = 0;  // kernels launched (bench's gpu_launches)
   double flops = 0;        // algorithmic 2*MAC of the launches
@@ -147,8 +171,8 @@ struct ConvEngine {
   }
 
   template <int BN, bool SP, bool CH>
-  void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const ConvParams& p,
-                 cudaStream_t st) {
+  void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+                 const CUtensorMap& ti, const ConvParams& p, cudaStream_t st) {
     using Cfg = IgemmCfg<BN, SP>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -158,7 +182,7 @@ struct ConvEngine {
     }
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
-    igemm_tc_kernel<BN, SP, CH><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, p);
+    igemm_tc_kernel<BN, SP, CH><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tr, ti, p);
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
     CALD_CUDA_CHECK(cudaGetLastError());
   }
@@ -207,6 +231,14 @@ struct ConvEngine {
           }
       }
       choose_tile(p.H, p.W, p.th, p.tw);
+      if (force_pow2_tiles) {
+        static const int cand[8][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {64, 2}, {1, 128}, {128, 1}};
+        long long bestA = -1;
+        for (auto& c : cand) {
+          long long area = (long long)((p.H + c[0] - 1) / c[0]) * c[0] * ((p.W + c[1] - 1) / c[1]) * c[1];
+          if (bestA < 0 || area < bestA) { bestA = area; p.th = c[0]; p.tw = c[1]; }
+        }
+      }
       p.tiles_x = (p.W + p.tw - 1) / p.tw;
       p.tiles_y = (p.H + p.th - 1) / p.th;
       p.a_lo_img = in.phases * in.n;
@@ -225,6 +257,7 @@ struct ConvEngine {
     }
     int BN = force_block_n ? force_block_n : (w.cout_pad <= 64 ? 64 : 128);
     if (!force_block_n && !split && w.cout_pad % 256 == 0) BN = 256;
+    p.a_bytes = p.th * p.tw * 128;
     p.n_blocks = (w.cout_pad + BN - 1) / BN;
     p.num_tiles = p.n_blocks * p.tiles_x * p.tiles_y * p.n_img;
     p.bias = w.bias;
@@ -286,17 +319,33 @@ struct ConvEngine {
         p.c_lo_img = 1;
       }
     }
-    const int num_kb = w.taps * (w.cin / 64);
+    // residual on the tensor core (see igemm.cuh): same-shape shortcut, channel count a multiple of BLOCK_N
+    CUtensorMap tr = tb, ti = tb;
+    p.res_kb = 0;
+    if (use_res_mma && o.res_mode == RES_SAME && p.tma_store && (w.cout_pad % BN) == 0 && o.res->c == w.cout_pad &&
+        o.res->split == split && o.res->phases == 1) {
+      if (spatial) {
+        tr = make_tmap(o.res->hi, o.res->c, o.res->w, o.res->h, (uint64_t)o.res->n * (split ? 2 : 1), p.tw, p.th);
+        p.r_lo_img = o.res->n;
+      } else {
+        tr = make_tmap(o.res->hi, o.res->c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);
+        p.r_lo_img = 1;
+      }
+      ti = make_tmap(identity(BN), 64, (uint64_t)(BN / 64) * BN, 1, 1, BN, 1);
+      p.res_kb = BN / 64;
+      p.res_mode = RES_NONE;  // the epilogue no longer sees a residual
+    }
+    const int num_kb = w.taps * (w.cin / 64) + p.res_kb;
     const bool chunked = split && kc > 0 && num_kb > kc && BN <= 128;
     p.kc = chunked ? kc : num_kb;
     if (split) {
-      if (BN == 64) { if (chunked) launch_tc<64, true, true>(ta, tb, tc, p, st); else launch_tc<64, true, false>(ta, tb, tc, p, st); }
-      else if (BN == 128) { if (chunked) launch_tc<128, true, true>(ta, tb, tc, p, st); else launch_tc<128, true, false>(ta, tb, tc, p, st); }
-      else launch_tc<256, true, false>(ta, tb, tc, p, st);
+      if (BN == 64) { if (chunked) launch_tc<64, true, true>(ta, tb, tc, tr, ti, p, st); else launch_tc<64, true, false>(ta, tb, tc, tr, ti, p, st); }
+      else if (BN == 128) { if (chunked) launch_tc<128, true, true>(ta, tb, tc, tr, ti, p, st); else launch_tc<128, true, false>(ta, tb, tc, tr, ti, p, st); }
+      else launch_tc<256, true, false>(ta, tb, tc, tr, ti, p, st);
     } else {
-      if (BN == 64) launch_tc<64, false, false>(ta, tb, tc, p, st);
-      else if (BN == 128) launch_tc<128, false, false>(ta, tb, tc, p, st);
-      else launch_tc<256, false, false>(ta, tb, tc, p, st);
+      if (BN == 64) launch_tc<64, false, false>(ta, tb, tc, tr, ti, p, st);
+      else if (BN == 128) launch_tc<128, false, false>(ta, tb, tc, tr, ti, p, st);
+      else launch_tc<256, false, false>(ta, tb, tc, tr, ti, p, st);
     }
   }
 };

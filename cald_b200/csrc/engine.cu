@@ -69,9 +69,12 @@ struct cald_engine {
   std::vector<float> last_per_view;
   int last_A = 0;
   cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint8_t* pinned = nullptr;   // staging for pageable caller buffers (H2D from pinned memory runs at link speed)
+  size_t pinned_cap = 0;
 
   ~cald_engine() {
     if (d_lut) cudaFree(d_lut);
+    if (pinned) cudaFreeHost(pinned);
     for (auto& kv : pil_cache) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
     auto fw = [](ConvW& w) { free_conv_weight(w); };
     fw(stem); fw(rpn_conv); fw(rpn_out); fw(fc6); fw(fc7); fw(pred);
@@ -658,6 +661,43 @@ void detect_views(cald_engine* e, const std::vector<HostView>& views, const CutR
   }
 }
 
+uint8_t* pil_resize_device(cald_engine* e, const uint8_t* src, int h, int w, int oh, int ow, int filter);
+}  // namespace
+
+// stage-level entry point (include/cald_b200_ops.h); needs no weights
+extern "C" int cald_op_aug_image(int kind, const uint8_t* img, int h, int w, uint8_t* out, int* out_h, int* out_w) {
+  try {
+    std::unique_ptr<cald_engine> e(new cald_engine());
+    memset(&e->cfg, 0, sizeof(e->cfg));
+    CALD_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    e->arena.init((size_t)64 << 20);
+    uint8_t* d = (uint8_t*)e->arena.alloc((size_t)h * w * 3);
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d, img, (size_t)h * w * 3, cudaMemcpyHostToDevice, e->st));
+    uint8_t* r = nullptr;
+    int oh = h, ow = w;
+    if (kind == CALD_AUG_SMALLER_RESIZE) {
+      ow = (int)(w * 0.8); oh = (int)(h * 0.8);
+      r = pil_resize_device(e.get(), d, h, w, oh, ow, 0);
+    } else if (kind == CALD_AUG_ROTATION) {
+      RotateGeom rg = pil_rotate_geom(w, h, 5.0);
+      uint8_t* t = (uint8_t*)e->arena.alloc((size_t)rg.nh * rg.nw * 3);
+      pil_rotate_nearest_kernel<<<dim3((rg.nw + 127) / 128, rg.nh), 128, 0, e->st>>>(d, t, w, h, rg);
+      r = pil_resize_device(e.get(), t, rg.nh, rg.nw, h, w, 1);
+    } else {
+      throw std::runtime_error("cald_op_aug_image: kind must be 2 (smaller_resize) or 3 (rotation)");
+    }
+    CALD_CUDA_CHECK(cudaMemcpyAsync(out, r, (size_t)oh * ow * 3, cudaMemcpyDeviceToHost, e->st));
+    CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
+    *out_h = oh; *out_w = ow;
+    return 0;
+  } catch (const std::exception& ex) {
+    g_create_err = ex.what();
+    cudaGetLastError();
+    return -1;
+  }
+}
+
+namespace {
 // Pillow-exact resize of a device u8 image (horizontal pass then vertical pass).
 uint8_t* pil_resize_device(cald_engine* e, const uint8_t* src, int h, int w, int oh, int ow, int filter) {
   Arena& ar = e->arena;
@@ -862,10 +902,31 @@ DeviceImages upload_images(cald_engine* e, int n, const uint8_t* const* images, 
   for (int i = 0; i < n; ++i) { off[i] = total; total += ((size_t)hs[i] * ws[i] * 3 + 255) & ~(size_t)255; }
   d.slab = (uint8_t*)e->arena.alloc(total);
   d.ptr.resize(n);
-  for (int i = 0; i < n; ++i) {
-    CALD_CUDA_CHECK(cudaMemcpyAsync(d.slab + off[i], images[i], (size_t)hs[i] * ws[i] * 3, cudaMemcpyHostToDevice, e->st));
-    d.ptr[i] = d.slab + off[i];
+  // caller buffers that are not page-locked are gathered into the engine's pinned slab first: one CPU memcpy, then
+  // a single link-speed DMA instead of n driver-staged pageable copies
+  bool all_pinned = true;
+  for (int i = 0; i < n && all_pinned; ++i) {
+    cudaPointerAttributes at;
+    cudaError_t ce = cudaPointerGetAttributes(&at, images[i]);
+    if (ce != cudaSuccess) { cudaGetLastError(); all_pinned = false; break; }
+    all_pinned = (at.type == cudaMemoryTypeHost);
   }
+  if (all_pinned) {
+    for (int i = 0; i < n; ++i)
+      CALD_CUDA_CHECK(cudaMemcpyAsync(d.slab + off[i], images[i], (size_t)hs[i] * ws[i] * 3, cudaMemcpyHostToDevice, e->st));
+  } else {
+    if (e->pinned_cap < total) {
+      CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
+      if (e->pinned) cudaFreeHost(e->pinned);
+      CALD_CUDA_CHECK(cudaMallocHost((void**)&e->pinned, total));
+      e->pinned_cap = total;
+    } else {
+      CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));  // the previous upload must have left the slab
+    }
+    for (int i = 0; i < n; ++i) memcpy(e->pinned + off[i], images[i], (size_t)hs[i] * ws[i] * 3);
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d.slab, e->pinned, total, cudaMemcpyHostToDevice, e->st));
+  }
+  for (int i = 0; i < n; ++i) d.ptr[i] = d.slab + off[i];
   return d;
 }
 

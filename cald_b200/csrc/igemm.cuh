@@ -133,7 +133,8 @@ __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& 
 template <int BLOCK_N, bool SPLIT, bool CHUNKED>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ ConvParams p) {
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                const __grid_constant__ CUtensorMap tmI, const __grid_constant__ ConvParams p) {
   using Cfg = IgemmCfg<BLOCK_N, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
@@ -153,6 +154,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmI) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -179,7 +182,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_holder;
 
   const int k_chunks = p.Cin / IG_BLOCK_K;
-  const int num_kb = p.taps * k_chunks;
+  const int conv_kb = p.taps * k_chunks;
+  // Residual add on the tensor core: the shortcut tensor is streamed through the same TMA pipeline as extra
+  // k-blocks and multiplied by a 64-wide identity (R_hi*I + R_lo*I is exact), so the epilogue never waits on
+  // strided residual loads.  res_kb = BLOCK_N / 64 for such layers, else 0.
+  const int num_kb = conv_kb + p.res_kb;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -190,12 +197,22 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int nb, img, y0, x0;
         tile_coords(p, tile, nb, img, y0, x0);
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / k_chunks;
-          const int c0 = (kb - tap * k_chunks) * IG_BLOCK_K;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
-          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          if (kb >= conv_kb) {
+            const int j = kb - conv_kb;
+            const int rc = nb * BLOCK_N + j * 64;
+            mbar_expect_tx(fb, (SPLIT ? 2 : 1) * p.a_bytes + Cfg::B_BYTES);
+            tma_load_4d(sa, &tmR, fb, rc, x0, y0, img);
+            tma_load_4d(sa + Cfg::A_BYTES, &tmI, fb, 0, j * BLOCK_N, 0, 0);
+            if (SPLIT) tma_load_4d(sa + Cfg::A_BYTES + Cfg::B_BYTES, &tmR, fb, rc, x0, y0, img + p.r_lo_img);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          const int tap = kb / k_chunks;
+          const int c0 = (kb - tap * k_chunks) * IG_BLOCK_K;
+          mbar_expect_tx(fb, (SPLIT ? 2 : 1) * (p.a_bytes + Cfg::B_BYTES));
           const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap], ai = img + p.tap_img[tap];
           const int bk = tap * p.Cin + c0, bn = nb * BLOCK_N;
           tma_load_4d(sa, &tmA, fb, c0, ax, ay, ai);
@@ -237,7 +254,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
             const uint64_t ko = (uint64_t)((k * IG_UMMA_K * 2) >> 4);  // advance start address inside the swizzle row
-            if (SPLIT) {
+            if (kb >= conv_kb) {
+              // residual k-block: D += R_lo * I + R_hi * I
+              if (SPLIT) tcgen05_mma_bf16(d, a_lo + ko, b_hi + ko, idesc, (kin | k) != 0);
+              tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, SPLIT ? 1u : (uint32_t)((kin | k) != 0));
+            } else if (SPLIT) {
               // small cross terms first, dominant term last
               tcgen05_mma_bf16(d, a_lo + ko, b_hi + ko, idesc, (kin | k) != 0);
               tcgen05_mma_bf16(d, a_hi + ko, b_lo + ko, idesc, 1);
@@ -270,7 +291,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int nb, img, y0, x0;
       tile_coords(p, tile, nb, img, y0, x0);
       const int y = y0 + row / p.tw, x = x0 + row % p.tw;
-      const bool valid = (y < p.H) && (x < p.W);
+      const bool valid = (row < p.th * p.tw) && (y < p.H) && (x < p.W);
       long long orow = 0, rrow = 0;
       if (valid) {
         orow = out_row_offset(p, img, y, x);

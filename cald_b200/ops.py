@@ -36,3 +36,19 @@ def conv2d(x_nhwc, weight_oihw, bias=None, stride=1, relu=False, res=None, res_m
     check_ops(lib().cald_op_conv2d(_p(x), n, h, wd, cin, _p(w), _p(b), cout, k, stride, int(relu), _p(r), res_mode,
                                    rh, rw, prec, impl, int(phase_out), block_n, kc, _p(out)))
     return out
+
+
+def aug_image(kind, img_u8):
+    """Device Pillow-exact augmentation image: kind 2 = smaller_resize (0.8, BILINEAR), 3 = rotation (5 deg)."""
+    img = np.ascontiguousarray(img_u8, dtype=np.uint8)
+    h, w = img.shape[:2]
+    out = np.zeros((h * w * 3,), dtype=np.uint8)
+    oh, ow = ctypes.c_int(0), ctypes.c_int(0)
+    L = lib()
+    rc = L.cald_op_aug_image(kind, img.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), h, w,
+                             out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), ctypes.byref(oh), ctypes.byref(ow))
+    if rc != 0:
+        L.cald_last_error.restype = ctypes.c_char_p
+        L.cald_last_error.argtypes = [ctypes.c_void_p]
+        raise RuntimeError(L.cald_last_error(None).decode())
+    return out[:oh.value * ow.value * 3].reshape(oh.value, ow.value, 3)
