@@ -178,8 +178,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from cald_b200 import api, synth
-    from cald_b200.engine import Engine, PREC_BF16, PREC_BF16X3, AUG_ORDER
-    kinds = [k for n, k in AUG_ORDER if n in AUGS]
+    from cald_b200.engine import Engine, PREC_BF16, PREC_BF16X3, expand_augs
+    kinds = expand_augs(AUGS)
     eng = Engine(depth=50, num_classes=NUM_CLASSES, min_size=MIN_SIZE, max_size=MAX_SIZE, device=local_rank,
                  precision=PREC_BF16 if args.precision == "bf16" else PREC_BF16X3,
                  max_views_per_pass=args.batch * len(AUGS))

@@ -15,7 +15,6 @@ from . import engine as _eng
 
 _AUG_WHITELIST = ['flip', 'multi_ga', 'color_adjust', 'color_swap', 'multi_color_adjust', 'multi_sp', 'cut_out',
                   'multi_cut_out', 'multi_resize', 'larger_resize', 'smaller_resize', 'rotation', 'ga', 'sp']
-_ENGINE_AUGS = dict(_eng.AUG_ORDER)
 
 # the reference reads a module-global ``args`` (cald_train.py:220, 254); mirror it as module state
 bp = 1.3
@@ -26,18 +25,15 @@ _engine_cache = {}
 
 
 def _aug_kinds(augs):
-    """Reference order (cald_train.py:123-183), restricted to what the engine implements."""
+    """Reference names -> (kind, param) views in reference order (cald_train.py:123-183)."""
     for a in augs:
         if a not in _AUG_WHITELIST:
             print('{} is not in the pre-set augmentations!'.format(a))  # cald_train.py:95
-    kinds = []
-    for name, kind in _eng.AUG_ORDER:
-        if name in augs:
-            kinds.append(kind)
-    unsupported = [a for a in augs if a in _AUG_WHITELIST and a not in _ENGINE_AUGS]
+    unsupported = [a for a in augs if a in _AUG_WHITELIST and a not in _eng.SUPPORTED_AUGS]
     if unsupported:
+        # colour augmentations (cald_helper.py:56-69); the reference's own 'multi_color_adjust' raises NameError
         raise NotImplementedError("augmentations not implemented by the B200 engine yet: %s" % unsupported)
-    return kinds
+    return _eng.expand_augs(augs)
 
 
 def _model_config(task_model, num_cls):
@@ -71,20 +67,38 @@ def _to_u8(image):
     return np.ascontiguousarray(a)
 
 
+def _draw_noise(images, views):
+    """torch CPU-generator draws in the order the reference makes them (cald_helper.py:74, 80): per image, per
+    noise view: torch.randn(image.size()) for GaussianNoise, torch.rand(image.size()) for SaltPepperNoise."""
+    import torch
+    planes = []
+    for im in images:
+        size = (3, im.shape[0], im.shape[1])
+        for kind, _ in views:
+            if kind == _eng.AUG_GAUSS:
+                planes.append(torch.randn(size).numpy())
+            elif kind == _eng.AUG_SALTPEPPER:
+                planes.append(torch.rand(size).numpy())
+    return planes
+
+
 def score_images(eng, images, augs, chunk=64):
-    """Score u8 images with an existing engine; consumes python's global ``random`` stream exactly as
-    cald_helper.cutout would (4 uniforms per try, data-dependent number of tries)."""
-    kinds = _aug_kinds(augs)
-    needs_rng = _eng.AUG_CUTOUT in kinds
+    """Score u8 images with an existing engine.  Consumes python's global ``random`` stream exactly as
+    cald_helper.cutout would (4 uniforms per try, data-dependent number of tries) and torch's global CPU
+    generator exactly as GaussianNoise / SaltPepperNoise would."""
+    views = _aug_kinds(augs)
+    n_cut = sum(1 for k, _ in views if k == _eng.AUG_CUTOUT)
+    has_noise = any(k in _eng.NOISE_KINDS for k, _ in views)
     cons_all, cls_all = [], []
     for pos in range(0, len(images), chunk):
         batch = images[pos:pos + chunk]
         u = None
-        if needs_rng:
+        if n_cut:
             state = random.getstate()
-            u = np.array([random.random() for _ in range(200 * len(batch))], dtype=np.float64)
-        cons, cls, used = eng.score(batch, kinds, bp, u)
-        if needs_rng:
+            u = np.array([random.random() for _ in range(200 * n_cut * len(batch))], dtype=np.float64)
+        noise = _draw_noise(batch, views) if has_noise else None
+        cons, cls, used = eng.score(batch, views, bp, u, noise)
+        if n_cut:
             random.setstate(state)
             for _ in range(used):
                 random.random()

@@ -9,7 +9,7 @@
 namespace cald {
 
 constexpr int REF_CAP = 50;     // cald_train.py:110-113: at most 50 reference boxes survive the sub-sampling
-enum { AUG_FLIP = 0, AUG_CUTOUT = 1, AUG_RESIZE = 2, AUG_ROTATE = 3, AUG_IDENT = 4 };
+enum { AUG_FLIP = 0, AUG_CUTOUT = 1, AUG_RESIZE = 2, AUG_ROTATE = 3, AUG_IDENT = 4 };  // AUG_IDENT: boxes unchanged
 
 struct RefSet {                 // per image, device
   int* n;                       // [B] number of reference rows (<= 50, duplicates allowed)
@@ -71,58 +71,62 @@ __global__ void class_max_kernel(DetOut det, int det_cap, int ncls1, const int* 
 // data-dependent number of draws: image b starts where image b-1 stopped.  `u` are raw random.random() doubles
 // drawn by the host from the saved generator state; consumed[0] returns how many were used so the host can advance
 // the real generator by exactly that amount.  random.uniform(a, b) = a + (b - a) * random().
-__global__ void cutout_kernel(const RefSet ref, const int* __restrict__ img_hw /*[B][2]*/, int B, int cut_num,
-                              const double* __restrict__ u, int n_u, CutRects* __restrict__ cuts,
-                              int* __restrict__ consumed) {
+__global__ void cutout_kernel(const RefSet ref, const int* __restrict__ img_hw /*[B][2]*/, int B, int n_cut,
+                              const int* __restrict__ cut_nums /*[n_cut]*/, const double* __restrict__ u, int n_u,
+                              CutRects* __restrict__ cuts /*[B][n_cut]*/, int* __restrict__ consumed) {
   __shared__ float s_max[32];
-  int cursor = 0;
+  int cursor = consumed[0];
   for (int b = 0; b < B; ++b) {
     const int n = ref.n[b];
     const double H = (double)img_hw[b * 2], W = (double)img_hw[b * 2 + 1];
-    int count = 0;
-    if (threadIdx.x == 0) cuts[b].n = 0;
-    if (n == 0) continue;  // the reference breaks out before augmenting (cald_train.py:118-121)
-    for (int t = 0; t < 50 && count < cut_num; ++t) {
-      if (cursor + 4 > n_u) break;
-      const double ch = 0.05 * H + (0.2 * H - 0.05 * H) * u[cursor + 0];
-      const double cw = 0.05 * W + (0.2 * W - 0.05 * W) * u[cursor + 1];
-      const double left = 0.0 + ((W - cw) - 0.0) * u[cursor + 2];
-      const double right = left + cw;
-      const double top = 0.0 + ((H - ch) - 0.0) * u[cursor + 3];
-      const double bottom = top + ch;
-      cursor += 4;
-      const float cl = (float)(int)left, ct = (float)(int)top, cr = (float)(int)right, cb = (float)(int)bottom;
-      float best = -INFINITY;
-      bool has_nan = false;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        float4 bx = ref.boxes[b * REF_CAP + i];
-        float ix = fmaxf(fminf(cr, bx.z) - fmaxf(cl, bx.x), 0.f);
-        float iy = fmaxf(fminf(cb, bx.w) - fmaxf(ct, bx.y), 0.f);
-        float ratio = (ix * iy) / ((bx.z - bx.x) * (bx.w - bx.y));
-        if (ratio != ratio) has_nan = true;
-        best = fmaxf(best, ratio);
-      }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-      has_nan = __any_sync(0xffffffffu, has_nan);
-      if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = has_nan ? NAN : best;
-      __syncthreads();
-      float m = -INFINITY;
-      bool nan = false;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { float q = s_max[w]; if (q != q) nan = true; m = fmaxf(m, q); }
-      __syncthreads();
-      // torch .max() propagates NaN; NaN > 0.4 and NaN < 0.1 are both False -> accepted (as in the reference)
-      bool reject = !nan && (m > 0.4f || m < 0.1f);
-      if (reject) continue;
-      if (threadIdx.x == 0) {
-        int k = cuts[b].n;
-        if (k < MAX_CUT) {
-          cuts[b].rect[k][0] = (int)left; cuts[b].rect[k][1] = (int)top;
-          cuts[b].rect[k][2] = (int)right; cuts[b].rect[k][3] = (int)bottom;
-          cuts[b].n = k + 1;
+    for (int ci = 0; ci < n_cut; ++ci) {
+      CutRects* cr = &cuts[b * n_cut + ci];
+      const int cut_num = cut_nums[ci];
+      int count = 0;
+      if (threadIdx.x == 0) cr->n = 0;
+      if (n == 0) continue;  // the reference breaks out before augmenting (cald_train.py:118-121)
+      for (int t = 0; t < 50 && count < cut_num; ++t) {
+        if (cursor + 4 > n_u) break;
+        const double ch = 0.05 * H + (0.2 * H - 0.05 * H) * u[cursor + 0];
+        const double cw = 0.05 * W + (0.2 * W - 0.05 * W) * u[cursor + 1];
+        const double left = 0.0 + ((W - cw) - 0.0) * u[cursor + 2];
+        const double right = left + cw;
+        const double top = 0.0 + ((H - ch) - 0.0) * u[cursor + 3];
+        const double bottom = top + ch;
+        cursor += 4;
+        const float cl = (float)(int)left, ct = (float)(int)top, crr = (float)(int)right, cb = (float)(int)bottom;
+        float best = -INFINITY;
+        bool has_nan = false;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          float4 bx = ref.boxes[b * REF_CAP + i];
+          float ix = fmaxf(fminf(crr, bx.z) - fmaxf(cl, bx.x), 0.f);
+          float iy = fmaxf(fminf(cb, bx.w) - fmaxf(ct, bx.y), 0.f);
+          float ratio = (ix * iy) / ((bx.z - bx.x) * (bx.w - bx.y));
+          if (ratio != ratio) has_nan = true;
+          best = fmaxf(best, ratio);
         }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        has_nan = __any_sync(0xffffffffu, has_nan);
+        if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = has_nan ? NAN : best;
+        __syncthreads();
+        float m = -INFINITY;
+        bool nan = false;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { float q = s_max[w]; if (q != q) nan = true; m = fmaxf(m, q); }
+        __syncthreads();
+        // torch .max() propagates NaN; NaN > 0.4 and NaN < 0.1 are both False -> accepted (as in the reference)
+        bool reject = !nan && (m > 0.4f || m < 0.1f);
+        if (reject) continue;
+        if (threadIdx.x == 0) {
+          int k = cr->n;
+          if (k < MAX_CUT) {
+            cr->rect[k][0] = (int)left; cr->rect[k][1] = (int)top;
+            cr->rect[k][2] = (int)right; cr->rect[k][3] = (int)bottom;
+            cr->n = k + 1;
+          }
+        }
+        count++;
       }
-      count++;
     }
   }
   if (threadIdx.x == 0) consumed[0] = cursor;

@@ -559,6 +559,9 @@ struct HostView {
   int sh, sw;
   int flip;
   int cut_slot;
+  const float* noise = nullptr;  // device planes [3][sh][sw]
+  int noise_mode = 0;
+  float n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 };
 
 void resized_hw(const cald_config& c, int h, int w, int& rh, int& rw) {
@@ -578,7 +581,8 @@ void detect_views(cald_engine* e, const std::vector<HostView>& views, const CutR
   for (int i = 0; i < V; ++i) {
     int rh, rw;
     resized_hw(e->cfg, views[i].sh, views[i].sw, rh, rw);
-    vd[i] = ViewDesc{views[i].src, views[i].sh, views[i].sw, rh, rw, views[i].flip, views[i].cut_slot};
+    vd[i] = ViewDesc{views[i].src, views[i].sh, views[i].sw, rh, rw, views[i].flip, views[i].cut_slot,
+                     views[i].noise, views[i].noise_mode, views[i].n0, views[i].n1, views[i].n2, views[i].n3};
     hw[i * 2] = rh; hw[i * 2 + 1] = rw;
     ratio[i * 2] = (float)((double)views[i].sh / (double)rh);
     ratio[i * 2 + 1] = (float)((double)views[i].sw / (double)rw);
@@ -761,9 +765,24 @@ void rotate_box_geom(int w, int h, double angle_deg, int rot_w, int rot_h, AugGe
   g.sy = (float)((double)rot_h / h);
 }
 
+// min / max of a device u8 image as to_tensor values (salt / pepper of cald_helper.py:81-82)
+__global__ void u8_minmax_kernel(const uint8_t* __restrict__ img, long long n, int* __restrict__ out /*[2] min,max*/) {
+  int lo = 255, hi = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int v = img[i];
+    lo = min(lo, v); hi = max(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&out[0], lo); atomicMax(&out[1], hi); }
+}
+
 void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const int* hs, const int* ws,
-                 const std::vector<int>& augs, double bp, const double* d_u, int n_u, int* d_cursor,
-                 double* out_cons, double* out_cls) {
+                 const std::vector<cald_aug>& augs, double bp, const double* d_u, int n_u, int* d_cursor,
+                 const float* const* d_noise /* [B][n_noise] device planes */, double* out_cons, double* out_cls) {
   Arena& ar = e->arena;
   cudaStream_t st = e->st;
   const int A = (int)augs.size();
@@ -784,35 +803,64 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
   ref_prepare_kernel<<<B, 64, 0, st>>>(ref.det, dc, e->d_lut, rs);
   class_max_kernel<<<B, 128, ncls1 * 4, st>>>(ref.det, dc, ncls1, e->d_lut, 1, d_cls);
   e->launches += 2;
-  CutRects* d_cuts = (CutRects*)ar.alloc((size_t)B * sizeof(CutRects));
-  CALD_CUDA_CHECK(cudaMemsetAsync(d_cuts, 0, (size_t)B * sizeof(CutRects), st));
+  // ---------------- cutout rectangles: every cutout view consumes the caller's RNG stream in view order
+  std::vector<int> cut_nums;
+  int n_noise = 0;
+  for (const cald_aug& a : augs) {
+    if (a.kind == CALD_AUG_CUTOUT) cut_nums.push_back((int)a.param);
+    if (a.kind == CALD_AUG_GAUSS || a.kind == CALD_AUG_SALTPEPPER) n_noise++;
+  }
+  const int n_cut = (int)cut_nums.size();
+  for (int c : cut_nums) if (c < 1 || c > MAX_CUT) throw std::runtime_error("cutout: cut_num must be 1..4");
+  CutRects* d_cuts = (CutRects*)ar.alloc((size_t)B * std::max(1, n_cut) * sizeof(CutRects));
+  CALD_CUDA_CHECK(cudaMemsetAsync(d_cuts, 0, (size_t)B * std::max(1, n_cut) * sizeof(CutRects), st));
   std::vector<int> img_hw(B * 2);
   for (int b = 0; b < B; ++b) { img_hw[b * 2] = hs[b]; img_hw[b * 2 + 1] = ws[b]; }
   int* d_img_hw = (int*)ar.alloc(B * 8);
   CALD_CUDA_CHECK(cudaMemcpyAsync(d_img_hw, img_hw.data(), B * 8, cudaMemcpyHostToDevice, st));
-  bool has_cut = false;
-  for (int a : augs) has_cut |= (a == CALD_AUG_CUTOUT);
-  if (has_cut) {
-    cutout_kernel<<<1, 64, 0, st>>>(rs, d_img_hw, B, 2, d_u, n_u, d_cuts, d_cursor);
+  if (n_cut) {
+    int* d_cn = (int*)ar.alloc(n_cut * 4);
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d_cn, cut_nums.data(), n_cut * 4, cudaMemcpyHostToDevice, st));
+    cutout_kernel<<<1, 64, 0, st>>>(rs, d_img_hw, B, n_cut, d_cn, d_u, n_u, d_cuts, d_cursor);
     KLAUNCH(e);
+    ar.free(d_cn);
+  }
+  // salt / pepper values need each image's min / max
+  std::vector<int> h_mm(B * 2, 0);
+  bool has_sp = false;
+  for (const cald_aug& a : augs) has_sp |= (a.kind == CALD_AUG_SALTPEPPER);
+  if (has_sp) {
+    int* d_mm = (int*)ar.alloc(B * 8);
+    std::vector<int> init(B * 2);
+    for (int b = 0; b < B; ++b) { init[b * 2] = 255; init[b * 2 + 1] = 0; }
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d_mm, init.data(), B * 8, cudaMemcpyHostToDevice, st));
+    for (int b = 0; b < B; ++b) {
+      u8_minmax_kernel<<<64, 256, 0, st>>>(d_images[b], (long long)hs[b] * ws[b] * 3, d_mm + b * 2);
+      KLAUNCH(e);
+    }
+    CALD_CUDA_CHECK(cudaMemcpyAsync(h_mm.data(), d_mm, B * 8, cudaMemcpyDeviceToHost, st));
+    CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+    ar.free(d_mm);
   }
   // ---------------- augmented views
   std::vector<HostView> av((size_t)B * A);
   std::vector<AugGeom> geom((size_t)B * A);
   std::vector<uint8_t*> temps;
   for (int b = 0; b < B; ++b) {
+    int cut_i = 0, noise_i = 0;
     for (int a = 0; a < A; ++a) {
       AugGeom& g = geom[(size_t)b * A + a];
       memset(&g, 0, sizeof(g));
       g.w = (float)ws[b]; g.h = (float)hs[b];
       HostView hv{d_images[b], hs[b], ws[b], 0, -1};
-      switch (augs[a]) {
+      const double prm = augs[a].param;
+      switch (augs[a].kind) {
         case CALD_AUG_FLIP: g.kind = AUG_FLIP; hv.flip = 1; break;
-        case CALD_AUG_CUTOUT: g.kind = AUG_CUTOUT; hv.cut_slot = b; break;
-        case CALD_AUG_SMALLER_RESIZE: {
+        case CALD_AUG_CUTOUT: g.kind = AUG_IDENT; hv.cut_slot = b * n_cut + cut_i++; break;
+        case CALD_AUG_RESIZE: {
           g.kind = AUG_RESIZE;
-          g.ratio = 0.8f;
-          int ow = (int)(ws[b] * 0.8), oh = (int)(hs[b] * 0.8);
+          g.ratio = (float)prm;
+          int ow = (int)(ws[b] * prm), oh = (int)(hs[b] * prm);
           uint8_t* t = pil_resize_device(e, d_images[b], hs[b], ws[b], oh, ow, 0);
           temps.push_back(t);
           hv.src = t; hv.sh = oh; hv.sw = ow;
@@ -820,7 +868,7 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
         }
         case CALD_AUG_ROTATION: {
           g.kind = AUG_ROTATE;
-          RotateGeom rg = pil_rotate_geom(ws[b], hs[b], 5.0);
+          RotateGeom rg = pil_rotate_geom(ws[b], hs[b], prm);
           uint8_t* r = (uint8_t*)ar.alloc((size_t)rg.nh * rg.nw * 3);
           pil_rotate_nearest_kernel<<<dim3((rg.nw + 127) / 128, rg.nh), 128, 0, st>>>(d_images[b], r, ws[b], hs[b], rg);
           KLAUNCH(e);
@@ -828,7 +876,24 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
           ar.free(r);
           temps.push_back(t);
           hv.src = t;
-          rotate_box_geom(ws[b], hs[b], 5.0, rg.nw, rg.nh, g);
+          rotate_box_geom(ws[b], hs[b], prm, rg.nw, rg.nh, g);
+          break;
+        }
+        case CALD_AUG_GAUSS:
+        case CALD_AUG_SALTPEPPER: {
+          g.kind = AUG_IDENT;
+          if (!d_noise) throw std::runtime_error("noise augmentation requested but no noise planes were passed");
+          hv.noise = d_noise[(size_t)b * n_noise + noise_i++];
+          if (augs[a].kind == CALD_AUG_GAUSS) {
+            hv.noise_mode = 1;
+            hv.n0 = (float)prm;  // torch: randn * std (python scalar -> fp32) / 255.0
+          } else {
+            hv.noise_mode = 2;
+            hv.n0 = (float)(prm / 2.0);
+            hv.n1 = (float)(1.0 - prm / 2.0);
+            hv.n2 = (float)h_mm[b * 2 + 1] / 255.0f;  // salt = max(image)
+            hv.n3 = (float)h_mm[b * 2] / 255.0f;      // pepper = min(image)
+          }
           break;
         }
         default: throw std::runtime_error("unsupported augmentation kind");
@@ -1043,14 +1108,18 @@ int cald_load_weights(cald_engine* e, int n, const char* const* names, const flo
 }
 
 static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, bool on_device, const int* heights,
-                      const int* widths, int n_augs, const int* aug_kinds, double bp, const double* rng_uniforms,
-                      int n_uniforms, int* uniforms_consumed, double* out_consistency, double* out_cls) {
+                      const int* widths, int n_augs, const cald_aug* aug_list, double bp, const double* rng_uniforms,
+                      int n_uniforms, int* uniforms_consumed, const float* const* noise, double* out_consistency,
+                      double* out_cls) {
   API_TRY(e)
   check_ready(e);
   e->arena.reset();
   e->last_per_view.clear();
   e->last_A = n_augs;
-  std::vector<int> augs(aug_kinds, aug_kinds + n_augs);
+  std::vector<cald_aug> augs(aug_list, aug_list + n_augs);
+  int n_noise = 0;
+  for (const cald_aug& a : augs) if (a.kind == CALD_AUG_GAUSS || a.kind == CALD_AUG_SALTPEPPER) n_noise++;
+  if (n_noise && !noise) throw std::runtime_error("noise augmentation requested but noise == NULL");
   double* d_u = nullptr;
   int* d_cursor = (int*)e->arena.alloc(4);
   CALD_CUDA_CHECK(cudaMemsetAsync(d_cursor, 0, 4, e->st));
@@ -1066,14 +1135,26 @@ static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, 
     const int B = std::min(Bmax, n_images - pos);
     DeviceImages di;
     const uint8_t* const* dptr;
+    std::vector<const float*> nz;
+    std::vector<float*> nz_owned;
     if (on_device) {
       dptr = imgs + pos;
+      for (int i = 0; i < B * n_noise; ++i) nz.push_back(noise[(size_t)pos * n_noise + i]);
     } else {
       di = upload_images(e, B, imgs + pos, heights + pos, widths + pos);
       dptr = di.ptr.data();
+      for (int b = 0; b < B; ++b)
+        for (int j = 0; j < n_noise; ++j) {
+          size_t bytes = (size_t)heights[pos + b] * widths[pos + b] * 3 * 4;
+          float* d = (float*)e->arena.alloc(bytes);
+          CALD_CUDA_CHECK(cudaMemcpyAsync(d, noise[(size_t)(pos + b) * n_noise + j], bytes, cudaMemcpyHostToDevice, e->st));
+          nz.push_back(d);
+          nz_owned.push_back(d);
+        }
     }
     score_chunk(e, B, dptr, heights + pos, widths + pos, augs, bp, d_u, n_uniforms, d_cursor,
-                out_consistency + pos, out_cls + (size_t)pos * (e->C - 1));
+                n_noise ? nz.data() : nullptr, out_consistency + pos, out_cls + (size_t)pos * (e->C - 1));
+    for (float* d : nz_owned) e->arena.free(d);
     if (di.slab) e->arena.free(di.slab);
   }
   int consumed = 0;
@@ -1084,16 +1165,17 @@ static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, 
 }
 
 int cald_score(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
-               int n_augs, const int* aug_kinds, double bp, const double* rng_uniforms, int n_uniforms,
-               int* uniforms_consumed, double* out_consistency, double* out_cls) {
-  return score_impl(e, n_images, images, false, heights, widths, n_augs, aug_kinds, bp, rng_uniforms, n_uniforms,
-                    uniforms_consumed, out_consistency, out_cls);
+               int n_augs, const cald_aug* augs, double bp, const double* rng_uniforms, int n_uniforms,
+               int* uniforms_consumed, const float* const* noise, double* out_consistency, double* out_cls) {
+  return score_impl(e, n_images, images, false, heights, widths, n_augs, augs, bp, rng_uniforms, n_uniforms,
+                    uniforms_consumed, noise, out_consistency, out_cls);
 }
 int cald_score_device(cald_engine* e, int n_images, const uint8_t* const* d_images, const int* heights,
-                      const int* widths, int n_augs, const int* aug_kinds, double bp, const double* rng_uniforms,
-                      int n_uniforms, int* uniforms_consumed, double* out_consistency, double* out_cls) {
-  return score_impl(e, n_images, d_images, true, heights, widths, n_augs, aug_kinds, bp, rng_uniforms, n_uniforms,
-                    uniforms_consumed, out_consistency, out_cls);
+                      const int* widths, int n_augs, const cald_aug* augs, double bp, const double* rng_uniforms,
+                      int n_uniforms, int* uniforms_consumed, const float* const* d_noise, double* out_consistency,
+                      double* out_cls) {
+  return score_impl(e, n_images, d_images, true, heights, widths, n_augs, augs, bp, rng_uniforms, n_uniforms,
+                    uniforms_consumed, d_noise, out_consistency, out_cls);
 }
 
 int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,

@@ -20,6 +20,10 @@ struct ViewDesc {
   int rh, rw;           // size after the detector's resize
   int flip;             // horizontal flip of the source
   int n_cut_slot;       // index into the device cutout-rect table, or -1
+  // noise views (cald_helper.py:72-85): planes [3][sh][sw] drawn by the caller from torch's CPU generator
+  const float* noise;   // null for the other views
+  int noise_mode;       // 1: x + noise * std / 255     2: salt (noise < lo) / pepper (noise > hi)
+  float n0, n1, n2, n3; // mode 1: std            mode 2: lo, hi, salt value, pepper value
 };
 
 struct CutRects {       // per image
@@ -38,6 +42,15 @@ __device__ __forceinline__ float src_pixel(const ViewDesc& d, const CutRects* cu
   }
   int sx = d.flip ? (d.sw - 1 - x) : x;
   v = zero ? 0.f : ((float)d.src[((long long)y * d.sw + sx) * 3 + c] / 255.f);
+  if (d.noise) {
+    const float nz = d.noise[((long long)c * d.sh + y) * d.sw + x];
+    if (d.noise_mode == 1) {
+      v = v + (nz * d.n0) / 255.0f;
+    } else {
+      if (nz < d.n0) v = d.n2;
+      if (nz > d.n1) v = d.n3;
+    }
+  }
   return (v - mean) / stdv;
 }
 

@@ -10,11 +10,47 @@ from ._lib import CaldError, lib
 ARCH_FRCNN, ARCH_RETINANET = 0, 1
 PREC_BF16X3, PREC_BF16 = 0, 1
 CONV_TCGEN05, CONV_SIMT = 0, 1
-AUG_FLIP, AUG_CUTOUT, AUG_SMALLER_RESIZE, AUG_ROTATION = 0, 1, 2, 3
+AUG_FLIP, AUG_CUTOUT, AUG_RESIZE, AUG_ROTATION, AUG_GAUSS, AUG_SALTPEPPER = 0, 1, 2, 3, 4, 5
+AUG_SMALLER_RESIZE = AUG_RESIZE
+NOISE_KINDS = (AUG_GAUSS, AUG_SALTPEPPER)
 
-# reference augmentation names (cald_train.py:93-94) -> engine kinds, in the order get_uncertainty appends them
-AUG_ORDER = (("flip", AUG_FLIP), ("cut_out", AUG_CUTOUT), ("smaller_resize", AUG_SMALLER_RESIZE),
-             ("rotation", AUG_ROTATION))
+
+class Aug(ctypes.Structure):
+    """cald_aug: one augmented view = (kind, the reference's per-call argument)."""
+    _fields_ = [("kind", c_int), ("param", c_double)]
+
+
+def expand_augs(names):
+    """Reference augmentation names (cald_train.py:93-94) -> list of (kind, param) views in the exact order
+    get_uncertainty appends them (cald_train.py:123-183), with the reference's literal arguments."""
+    v = []
+    if 'flip' in names:
+        v.append((AUG_FLIP, 0.0))
+    if 'ga' in names:
+        v.append((AUG_GAUSS, 16.0))
+    if 'multi_ga' in names:
+        v += [(AUG_GAUSS, float(i * 8)) for i in range(1, 7)]
+    if 'sp' in names:
+        v.append((AUG_SALTPEPPER, 0.1))
+    if 'multi_sp' in names:
+        v += [(AUG_SALTPEPPER, i * 0.05) for i in range(1, 7)]
+    if 'cut_out' in names:
+        v.append((AUG_CUTOUT, 2.0))
+    if 'multi_cut_out' in names:
+        v += [(AUG_CUTOUT, float(i)) for i in range(1, 5)]
+    if 'multi_resize' in names:
+        v += [(AUG_RESIZE, i * 0.1) for i in range(7, 10)]
+    if 'larger_resize' in names:
+        v.append((AUG_RESIZE, 1.2))
+    if 'smaller_resize' in names:
+        v.append((AUG_RESIZE, 0.8))
+    if 'rotation' in names:
+        v.append((AUG_ROTATION, 5.0))
+    return v
+
+
+SUPPORTED_AUGS = ('flip', 'ga', 'multi_ga', 'sp', 'multi_sp', 'cut_out', 'multi_cut_out', 'multi_resize',
+                  'larger_resize', 'smaller_resize', 'rotation')
 
 
 class Config(ctypes.Structure):
@@ -103,42 +139,53 @@ class Engine:
                                               shp.ctypes.data_as(POINTER(c_int64))))
 
     # ------------------------------------------------------------------ scoring
-    def score(self, images, aug_kinds, bp=1.3, uniforms=None):
-        """-> (consistency float64[n], cls float64[n, C-1], uniforms_consumed)."""
+    @staticmethod
+    def _aug_array(views):
+        views = [(v, 0.0) if isinstance(v, int) else v for v in views]
+        return (Aug * max(1, len(views)))(*[Aug(int(k), float(p)) for k, p in views]), len(views)
+
+    def score(self, images, views, bp=1.3, uniforms=None, noise=None):
+        """views: list of (kind, param) (see expand_augs); noise: list of float32 [3,H,W] planes, one per
+        (image, noise view) in image-major order.  -> (consistency float64[n], cls float64[n, C-1], consumed)."""
         imgs, ptrs, hs, ws = _u8_list(images)
         n = len(imgs)
-        a = (c_int * len(aug_kinds))(*aug_kinds)
+        a, na = self._aug_array(views)
         u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
         nu = 0 if u is None else u.size
+        nz_keep, nz_ptrs = [], None
+        if noise:
+            nz_keep = [np.ascontiguousarray(z, dtype=np.float32) for z in noise]
+            nz_ptrs = (POINTER(c_float) * len(nz_keep))(*[z.ctypes.data_as(POINTER(c_float)) for z in nz_keep])
         consumed = c_int(0)
         cons = np.zeros(n, dtype=np.float64)
         cls = np.zeros((n, self.num_classes - 1), dtype=np.float64)
         self._L.cald_score.argtypes = [c_void_p, c_int, POINTER(POINTER(c_uint8)), POINTER(c_int), POINTER(c_int),
-                                       c_int, POINTER(c_int), c_double, POINTER(c_double), c_int, POINTER(c_int),
-                                       POINTER(c_double), POINTER(c_double)]
-        self._check(self._L.cald_score(self._h, n, ptrs, hs, ws, len(aug_kinds), a, float(bp),
+                                       c_int, POINTER(Aug), c_double, POINTER(c_double), c_int, POINTER(c_int),
+                                       POINTER(POINTER(c_float)), POINTER(c_double), POINTER(c_double)]
+        self._check(self._L.cald_score(self._h, n, ptrs, hs, ws, na, a, float(bp),
                                        None if u is None else u.ctypes.data_as(POINTER(c_double)), nu,
-                                       ctypes.byref(consumed), cons.ctypes.data_as(POINTER(c_double)),
+                                       ctypes.byref(consumed), nz_ptrs, cons.ctypes.data_as(POINTER(c_double)),
                                        cls.ctypes.data_as(POINTER(c_double))))
         return cons, cls, consumed.value
 
-    def score_device(self, d_ptrs, hs, ws, aug_kinds, bp=1.3, uniforms=None):
+    def score_device(self, d_ptrs, hs, ws, views, bp=1.3, uniforms=None):
         """Like score() but images are already resident in HBM (list of device pointers)."""
         n = len(d_ptrs)
         ptrs = (POINTER(c_uint8) * n)(*[ctypes.cast(int(p), POINTER(c_uint8)) for p in d_ptrs])
         chs = (c_int * n)(*hs)
         cws = (c_int * n)(*ws)
-        a = (c_int * len(aug_kinds))(*aug_kinds)
+        a, na = self._aug_array(views)
         u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
         consumed = c_int(0)
         cons = np.zeros(n, dtype=np.float64)
         cls = np.zeros((n, self.num_classes - 1), dtype=np.float64)
         self._L.cald_score_device.argtypes = [c_void_p, c_int, POINTER(POINTER(c_uint8)), POINTER(c_int),
-                                              POINTER(c_int), c_int, POINTER(c_int), c_double, POINTER(c_double),
-                                              c_int, POINTER(c_int), POINTER(c_double), POINTER(c_double)]
-        self._check(self._L.cald_score_device(self._h, n, ptrs, chs, cws, len(aug_kinds), a, float(bp),
+                                              POINTER(c_int), c_int, POINTER(Aug), c_double, POINTER(c_double),
+                                              c_int, POINTER(c_int), POINTER(POINTER(c_float)), POINTER(c_double),
+                                              POINTER(c_double)]
+        self._check(self._L.cald_score_device(self._h, n, ptrs, chs, cws, na, a, float(bp),
                                               None if u is None else u.ctypes.data_as(POINTER(c_double)),
-                                              0 if u is None else u.size, ctypes.byref(consumed),
+                                              0 if u is None else u.size, ctypes.byref(consumed), None,
                                               cons.ctypes.data_as(POINTER(c_double)),
                                               cls.ctypes.data_as(POINTER(c_double))))
         return cons, cls, consumed.value

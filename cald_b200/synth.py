@@ -50,9 +50,13 @@ def planted_frcnn_weights(depth=50, num_classes=21, seed=0, cls_gain=2.5, bg_bia
         else:  # FrozenBN weight
             w[name] = rs.uniform(0.8, 1.2, shp).astype(np.float32)
     # keep the residual stack O(1): damp the last BN of every bottleneck
+    # (R50 keeps the literal 0.35 its fixtures were generated with; deeper bodies get the gain that gives the same
+    #  total variance growth (1 + g^2)^n_blocks over the residual stack)
+    nblk = sum(arch.RESNET_BLOCKS[depth])
+    g3 = 0.35 if depth == 50 else float(np.sqrt((1.0 + 0.35 ** 2) ** (16.0 / nblk) - 1.0))
     for name in shapes:
         if name.endswith(".bn3.weight"):
-            w[name] *= np.float32(0.35)
+            w[name] *= np.float32(g3)
         if name.endswith(".downsample.1.weight"):
             w[name] *= np.float32(0.8)
     for name in shapes:

@@ -27,8 +27,20 @@ typedef struct cald_engine cald_engine;
 enum { CALD_ARCH_FRCNN = 0, CALD_ARCH_RETINANET = 1 };
 enum { CALD_PREC_BF16X3 = 0, CALD_PREC_BF16 = 1 };
 enum { CALD_CONV_TCGEN05 = 0, CALD_CONV_SIMT = 1 };
-/* augmentation kinds, in the order cald_train.py:123-183 appends them */
-enum { CALD_AUG_FLIP = 0, CALD_AUG_CUTOUT = 1, CALD_AUG_SMALLER_RESIZE = 2, CALD_AUG_ROTATION = 3 };
+/* augmentation kinds (cald/cald_helper.py); `param` carries the reference's per-call argument */
+enum {
+  CALD_AUG_FLIP = 0,        /* HorizontalFlip                      cald_helper.py:23-30   */
+  CALD_AUG_CUTOUT = 1,      /* cutout(cut_num = param)             cald_helper.py:88-132  */
+  CALD_AUG_RESIZE = 2,      /* resize(ratio = param), PIL BILINEAR cald_helper.py:47-53   */
+  CALD_AUG_ROTATION = 3,    /* rotate(angle = param degrees)       cald_helper.py:135-223 */
+  CALD_AUG_GAUSS = 4,       /* GaussianNoise(std = param)          cald_helper.py:72-75   */
+  CALD_AUG_SALTPEPPER = 5   /* SaltPepperNoise(prob = param)       cald_helper.py:78-85   */
+};
+#define CALD_AUG_SMALLER_RESIZE CALD_AUG_RESIZE
+typedef struct {
+  int kind;
+  double param;
+} cald_aug;
 
 typedef struct {
   int arch;                  /* CALD_ARCH_*: FRCNN_Feature (frcnn_la.py:146) */
@@ -65,14 +77,17 @@ int cald_load_weights(cald_engine* e, int n, const char* const* names, const flo
 
 /* get_uncertainty over n images (cald_train.py:91-231).
  * images[i]: u8 RGB, HWC contiguous, heights[i] x widths[i]  (what F.to_tensor(PIL) reads, cald_train.py:107).
- * aug_kinds: the augmentation list in reference order; bp: args.bp (cald_train.py:220, default 1.3).
+ * augs: the augmented views in the order cald_train.py:123-183 appends them; bp: args.bp (cald_train.py:220, 1.3).
+ * noise: for GAUSS / SALTPEPPER views, host fp32 planes [3][H][W] drawn by the caller from torch's CPU generator
+ *   (torch.randn / torch.rand of image.size(), cald_helper.py:74,80), one pointer per (image, noise view) in
+ *   image-major order; NULL when no such view is requested.
  * rng_uniforms: raw random.random() doubles from python's generator (4 per cutout try, drawn in stream order);
  *   uniforms_consumed returns how many the scoring consumed so the caller can advance its generator exactly as
  *   cald_helper.cutout would have (cald_helper.py:106-114).
  * out_consistency[n]: np.mean(consistency_aug) per image; out_cls[n][num_classes-1]: mean class-max vector. */
 int cald_score(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
-               int n_augs, const int* aug_kinds, double bp, const double* rng_uniforms, int n_uniforms,
-               int* uniforms_consumed, double* out_consistency, double* out_cls);
+               int n_augs, const cald_aug* augs, double bp, const double* rng_uniforms, int n_uniforms,
+               int* uniforms_consumed, const float* const* noise, double* out_consistency, double* out_cls);
 
 /* One detector forward per image: task_model([F.to_tensor(img)])[0] (frcnn_la.py:131-141).
  * Outputs are fixed-capacity [n][cap] with counts[n]; cap = box_detections_per_img.
@@ -102,8 +117,9 @@ int cald_event_elapsed_ms(cald_engine* e, int slot_a, int slot_b, float* ms);
 
 /* Same as cald_score but the u8 images already live in device memory (device pointers). */
 int cald_score_device(cald_engine* e, int n_images, const uint8_t* const* d_images, const int* heights,
-                      const int* widths, int n_augs, const int* aug_kinds, double bp, const double* rng_uniforms,
-                      int n_uniforms, int* uniforms_consumed, double* out_consistency, double* out_cls);
+                      const int* widths, int n_augs, const cald_aug* augs, double bp, const double* rng_uniforms,
+                      int n_uniforms, int* uniforms_consumed, const float* const* d_noise, double* out_consistency,
+                      double* out_cls);
 
 #ifdef __cplusplus
 }

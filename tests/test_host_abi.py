@@ -72,9 +72,13 @@ def test_aug_order_follows_reference():
     from cald_b200 import api
     from cald_b200 import engine as E
     assert api._aug_kinds(['rotation', 'flip', 'cut_out', 'smaller_resize']) == \
-        [E.AUG_FLIP, E.AUG_CUTOUT, E.AUG_SMALLER_RESIZE, E.AUG_ROTATION]
+        [(E.AUG_FLIP, 0.0), (E.AUG_CUTOUT, 2.0), (E.AUG_RESIZE, 0.8), (E.AUG_ROTATION, 5.0)]
+    v = api._aug_kinds(['multi_resize', 'ga', 'multi_cut_out', 'sp'])
+    assert v == [(E.AUG_GAUSS, 16.0), (E.AUG_SALTPEPPER, 0.1)] + [(E.AUG_CUTOUT, float(i)) for i in range(1, 5)] + \
+        [(E.AUG_RESIZE, i * 0.1) for i in range(7, 10)]
+    assert len(api._aug_kinds(['multi_ga', 'multi_sp'])) == 12
     with pytest.raises(NotImplementedError):
-        api._aug_kinds(['ga'])
+        api._aug_kinds(['color_swap'])
 
 
 def test_shard_partition_covers_pool_in_order():
