@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=1)
+    ap.add_argument("--layers", default=None, help="write the per-layer conv timing table (TSV) to this path")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -234,6 +235,14 @@ def main():
     ms = eng.event_elapsed_ms(0, 1)
     k1, _ = eng.counters()
     conv_ms, conv_launches, conv_flops = eng.profile_read()
+    if args.layers and rank == 0:
+        rows = sorted(eng.profile_layers(), key=lambda r: -r[2])
+        with open(args.layers, "w") as f:
+            f.write("layer\tcount\tms_total\tus_per_launch\tTFLOPs_algorithmic\tGBs_algorithmic\tshare\n")
+            for sig, cnt, lms, gf, mb in rows:
+                f.write("%s\t%d\t%.3f\t%.1f\t%.1f\t%.0f\t%.3f\n" % (
+                    sig, cnt, lms, 1000.0 * lms / cnt, gf / lms if lms else 0, mb / lms if lms else 0,
+                    lms / conv_ms if conv_ms else 0))
     eng.profile(False)
     clocks = sampler.stop()
     if world > 1:

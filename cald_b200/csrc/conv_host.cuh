@@ -3,6 +3,8 @@
 #include <cstring>
 #include <vector>
 #include <cstdlib>
+#include <map>
+#include <string>
 #include "igemm.cuh"
 
 namespace cald {
@@ -148,6 +150,11 @@ struct ConvEngine {
   size_t ev_used = 0;
   double prof_flops = 0;
   long long prof_launches = 0;
+  // per-launch description (aligned with the event pairs) and the per-layer aggregate of the last drain
+  struct LayerRec { char sig[96]; double flops, bytes; };
+  struct LayerAgg { long long count = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::vector<LayerRec> recs;
+  std::map<std::string, LayerAgg> layer_agg;
   cudaEvent_t next_event() {
     if (ev_used == ev.size()) {
       cudaEvent_t e;
@@ -159,14 +166,21 @@ struct ConvEngine {
   // sum of kernel durations (ms) since the last call; the stream must be idle
   double drain_profile(double* fl, long long* n) {
     double ms = 0;
+    layer_agg.clear();
     for (size_t i = 0; i + 1 < ev_used; i += 2) {
       float t = 0;
       CALD_CUDA_CHECK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
       ms += t;
+      if (i / 2 < recs.size()) {
+        const LayerRec& r = recs[i / 2];
+        LayerAgg& a = layer_agg[r.sig];
+        a.count++; a.ms += t; a.flops += r.flops; a.bytes += r.bytes;
+      }
     }
     if (fl) *fl = prof_flops;
     if (n) *n = prof_launches;
     ev_used = 0; prof_flops = 0; prof_launches = 0;
+    recs.clear();
     return ms;
   }
 
@@ -338,6 +352,23 @@ struct ConvEngine {
     const int num_kb = w.taps * (w.cin / 64) + p.res_kb;
     const bool chunked = split && kc > 0 && num_kb > kc && BN <= 128;
     p.kc = chunked ? kc : num_kb;
+    if (profiling) {
+      // algorithmic HBM bytes: every operand element once at its stored width (activations 4 B split / 2 B bf16)
+      const double eb = split ? 4.0 : 2.0;
+      const double pix = (double)p.n_img * p.H * p.W;
+      double by = pix * (o.stem_window ? 16.0 : (double)w.cin) * eb * (o.stride == 2 ? 1.0 : 1.0) +
+                  (double)w.cout_pad * w.taps * w.cin * eb;
+      if (o.out_f32) by += pix * out.c * 4.0;
+      if (!o.no_bf16_out) by += pix * out.c * eb;
+      if (o.res_mode != RES_NONE) by += (o.res_mode == RES_NEAREST ? 0.25 : 1.0) * pix * w.cout_pad * eb;
+      LayerRec r;
+      snprintf(r.sig, sizeof(r.sig), "%dx%dx%d k%d%s cin%d cout%d BN%d%s%s%s%s", p.n_img, p.H, p.W,
+               o.stem_window ? 7 : (w.taps == 9 ? 3 : 1), o.stride == 2 ? "s2" : "", o.stem_window ? 3 : w.cin, w.cout, BN,
+               chunked ? " chunk" : "", p.res_kb ? " resmma" : (o.res_mode != RES_NONE ? " res" : ""),
+               p.tma_store ? " tma" : " direct", o.relu ? " relu" : "");
+      r.flops = fl; r.bytes = by;
+      recs.push_back(r);
+    }
     if (split) {
       if (BN == 64) { if (chunked) launch_tc<64, true, true>(ta, tb, tc, tr, ti, p, st); else launch_tc<64, true, false>(ta, tb, tc, tr, ti, p, st); }
       else if (BN == 128) { if (chunked) launch_tc<128, true, true>(ta, tb, tc, tr, ti, p, st); else launch_tc<128, true, false>(ta, tb, tc, tr, ti, p, st); }

@@ -4,6 +4,8 @@
 #include <cmath>
 #include <algorithm>
 #include <memory>
+#include <chrono>
+#include <cstdlib>
 #include "layers.cuh"
 #include "det.cuh"
 #include "pre.cuh"
@@ -69,6 +71,33 @@ struct cald_engine {
   std::vector<float> last_per_view;
   int last_A = 0;
   cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // CALD_TRACE=1: host timestamp + CUDA event at named points of a scoring call, printed at the end of the call
+  struct TracePt { const char* name; double host_us; cudaEvent_t ev; };
+  std::vector<TracePt> trace_pts;
+  std::vector<cudaEvent_t> trace_pool;
+  std::chrono::steady_clock::time_point trace_t0;
+  bool tracing = getenv("CALD_TRACE") != nullptr;
+  void trace(const char* name) {
+    if (!tracing) return;
+    if (trace_pts.empty()) trace_t0 = std::chrono::steady_clock::now();
+    cudaEvent_t ev;
+    if (trace_pts.size() < trace_pool.size()) ev = trace_pool[trace_pts.size()];
+    else { cudaEventCreate(&ev); trace_pool.push_back(ev); }
+    cudaEventRecord(ev, st);
+    trace_pts.push_back({name, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - trace_t0).count(), ev});
+  }
+  void trace_dump() {
+    if (!tracing || trace_pts.empty()) return;
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[trace]");
+    for (size_t i = 0; i < trace_pts.size(); ++i) {
+      float ms = 0;
+      if (i) cudaEventElapsedTime(&ms, trace_pts[0].ev, trace_pts[i].ev);
+      fprintf(stderr, " %s host=%.1fms gpu=%.1fms |", trace_pts[i].name, trace_pts[i].host_us / 1000.0, ms);
+    }
+    fprintf(stderr, "\n");
+    trace_pts.clear();
+  }
   uint8_t* pinned = nullptr;   // staging for pageable caller buffers (H2D from pinned memory runs at link speed)
   size_t pinned_cap = 0;
 
@@ -791,7 +820,9 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
   std::vector<HostView> rv(B);
   for (int b = 0; b < B; ++b) rv[b] = HostView{d_images[b], hs[b], ws[b], 0, -1};
   ViewSet ref = alloc_viewset(e, B);
+  e->trace("chunk_start");
   detect_views(e, rv, nullptr, ref);
+  e->trace("ref_pass_enqueued");
   // ---------------- reference sub-sample, class vectors, cutout rects, boxes in aug coordinates
   RefSet rs;
   rs.n = (int*)ar.alloc(B * 4);
@@ -910,7 +941,9 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
     aug_boxes_kernel<<<B * A, 64, 0, st>>>(rs, d_geom, A, d_augb);
     KLAUNCH(e);
     aug = alloc_viewset(e, B * A);
+    e->trace("aug_prep_enqueued");
     detect_views(e, av, d_cuts, aug);
+    e->trace("aug_pass_enqueued");
     class_max_kernel<<<B * A, 128, ncls1 * 4, st>>>(aug.det, dc, ncls1, e->d_lut, 0, d_cls + (size_t)B * ncls1);
     d_cons = (float*)ar.alloc((size_t)B * A * 4);
     ConsArgs ca;
@@ -930,6 +963,7 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
   CALD_CUDA_CHECK(cudaMemcpyAsync(h_cls.data(), d_cls, h_cls.size() * 4, cudaMemcpyDeviceToHost, st));
   CALD_CUDA_CHECK(cudaMemcpyAsync(h_ndet.data(), rs.n_det, B * 4, cudaMemcpyDeviceToHost, st));
   CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+  e->trace("results_on_host");
   for (int b = 0; b < B; ++b) {
     double* cls = out_cls + (size_t)b * ncls1;
     if (h_ndet[b] == 0 || A == 0) {
@@ -969,16 +1003,30 @@ DeviceImages upload_images(cald_engine* e, int n, const uint8_t* const* images, 
   d.ptr.resize(n);
   // caller buffers that are not page-locked are gathered into the engine's pinned slab first: one CPU memcpy, then
   // a single link-speed DMA instead of n driver-staged pageable copies
+  static const bool trace = getenv("CALD_TRACE_UPLOAD") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  };
+  auto t0 = now();
   bool all_pinned = true;
   for (int i = 0; i < n && all_pinned; ++i) {
     cudaPointerAttributes at;
     cudaError_t ce = cudaPointerGetAttributes(&at, images[i]);
     if (ce != cudaSuccess) { cudaGetLastError(); all_pinned = false; break; }
     all_pinned = (at.type == cudaMemoryTypeHost);
+    if (trace && !all_pinned) fprintf(stderr, "[upload] image %d: cudaPointerGetAttributes type %d\n", i, (int)at.type);
   }
+  auto t1 = now();
   if (all_pinned) {
     for (int i = 0; i < n; ++i)
       CALD_CUDA_CHECK(cudaMemcpyAsync(d.slab + off[i], images[i], (size_t)hs[i] * ws[i] * 3, cudaMemcpyHostToDevice, e->st));
+    if (trace) {
+      auto t2 = now();
+      CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
+      fprintf(stderr, "[upload] pinned: attr %.0f us, %d copies enqueued in %.0f us, complete after %.0f us\n", us(t0, t1), n,
+              us(t1, t2), us(t1, now()));
+    }
   } else {
     if (e->pinned_cap < total) {
       CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
@@ -988,8 +1036,13 @@ DeviceImages upload_images(cald_engine* e, int n, const uint8_t* const* images, 
     } else {
       CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));  // the previous upload must have left the slab
     }
+    auto t2 = now();
     for (int i = 0; i < n; ++i) memcpy(e->pinned + off[i], images[i], (size_t)hs[i] * ws[i] * 3);
+    auto t3 = now();
     CALD_CUDA_CHECK(cudaMemcpyAsync(d.slab, e->pinned, total, cudaMemcpyHostToDevice, e->st));
+    if (trace)
+      fprintf(stderr, "[upload] staged: attr %.0f us, sync %.0f us, memcpy %.0f us, enqueue %.0f us\n", us(t0, t1), us(t1, t2),
+              us(t2, t3), us(t3, now()));
   }
   for (int i = 0; i < n; ++i) d.ptr[i] = d.slab + off[i];
   return d;
@@ -1131,6 +1184,7 @@ static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, 
   }
   const int maxv = e->cfg.max_views_per_pass > 0 ? e->cfg.max_views_per_pass : 8;
   const int Bmax = std::max(1, maxv / std::max(1, n_augs));
+  e->trace("call_start");
   for (int pos = 0; pos < n_images; pos += Bmax) {
     const int B = std::min(Bmax, n_images - pos);
     DeviceImages di;
@@ -1161,6 +1215,7 @@ static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, 
   CALD_CUDA_CHECK(cudaMemcpyAsync(&consumed, d_cursor, 4, cudaMemcpyDeviceToHost, e->st));
   CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
   if (uniforms_consumed) *uniforms_consumed = consumed;
+  e->trace_dump();
   API_CATCH(e)
 }
 
@@ -1260,6 +1315,23 @@ int cald_profile_read(cald_engine* e, double* conv_ms, long long* conv_launches,
   if (conv_launches) *conv_launches = n;
   if (conv_flops) *conv_flops = fl;
   API_CATCH(e)
+}
+
+long long cald_profile_layers(cald_engine* e, char* buf, long long capacity) {
+  if (!e) return -1;
+  std::string s = "layer\tcount\tms\tgflop\tmbyte\n";
+  char line[256];
+  for (auto& kv : e->conv.layer_agg) {
+    snprintf(line, sizeof(line), "%s\t%lld\t%.4f\t%.3f\t%.3f\n", kv.first.c_str(), kv.second.count, kv.second.ms,
+             kv.second.flops / 1e9, kv.second.bytes / 1e6);
+    s += line;
+  }
+  if (buf && capacity > 0) {
+    size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (long long)s.size() + 1;
 }
 
 int cald_event_record(cald_engine* e, int slot) {

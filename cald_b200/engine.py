@@ -62,8 +62,16 @@ class Config(ctypes.Structure):
                 ("debug", c_int)]
 
 
+def _as_u8(im):
+    # np.ascontiguousarray was observed to copy arrays that view page-locked torch memory (31 ms per 8 images):
+    # pass anything that already is a contiguous u8 ndarray through untouched
+    if isinstance(im, np.ndarray) and im.dtype == np.uint8 and im.flags["C_CONTIGUOUS"]:
+        return im
+    return np.ascontiguousarray(im, dtype=np.uint8)
+
+
 def _u8_list(images):
-    imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+    imgs = [_as_u8(im) for im in images]
     for im in imgs:
         if im.ndim != 3 or im.shape[2] != 3:
             raise ValueError("images must be HxWx3 uint8 (RGB)")
@@ -250,6 +258,19 @@ class Engine:
         self._L.cald_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_longlong), POINTER(c_double)]
         self._check(self._L.cald_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
         return ms.value, n.value, fl.value
+
+    def profile_layers(self):
+        """Per-layer rows of the last profile_read(): list of (signature, count, ms, gflop, mbyte)."""
+        self._L.cald_profile_layers.restype = c_longlong
+        self._L.cald_profile_layers.argtypes = [c_void_p, c_char_p, c_longlong]
+        n = self._L.cald_profile_layers(self._h, None, 0)
+        buf = ctypes.create_string_buffer(int(n))
+        self._L.cald_profile_layers(self._h, buf, n)
+        rows = []
+        for line in buf.value.decode().splitlines()[1:]:
+            sig, cnt, ms, gf, mb = line.split("\t")
+            rows.append((sig, int(cnt), float(ms), float(gf), float(mb)))
+        return rows
 
     def event_record(self, slot):
         self._L.cald_event_record.argtypes = [c_void_p, c_int]

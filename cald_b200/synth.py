@@ -130,7 +130,8 @@ def synth_image(index, height, width, seed=0, n_rect=6):
         tex = rs.uniform(-25, 25, (rh // 8 + 1, rw // 8 + 1, 3))
         tex = np.repeat(np.repeat(tex, 8, 0), 8, 1)[:rh, :rw]
         img[ry:ry + rh, rx:rx + rw] = col + tex
-    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    # fancy indexing above leaves `img` in a permuted memory order; hand out a C-contiguous HWC image
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
 
 
 def synth_pool(n, height, width, seed=0, portrait_every=0):

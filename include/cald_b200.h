@@ -112,6 +112,9 @@ int cald_counters(cald_engine* e, long long* kernel_launches, double* conv_flops
  * algorithmic FLOPs since the last read.  cald_event_record/elapsed time whole regions on the same stream. */
 int cald_profile(cald_engine* e, int enable);
 int cald_profile_read(cald_engine* e, double* conv_ms, long long* conv_launches, double* conv_flops);
+/* Per-layer breakdown of the last cald_profile_read(): TSV text "layer count ms gflop mbyte" (algorithmic FLOPs and
+ * HBM bytes per distinct conv problem); returns the size needed incl. the terminator (buf may be NULL). */
+long long cald_profile_layers(cald_engine* e, char* buf, long long capacity);
 int cald_event_record(cald_engine* e, int slot /* 0..7 */);
 int cald_event_elapsed_ms(cald_engine* e, int slot_a, int slot_b, float* ms);
 
