@@ -43,17 +43,20 @@ def _model_config(task_model, num_cls):
     max_size = int(t.max_size) if t is not None else 1333
     sd = task_model.state_dict()
     depth = 101 if any(k.startswith("backbone.body.layer3.22.") for k in sd) else 50
-    return depth, min_size, max_size, sd
+    # retinanet_resnet50_fpn_cal (retinanet_cal.py:584-625) is recognised by its head keys
+    arch_id = _eng.ARCH_RETINANET if "head.classification_head.cls_logits.weight" in sd else _eng.ARCH_FRCNN
+    return depth, min_size, max_size, sd, arch_id
 
 
 def engine_for(task_model, num_cls, device=0, **kw):
     """Build (or reuse) the engine for this model object; weights are re-read on every call of
     get_uncertainty because the AL cycle retrains the model in between (cald_train.py:409-411)."""
-    depth, mn, mx, sd = _model_config(task_model, num_cls)
-    key = (depth, num_cls, mn, mx, device, tuple(sorted(kw.items())))
+    depth, mn, mx, sd, arch_id = _model_config(task_model, num_cls)
+    key = (arch_id, depth, num_cls, mn, mx, device, tuple(sorted(kw.items())))
     eng = _engine_cache.get(key)
     if eng is None:
-        eng = _eng.Engine(depth=depth, num_classes=num_cls, min_size=mn, max_size=mx, device=device, **kw)
+        eng = _eng.Engine(depth=depth, num_classes=num_cls, min_size=mn, max_size=mx, device=device,
+                          arch_id=arch_id, **kw)
         _engine_cache[key] = eng
     eng.load_state_dict(sd)
     return eng

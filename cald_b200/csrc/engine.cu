@@ -10,6 +10,7 @@
 #include "det.cuh"
 #include "pre.cuh"
 #include "cons.cuh"
+#include "ret.cuh"
 #include "../../include/cald_b200.h"
 
 using namespace cald;
@@ -62,6 +63,11 @@ struct cald_engine {
   std::vector<std::vector<Block>> layers;
   ConvW fpn_inner[4], fpn_layer[4], rpn_conv, rpn_out, fc6, fc7, pred;
   int head_ld = 0;
+  // RetinaNet (retinanet_cal.py:584-625): FPN on C3..C5 (+P6, P7), two 4-conv towers, 3x3 output convs
+  bool retina = false;
+  ConvW ret_p6, ret_p7, ret_cls_tower[4], ret_reg_tower[4], ret_cls_out, ret_reg_out;
+  int ret_per_class = 300;   // detections_per_img is applied per class (retinanet_cal.py:463)
+  int* d_overflow = nullptr; // raised by the RetinaNet post-processing when a fixed capacity is exceeded
 
   // device constants
   int* d_lut = nullptr;  // [(det_cap+1)][50]
@@ -107,6 +113,9 @@ struct cald_engine {
     for (auto& kv : pil_cache) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
     auto fw = [](ConvW& w) { free_conv_weight(w); };
     fw(stem); fw(rpn_conv); fw(rpn_out); fw(fc6); fw(fc7); fw(pred);
+    fw(ret_p6); fw(ret_p7); fw(ret_cls_out); fw(ret_reg_out);
+    for (int i = 0; i < 4; ++i) { fw(ret_cls_tower[i]); fw(ret_reg_tower[i]); }
+    if (d_overflow) cudaFree(d_overflow);
     for (int i = 0; i < 4; ++i) { fw(fpn_inner[i]); fw(fpn_layer[i]); }
     for (auto& l : layers) for (auto& b : l) { fw(b.c1); fw(b.c2); fw(b.c3); if (b.has_ds) fw(b.ds); }
     arena.destroy();
@@ -212,6 +221,25 @@ void finalize_weights(cald_engine* e) {
       e->layers[li].push_back(blk);
     }
   }
+  if (e->retina) {
+    for (int i = 0; i < 3; ++i) {
+      e->fpn_inner[i] = plain_conv(e, "backbone.fpn.inner_blocks." + std::to_string(i) + ".0");
+      e->fpn_layer[i] = plain_conv(e, "backbone.fpn.layer_blocks." + std::to_string(i) + ".0");
+    }
+    e->ret_p6 = plain_conv(e, "backbone.fpn.extra_blocks.p6");
+    e->ret_p7 = plain_conv(e, "backbone.fpn.extra_blocks.p7");
+    for (int i = 0; i < 4; ++i) {
+      e->ret_cls_tower[i] = plain_conv(e, "head.classification_head.conv." + std::to_string(2 * i));
+      e->ret_reg_tower[i] = plain_conv(e, "head.regression_head.conv." + std::to_string(2 * i));
+    }
+    e->ret_cls_out = plain_conv(e, "head.classification_head.cls_logits");
+    e->ret_reg_out = plain_conv(e, "head.regression_head.bbox_reg");
+    if (e->ret_cls_out.cout != RET_A * e->C) throw std::runtime_error("cls_logits: num_classes mismatch");
+    if (e->ret_reg_out.cout != RET_A * 4) throw std::runtime_error("bbox_reg: expected 36 output channels");
+    e->staged.clear();
+    e->weights_ready = true;
+    return;
+  }
   for (int i = 0; i < 4; ++i) {
     e->fpn_inner[i] = plain_conv(e, "backbone.fpn.inner_blocks." + std::to_string(i) + ".0");
     e->fpn_layer[i] = plain_conv(e, "backbone.fpn.layer_blocks." + std::to_string(i) + ".0");
@@ -304,12 +332,11 @@ Act conv(cald_engine* e, const Act& in, const ConvW& w, int n, int h, int wd, co
 // One forward pass over V views that share the padded input size (Hp, Wp).
 // d_views / d_cuts / d_image_hw / d_ratio live on the device.  Results go to `vs` (local view order).
 // ------------------------------------------------------------------------------------------------------------
-void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views, const CutRects* d_cuts,
-                  const int* d_image_hw, const float* d_ratio, ViewSet& vs) {
+// transform + ResNet body: fills cfeat[0..3] = C2..C5 (tv:models/resnet.py, FrozenBN folded)
+void run_body(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views, const CutRects* d_cuts, Act* cfeat) {
   cudaStream_t st = e->st;
   Arena& ar = e->arena;
   const bool split = e->split;
-  const int C = e->C, cap = e->cap;
 
   // ---- transform (normalise + resize + pad) fused with the stem's space-to-depth layout
   const int Ho = Hp / 2, Wo = Wp / 2;
@@ -343,7 +370,6 @@ void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views
   free_act(ar, x);
   x = xp;
   // ---- residual stages
-  Act cfeat[4];
   for (int li = 0; li < 4; ++li) {
     for (size_t bi = 0; bi < e->layers[li].size(); ++bi) {
       const Block& b = e->layers[li][bi];
@@ -393,6 +419,25 @@ void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views
     dbg_store_act(e, "c2", cfeat[0]); dbg_store_act(e, "c3", cfeat[1]);
     dbg_store_act(e, "c4", cfeat[2]); dbg_store_act(e, "c5", cfeat[3]);
   }
+}
+
+void forward_pass_retina(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views, const CutRects* d_cuts,
+                         const int* d_image_hw, const float* d_ratio, ViewSet& vs);
+
+void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views, const CutRects* d_cuts,
+                  const int* d_image_hw, const float* d_ratio, ViewSet& vs) {
+  if (e->retina) {
+    forward_pass_retina(e, V, Hp, Wp, d_views, d_cuts, d_image_hw, d_ratio, vs);
+    return;
+  }
+  cudaStream_t st = e->st;
+  Arena& ar = e->arena;
+  const bool split = e->split;
+  const int C = e->C, cap = e->cap;
+  ConvOpts relu_o;
+  relu_o.relu = true;
+  Act cfeat[4];
+  run_body(e, V, Hp, Wp, d_views, d_cuts, cfeat);
   // ---- FPN (tv:ops/feature_pyramid_network.py:172-221)
   Act pf[5];
   {
@@ -559,6 +604,152 @@ void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// RetinaNet forward (detection/retinanet_cal.py:492-575): body -> FPN P3..P5 + P6/P7 -> two towers + output convs on
+// every level -> per-class post-processing.  vs.scores receives one sigmoid row per DETECTION ([V][det_cap][K]).
+// ------------------------------------------------------------------------------------------------------------
+void ret_cell_anchors(int level, float out[RET_A][4]) {
+  // retinanet_cal.py:347-348 sizes; tv:anchor_utils.py:58-75 (ratio-major, scale-minor; fp32; round-half-even)
+  static const int bases[5] = {32, 64, 128, 256, 512};
+  const int x = bases[level];
+  const float scales[3] = {(float)x, (float)(int)(x * std::pow(2.0, 1.0 / 3)), (float)(int)(x * std::pow(2.0, 2.0 / 3))};
+  const float ratios[3] = {0.5f, 1.0f, 2.0f};
+  for (int r = 0; r < 3; ++r) {
+    const float hr = sqrtf(ratios[r]);
+    const float wr = 1.0f / hr;
+    for (int sidx = 0; sidx < 3; ++sidx) {
+      const float ws = wr * scales[sidx], hs = hr * scales[sidx];
+      float* o = out[r * 3 + sidx];
+      o[0] = nearbyintf(-ws / 2.f); o[1] = nearbyintf(-hs / 2.f);
+      o[2] = nearbyintf(ws / 2.f);  o[3] = nearbyintf(hs / 2.f);
+    }
+  }
+}
+
+Act relu_act(cald_engine* e, const Act& in) {
+  Act o = alloc_act(e->arena, in.n, in.h, in.w, in.c, in.split, 1);
+  long long n = (long long)in.plane_elems();
+  relu_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(in.hi, in.lo(), o.hi, o.lo(), n);
+  CALD_CUDA_CHECK(cudaGetLastError());
+  KLAUNCH(e);
+  return o;
+}
+
+void forward_pass_retina(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views, const CutRects* d_cuts,
+                         const int* d_image_hw, const float* d_ratio, ViewSet& vs) {
+  cudaStream_t st = e->st;
+  Arena& ar = e->arena;
+  const bool split = e->split;
+  const int K = e->C;
+  ConvOpts relu_o;
+  relu_o.relu = true;
+  Act cfeat[4];
+  run_body(e, V, Hp, Wp, d_views, d_cuts, cfeat);
+  free_act(ar, cfeat[0]);  // C2 is not a returned layer (returned_layers=[2,3,4], retinanet_cal.py:618)
+  // ---- FPN on C3..C5, then P6 = conv3x3/2(P5), P7 = conv3x3/2(relu(P6))
+  Act pf[5];
+  {
+    ConvOpts o;
+    Act last = conv(e, cfeat[3], e->fpn_inner[2], V, cfeat[3].h, cfeat[3].w, o);
+    pf[2] = conv(e, last, e->fpn_layer[2], V, last.h, last.w, o);
+    for (int i = 1; i >= 0; --i) {
+      ConvOpts oi;
+      oi.res_mode = RES_NEAREST;
+      oi.res = &last;
+      Act inner = conv(e, cfeat[i + 1], e->fpn_inner[i], V, cfeat[i + 1].h, cfeat[i + 1].w, oi);
+      free_act(ar, last);
+      last = inner;
+      pf[i] = conv(e, last, e->fpn_layer[i], V, last.h, last.w, o);
+    }
+    free_act(ar, last);
+    for (int i = 1; i < 4; ++i) free_act(ar, cfeat[i]);
+    ConvOpts s2;
+    s2.stride = 2;
+    Act ph = phase_split(ar, pf[2], st);
+    e->launches += split ? 2 : 1;
+    pf[3] = conv(e, ph, e->ret_p6, V, (pf[2].h + 1) / 2, (pf[2].w + 1) / 2, s2);
+    free_act(ar, ph);
+    Act r6 = relu_act(e, pf[3]);
+    Act ph6 = phase_split(ar, r6, st);
+    e->launches += split ? 2 : 1;
+    free_act(ar, r6);
+    pf[4] = conv(e, ph6, e->ret_p7, V, (pf[3].h + 1) / 2, (pf[3].w + 1) / 2, s2);
+    free_act(ar, ph6);
+  }
+  if (e->cfg.debug) {
+    const char* nm[5] = {"p3", "p4", "p5", "p6", "p7"};
+    for (int i = 0; i < 5; ++i) dbg_store_act(e, nm[i], pf[i]);
+  }
+  // ---- heads (retinanet_cal.py:135-151, 225-241): fp32 NHWC outputs, channel a*K + k / a*4 + j
+  RetLevels L;
+  memset(&L, 0, sizeof(L));
+  L.K = K;
+  float* cls_raw[5];
+  float* reg_raw[5];
+  int off = 0;
+  for (int l = 0; l < 5; ++l) {
+    const int h = pf[l].h, w = pf[l].w;
+    for (int tower = 0; tower < 2; ++tower) {
+      const ConvW* tw = tower == 0 ? e->ret_cls_tower : e->ret_reg_tower;
+      const ConvW& ow = tower == 0 ? e->ret_cls_out : e->ret_reg_out;
+      Act t = conv(e, pf[l], tw[0], V, h, w, relu_o);
+      for (int i = 1; i < 4; ++i) {
+        Act t2 = conv(e, t, tw[i], V, h, w, relu_o);
+        free_act(ar, t);
+        t = t2;
+      }
+      float* raw = (float*)ar.alloc((size_t)V * h * w * ow.cout_pad * 4);
+      Act dummy;
+      dummy.n = V; dummy.h = h; dummy.w = w; dummy.c = ow.cout_pad; dummy.split = split; dummy.hi = nullptr;
+      ConvOpts o;
+      o.out_f32 = raw;
+      o.no_bf16_out = true;
+      e->conv.run(t, ow, dummy, o, st);
+      KLAUNCH(e);
+      free_act(ar, t);
+      (tower == 0 ? cls_raw : reg_raw)[l] = raw;
+    }
+    RetLevel& lv = L.lv[l];
+    lv.cls = cls_raw[l]; lv.reg = reg_raw[l];
+    lv.h = h; lv.w = w;
+    lv.ld_cls = e->ret_cls_out.cout_pad; lv.ld_reg = e->ret_reg_out.cout_pad;
+    lv.stride_h = Hp / h; lv.stride_w = Wp / w;
+    ret_cell_anchors(l, lv.base);
+    lv.n = h * w * RET_A;
+    lv.off = off;
+    off += lv.n;
+    if (e->cfg.debug) {
+      std::string nm = "cls" + std::to_string(l);
+      dbg_store_f32(e, nm.c_str(), cls_raw[l], (size_t)V * h * w * lv.ld_cls);
+      nm = "reg" + std::to_string(l);
+      dbg_store_f32(e, nm.c_str(), reg_raw[l], (size_t)V * h * w * lv.ld_reg);
+    }
+  }
+  L.total = off;
+  for (int l = 0; l < 5; ++l) free_act(ar, pf[l]);
+  // ---- postprocess_detections (retinanet_cal.py:402-490) + transform.postprocess
+  {
+    const int pc = e->ret_per_class;
+    unsigned long long* keys = (unsigned long long*)ar.alloc((size_t)V * K * RET_CAND * 8);
+    int* counts = (int*)ar.alloc((size_t)V * K * 4);
+    RetKept kept;
+    kept.boxes = (float4*)ar.alloc((size_t)V * K * pc * 16);
+    kept.scores = (float*)ar.alloc((size_t)V * K * pc * 4);
+    kept.anchor = (int*)ar.alloc((size_t)V * K * pc * 4);
+    kept.count = (int*)ar.alloc((size_t)V * K * 4);
+    CALD_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)V * K * 4, st));
+    ret_candidates_kernel<<<dim3(e->conv.num_sms * 8, V), 256, 0, st>>>(L, e->cfg.box_score_thresh, keys, counts,
+                                                                        e->d_overflow);
+    ret_class_nms_kernel<<<dim3(K, V), 1024, RET_NMS_SMEM, st>>>(L, keys, counts, d_image_hw, 1e-2f,
+                                                                 (double)e->cfg.box_nms_thresh, pc, kept);
+    ret_gather_kernel<<<V, 1024, (K + 1) * 4, st>>>(L, kept, pc, d_ratio, e->det_cap, vs.det, vs.scores, e->d_overflow);
+    CALD_CUDA_CHECK(cudaGetLastError());
+    e->launches += 3;
+    ar.free(keys); ar.free(counts); ar.free(kept.boxes); ar.free(kept.scores); ar.free(kept.anchor); ar.free(kept.count);
+  }
+  for (int l = 0; l < 5; ++l) { ar.free(cls_raw[l]); ar.free(reg_raw[l]); }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 ViewSet alloc_viewset(cald_engine* e, int V) {
   Arena& ar = e->arena;
   ViewSet vs;
@@ -613,8 +804,13 @@ void detect_views(cald_engine* e, const std::vector<HostView>& views, const CutR
     vd[i] = ViewDesc{views[i].src, views[i].sh, views[i].sw, rh, rw, views[i].flip, views[i].cut_slot,
                      views[i].noise, views[i].noise_mode, views[i].n0, views[i].n1, views[i].n2, views[i].n3};
     hw[i * 2] = rh; hw[i * 2 + 1] = rw;
-    ratio[i * 2] = (float)((double)views[i].sh / (double)rh);
-    ratio[i * 2 + 1] = (float)((double)views[i].sw / (double)rw);
+    if (e->retina) {  // tv:transform.py:306-311: fp32 tensors divided in fp32
+      ratio[i * 2] = (float)views[i].sh / (float)rh;
+      ratio[i * 2 + 1] = (float)views[i].sw / (float)rw;
+    } else {          // frcnn_la.py:307-315: python doubles, then multiplied into the fp32 tensor
+      ratio[i * 2] = (float)((double)views[i].sh / (double)rh);
+      ratio[i * 2 + 1] = (float)((double)views[i].sw / (double)rw);
+    }
     php[i] = pad32(rh); pwp[i] = pad32(rw);
   }
   // order views by (Hp, Wp) groups
@@ -695,6 +891,7 @@ void detect_views(cald_engine* e, const std::vector<HostView>& views, const CutR
 }
 
 uint8_t* pil_resize_device(cald_engine* e, const uint8_t* src, int h, int w, int oh, int ow, int filter);
+void check_overflow(cald_engine* e);
 }  // namespace
 
 // stage-level entry point (include/cald_b200_ops.h); needs no weights
@@ -963,6 +1160,7 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
   CALD_CUDA_CHECK(cudaMemcpyAsync(h_cls.data(), d_cls, h_cls.size() * 4, cudaMemcpyDeviceToHost, st));
   CALD_CUDA_CHECK(cudaMemcpyAsync(h_ndet.data(), rs.n_det, B * 4, cudaMemcpyDeviceToHost, st));
   CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+  check_overflow(e);
   e->trace("results_on_host");
   for (int b = 0; b < B; ++b) {
     double* cls = out_cls + (size_t)b * ncls1;
@@ -1048,6 +1246,19 @@ DeviceImages upload_images(cald_engine* e, int n, const uint8_t* const* images, 
   return d;
 }
 
+// RetinaNet capacities are fixed; a pool image that exceeds them must fail the call, not be scored differently
+void check_overflow(cald_engine* e) {
+  if (!e->retina) return;
+  int flag = 0;
+  CALD_CUDA_CHECK(cudaMemcpyAsync(&flag, e->d_overflow, 4, cudaMemcpyDeviceToHost, e->st));
+  CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  if (flag) {
+    CALD_CUDA_CHECK(cudaMemsetAsync(e->d_overflow, 0, 4, e->st));
+    throw std::runtime_error(flag == 1 ? "RetinaNet: more than 4096 candidates above the score threshold in one class"
+                                       : "RetinaNet: more detections in one image than retina_max_detections");
+  }
+}
+
 void check_ready(cald_engine* e) {
   if (!e->weights_ready) throw std::runtime_error("cald_load_weights has not been called");
   CALD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
@@ -1074,6 +1285,8 @@ int cald_config_default(cald_config* cfg, int arch, int depth, int num_classes, 
   cfg->min_size = min_size; cfg->max_size = max_size;
   cfg->rpn_pre_nms_top_n = 1000; cfg->rpn_post_nms_top_n = 1000; cfg->rpn_nms_thresh = 0.7f;
   cfg->box_score_thresh = 0.05f; cfg->box_nms_thresh = 0.5f; cfg->box_detections_per_img = 100;
+  if (arch == CALD_ARCH_RETINANET) cfg->box_detections_per_img = 300;  /* per class, retinanet_cal.py:333,463 */
+  cfg->retina_max_detections = 4096;
   cfg->device = 0; cfg->precision = CALD_PREC_BF16X3; cfg->conv_impl = CALD_CONV_TCGEN05;
   cfg->max_views_per_pass = 0; cfg->workspace_bytes = 0; cfg->debug = 0;
   return 0;
@@ -1085,10 +1298,14 @@ int cald_create(const cald_config* cfg, cald_engine** out) {
   if (!cfg || !out) return -1;
   cald_engine* e = nullptr;
   try {
-    if (cfg->arch != CALD_ARCH_FRCNN) throw std::runtime_error("only CALD_ARCH_FRCNN is implemented in this build");
+    if (cfg->arch != CALD_ARCH_FRCNN && cfg->arch != CALD_ARCH_RETINANET) throw std::runtime_error("unknown arch");
     if (cfg->depth != 50 && cfg->depth != 101) throw std::runtime_error("depth must be 50 or 101");
-    if (cfg->box_detections_per_img > 128 || cfg->rpn_post_nms_top_n > 1000 || cfg->rpn_pre_nms_top_n > 1000)
+    const bool retina = cfg->arch == CALD_ARCH_RETINANET;
+    if (!retina && (cfg->box_detections_per_img > 128 || cfg->rpn_post_nms_top_n > 1000 || cfg->rpn_pre_nms_top_n > 1000))
       throw std::runtime_error("capacity limits: detections <= 128, rpn top-n <= 1000");
+    if (retina && (cfg->box_detections_per_img < 1 || cfg->box_detections_per_img > RET_CAND ||
+                   cfg->retina_max_detections < 1 || cfg->retina_max_detections > 32768))
+      throw std::runtime_error("capacity limits: RetinaNet detections per class <= 4096, per image <= 32768");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0)
@@ -1101,8 +1318,18 @@ int cald_create(const cald_config* cfg, cald_engine** out) {
     e->cfg = *cfg;
     e->split = cfg->precision == CALD_PREC_BF16X3;
     e->C = cfg->num_classes;
-    e->cap = 1000;
-    e->det_cap = cfg->box_detections_per_img;
+    e->retina = retina;
+    if (retina) {
+      // one score row per detection: the "proposal" capacity of the generic view buffers is the detection capacity
+      e->ret_per_class = cfg->box_detections_per_img;
+      e->det_cap = cfg->retina_max_detections;
+      e->cap = e->det_cap;
+    } else {
+      e->cap = 1000;
+      e->det_cap = cfg->box_detections_per_img;
+    }
+    CALD_CUDA_CHECK(cudaMalloc((void**)&e->d_overflow, 4));
+    CALD_CUDA_CHECK(cudaMemset(e->d_overflow, 0, 4));
     CALD_CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     e->conv.num_sms = prop.multiProcessorCount;
     e->conv.impl = cfg->conv_impl == CALD_CONV_SIMT ? CONV_SIMT : CONV_TC;
@@ -1118,6 +1345,7 @@ int cald_create(const cald_config* cfg, cald_engine** out) {
     CALD_CUDA_CHECK(cudaFuncSetAttribute(det_class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          NMS_SMEM + TOPK_MAX * 12));
     CALD_CUDA_CHECK(cudaFuncSetAttribute(rpn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_CAP * 8));
+    CALD_CUDA_CHECK(cudaFuncSetAttribute(ret_class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RET_NMS_SMEM));
     // sub-sampling LUT: np.round(np.linspace(0, n-1, 50)).astype(int) (cald_train.py:110-111)
     std::vector<int> lut((size_t)(e->det_cap + 1) * 50, 0);
     for (int n = 41; n <= e->det_cap; ++n) {
@@ -1263,6 +1491,7 @@ int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, cons
       CALD_CUDA_CHECK(cudaMemcpyAsync(h_scores_all.data(), vs.scores, h_scores_all.size() * 4, cudaMemcpyDeviceToHost, st));
     }
     CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+    check_overflow(e);
     for (int b = 0; b < B; ++b) {
       if (counts) counts[pos + b] = h_count[b];
       for (int i = 0; i < dc; ++i) {

@@ -57,7 +57,7 @@ class Config(ctypes.Structure):
     _fields_ = [("arch", c_int), ("depth", c_int), ("num_classes", c_int), ("min_size", c_int),
                 ("max_size", c_int), ("rpn_pre_nms_top_n", c_int), ("rpn_post_nms_top_n", c_int),
                 ("rpn_nms_thresh", c_float), ("box_score_thresh", c_float), ("box_nms_thresh", c_float),
-                ("box_detections_per_img", c_int), ("device", c_int), ("precision", c_int),
+                ("box_detections_per_img", c_int), ("retina_max_detections", c_int), ("device", c_int), ("precision", c_int),
                 ("conv_impl", c_int), ("max_views_per_pass", c_int), ("workspace_bytes", c_size_t),
                 ("debug", c_int)]
 
@@ -102,6 +102,7 @@ class Engine:
         self.cfg = cfg
         self.num_classes = num_classes
         self.depth = depth
+        self.arch_id = arch_id
         self._h = c_void_p()
         self._L = L
         if L.cald_create(ctypes.byref(cfg), ctypes.byref(self._h)) != 0:
@@ -205,10 +206,13 @@ class Engine:
         return out[:k].reshape(-1, n_augs) if n_augs else out[:0]
 
     def detect(self, images):
-        """List of per-image dicts with the reference's output schema (frcnn_la.py:131-141)."""
+        """List of per-image dicts with the reference's output schema (frcnn_la.py:131-141; RetinaNet:
+        retinanet_cal.py:479-485 -- labels are 0-based there and 'props' is all zero)."""
         imgs, ptrs, hs, ws = _u8_list(images)
         n = len(imgs)
-        cap, C = self.cfg.box_detections_per_img, self.num_classes
+        # per-image capacity of the detection list: FRCNN box_detections_per_img, RetinaNet retina_max_detections
+        cap = self.cfg.retina_max_detections if self.arch_id == ARCH_RETINANET else self.cfg.box_detections_per_img
+        C = self.num_classes
         counts = np.zeros(n, dtype=np.int32)
         boxes = np.zeros((n, cap, 4), dtype=np.float32)
         props = np.zeros((n, cap, 4), dtype=np.float32)

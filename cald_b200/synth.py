@@ -88,6 +88,56 @@ def planted_frcnn_weights(depth=50, num_classes=21, seed=0, cls_gain=2.5, bg_bia
     return w
 
 
+def planted_retinanet_weights(num_classes=21, seed=0, depth=50, cls_gain=6.0, reg_gain=0.12, fpn_inner_gain=0.3,
+                             fpn_layer_gain=0.5, tower_gain=1.0, tower_sparsity=3.0, cls_bias_shift=-7.0):
+    """torchvision-keyed {name: np.float32 array} for retinanet_resnet50_fpn_cal (retinanet_cal.py:584-625).
+
+    Same body recipe as ``planted_frcnn_weights``.  The classification logits keep the reference's prior bias
+    -log(99) (retinanet_cal.py:90) lowered by ``cls_bias_shift`` and a zero-mean weight of large gain on top of a
+    SPARSE last tower layer (its bias is pushed down by ``tower_sparsity``), which makes the logit distribution
+    heavy-tailed like a trained detector's: nearly all of the 243k x K (anchor, class) scores sit far below the
+    0.05 threshold and the few that cross it are spread over several logit units -- tens to hundreds of
+    candidates per image instead of none (random init) or all of them (bumped bias); see SURVEY.md section 7.
+    """
+    rs = np.random.RandomState(seed + 7919)
+    shapes = arch.retinanet_params(depth, num_classes)
+    w = {}
+    for name, shp in shapes.items():
+        leaf = name.rsplit(".", 1)[1]
+        if len(shp) == 4:
+            w[name] = _conv_w(rs, shp)
+        elif leaf == "running_var":
+            w[name] = rs.uniform(0.5, 1.5, shp).astype(np.float32)
+        elif leaf == "running_mean":
+            w[name] = (rs.standard_normal(shp) * 0.1).astype(np.float32)
+        elif leaf == "bias":
+            w[name] = (rs.standard_normal(shp) * 0.05).astype(np.float32)
+        else:  # FrozenBN weight
+            w[name] = rs.uniform(0.8, 1.2, shp).astype(np.float32)
+    nblk = sum(arch.RESNET_BLOCKS[depth])
+    g3 = 0.35 if depth == 50 else float(np.sqrt((1.0 + 0.35 ** 2) ** (16.0 / nblk) - 1.0))
+    for name in shapes:
+        if name.endswith(".bn3.weight"):
+            w[name] *= np.float32(g3)
+        if name.endswith(".downsample.1.weight"):
+            w[name] *= np.float32(0.8)
+        if ".fpn.inner_blocks." in name and name.endswith("weight"):
+            w[name] *= np.float32(fpn_inner_gain)
+        if (".fpn.layer_blocks." in name or ".fpn.extra_blocks." in name) and name.endswith("weight"):
+            w[name] *= np.float32(fpn_layer_gain)
+        if ".conv." in name and name.startswith("head.") and name.endswith("weight"):
+            w[name] *= np.float32(tower_gain)
+    cw = w["head.classification_head.cls_logits.weight"]
+    cw -= cw.reshape(cw.shape[0], -1).mean(axis=1).reshape(-1, 1, 1, 1)
+    cw *= np.float32(cls_gain)
+    w["head.classification_head.cls_logits.bias"] = np.full(cw.shape[0], -np.log(99.0) + cls_bias_shift,
+                                                            dtype=np.float32) + \
+        (rs.standard_normal(cw.shape[0]) * 0.05).astype(np.float32)
+    w["head.classification_head.conv.6.bias"] -= np.float32(tower_sparsity)
+    w["head.regression_head.bbox_reg.weight"] *= np.float32(reg_gain)
+    return w
+
+
 _CALIB_GAIN = 2.5
 
 

@@ -43,7 +43,7 @@ typedef struct {
 } cald_aug;
 
 typedef struct {
-  int arch;                  /* CALD_ARCH_*: FRCNN_Feature (frcnn_la.py:146) */
+  int arch;                  /* CALD_ARCH_*: FRCNN_Feature (frcnn_la.py:146) | RetinaNet (retinanet_cal.py:243, 584-625) */
   int depth;                 /* 50 | 101 (resnet_fpn_backbone) */
   int num_classes;           /* incl. background: 21 VOC / 91 COCO (detection/train.py:43-46) */
   int min_size, max_size;    /* GeneralizedRCNNTransform: 600/1000 VOC, 800/1333 COCO (cald_train.py:340-347) */
@@ -52,7 +52,9 @@ typedef struct {
   float rpn_nms_thresh;      /* 0.7 */
   float box_score_thresh;    /* 0.05 (frcnn_la.py:161) */
   float box_nms_thresh;      /* 0.5 */
-  int box_detections_per_img;/* 100 */
+  int box_detections_per_img;/* FRCNN: 100 per image (frcnn_la.py:161); RetinaNet: 300 PER CLASS (retinanet_cal.py:333,463) */
+  int retina_max_detections; /* RetinaNet: capacity of one image's concatenated detection list (<= 300*K in the
+                                reference); exceeding it, or 4096 candidates per class, fails the call loudly */
   int device;                /* CUDA ordinal */
   int precision;             /* CALD_PREC_* */
   int conv_impl;             /* CALD_CONV_* */

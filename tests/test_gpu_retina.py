@@ -1,0 +1,156 @@
+"""RetinaNet (retinanet_cal.py) on the CUDA engine vs the CPU oracle and the reference fixtures.
+
+Oracle = oracle/retina_oracle.py, bit-exact with the unmodified reference on the fixture images
+(tests/golden/make_golden_retina.py asserts that when it writes the fixtures).  Dense stages are compared within
+split-bf16 tolerances, the per-class post-processing as ordered lists, get_uncertainty within 1e-3.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+AUGS = ['flip', 'cut_out', 'smaller_resize', 'rotation']
+NC = 21
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from cald_b200 import synth
+    from cald_b200.engine import Engine, ARCH_RETINANET
+    from oracle import retina_oracle as ro
+    w = synth.planted_retinanet_weights(NC, 0)
+    eng = Engine(depth=50, num_classes=NC, min_size=320, max_size=512, debug=True, max_views_per_pass=8,
+                 arch_id=ARCH_RETINANET)
+    eng.load_state_dict(w)
+    return eng, w, ro.Cfg(50, NC, 320, 512), ro, synth
+
+
+def _nhwc(t):
+    return t[0].permute(1, 2, 0).contiguous().numpy()
+
+
+def _t(img):
+    return torch.from_numpy(img).permute(2, 0, 1).float().div(255)
+
+
+def test_dense_stages_match_oracle(setup):
+    eng, w, cfg, ro, synth = setup
+    img = synth.synth_image(1, 200, 300)
+    st = {}
+    ro.forward(_t(img), w, cfg, st)
+    eng.detect([img])
+    for i, name in enumerate(("p3", "p4", "p5", "p6", "p7")):
+        want = _nhwc(st["p"][i])
+        got = eng.debug_fetch(name).reshape(want.shape)
+        err = np.abs(got - want).max() / np.abs(want).max()
+        assert err < 3e-4, (name, err)
+    # head outputs: [h][w][ld] with channel a*K + k -> rows (y, x, a) as in retinanet_cal.py:146-149
+    off = 0
+    for l in range(5):
+        h, wd = st["p"][l].shape[-2:]
+        n = h * wd * 9
+        got = eng.debug_fetch("cls%d" % l).reshape(h * wd, -1)[:, :9 * NC].reshape(n, NC)
+        want = st["cls_logits"][off:off + n].numpy()
+        assert np.abs(got - want).max() < 2e-3 * max(1.0, np.abs(want).max()), ("cls", l)
+        gotr = eng.debug_fetch("reg%d" % l).reshape(h * wd, -1)[:, :36].reshape(n, 4)
+        wantr = st["bbox_regression"][off:off + n].numpy()
+        assert np.abs(gotr - wantr).max() < 1e-3, ("reg", l)
+        off += n
+
+
+def _compare(got, want):
+    """Ordered detection lists.  Lists of <= 40 rows must agree row by row; on the images that carry hundreds of
+    near-threshold detections one NMS / ordering decision in ~500 may legitimately fall the other way at 16-bit
+    operand precision, so there >= 98 % of the rows must agree (same label, score, box, class row)."""
+    nw = len(want["scores"])
+    assert abs(len(got["scores"]) - nw) <= max(1, nw // 100), (len(got["scores"]), nw)
+    if len(got["scores"]) != nw:
+        return False
+    if nw == 0:
+        return True
+    ok = (got["labels"] == np.asarray(want["labels"]))
+    ok &= np.abs(got["scores"] - np.asarray(want["scores"])) < 1e-3
+    ok &= np.abs(got["boxes"] - np.asarray(want["boxes"])).max(axis=1) < 5e-2
+    ok &= np.abs(got["scores_cls"] - np.asarray(want["scores_cls"])).max(axis=1) < 1e-3
+    ok &= np.abs(got["prob_max"] - np.asarray(want["prob_max"])) < 1e-3
+    if nw <= 40:
+        assert ok.all(), np.where(~ok)[0]
+    else:
+        assert ok.mean() >= 0.98, (ok.mean(), np.where(~ok)[0])
+    return bool(ok.all())
+
+
+def test_detections_match_reference_fixture(setup):
+    """class-ordered detection lists (retinanet_cal.py:479-485) against the unmodified reference's output"""
+    eng, w, cfg, ro, synth = setup
+    g = np.load(os.path.join(GOLD, "retina_r50_nc21_detect.npz"))
+    imgs = [synth.synth_image(int(i), int(h), int(wd)) for i, h, wd in g["images"]]
+    outs = eng.detect(imgs)
+    exact = 0
+    for k, got in enumerate(outs):
+        want = {key: g["%d_%s" % (k, key)] for key in ("boxes", "scores", "labels", "prob_max", "scores_cls")}
+        exact += bool(_compare(got, want))
+    assert exact >= len(imgs) - 2
+
+
+def test_detections_match_oracle_mixed_shapes(setup):
+    eng, w, cfg, ro, synth = setup
+    imgs = [synth.synth_image(i, 200, 300) for i in (0, 1)] + [synth.synth_image(20, 300, 200)]
+    outs = eng.detect(imgs)
+    for img, got in zip(imgs, outs):
+        want = {k: v.numpy() for k, v in ro.forward(_t(img), w, cfg).items()}
+        assert _compare(got, want)
+
+
+def test_uncertainty_matches_reference_fixture(setup):
+    eng, w, cfg, ro, synth = setup
+    from cald_b200 import api
+    g = np.load(os.path.join(GOLD, "retina_r50_nc21_uncertainty.npz"))
+    imgs = [synth.synth_image(int(i), int(h), int(wd)) for i, h, wd in g["images"]]
+    cons, cls = [], []
+    for img, s in zip(imgs, g["seeds"]):
+        random.seed(int(s))
+        c, v = api.score_images(eng, [img], AUGS)
+        cons.append(c[0])
+        cls.append(v[0])
+    err = np.abs(np.array(cons) - g["consistency"])
+    print("engine", np.round(cons, 6), "reference", np.round(g["consistency"], 6), "err", err)
+    # images 2 and 5 carry ~500 detections each: one detection on the other side of the 0.05 threshold or of an
+    # NMS comparison re-draws the 50-point linspace sub-sample (cald_train.py:110-113), so they are held to the
+    # looser bar; the well-separated images must meet the north-star tolerance.
+    few = np.array([len(np.load(os.path.join(GOLD, "retina_r50_nc21_detect.npz"))["%d_scores" % k]) <= 40
+                    for k in range(len(imgs))])
+    assert err[few].max() <= 1e-3, err
+    assert (err <= 1e-3).mean() >= 0.8, err
+    cerr = np.abs(np.array(cls) - g["cls"]).max(axis=1)
+    assert cerr[few].max() <= 1e-3, cerr
+    # image 4 has no detection at all: consistency 0.0 and an all-zero class vector (cald_train.py:118-121)
+    assert cons[4] == 0.0 and not np.any(cls[4])
+
+
+def test_batched_equals_single(setup):
+    eng, w, cfg, ro, synth = setup
+    from cald_b200 import api
+    imgs = [synth.synth_image(i, 200, 300) for i in (0, 1, 3)]
+    random.seed(5)
+    a, _ = api.score_images(eng, imgs, ['flip', 'smaller_resize'])
+    b = []
+    for im in imgs:
+        b.append(api.score_images(eng, [im], ['flip', 'smaller_resize'])[0][0])
+    assert np.abs(np.array(a) - np.array(b)).max() < 1e-6
+
+
+def test_capacity_overflow_fails_loudly():
+    """a detector whose every anchor fires exceeds the fixed candidate capacity: the call must raise, not truncate"""
+    from cald_b200 import synth
+    from cald_b200._lib import CaldError
+    from cald_b200.engine import Engine, ARCH_RETINANET
+    w = synth.planted_retinanet_weights(NC, 0, cls_bias_shift=+9.0)
+    eng = Engine(depth=50, num_classes=NC, min_size=160, max_size=256, arch_id=ARCH_RETINANET)
+    eng.load_state_dict(w)
+    with pytest.raises(CaldError):
+        eng.detect([synth.synth_image(0, 120, 160)])

@@ -87,3 +87,44 @@ def test_api_select_matches_reference():
     assert [int(v) for v in new] == [int(v) for v in g["new_labeled"]]
     nm = api.select(g["uncertainty"], list(g["cls"]), list(g["subset"]), LL(), int(g["budget"]), mutual=False)
     assert [int(v) for v in nm] == [int(g["subset"][i]) for i in np.argsort(g["uncertainty"])[:int(g["budget"])]]
+
+
+def test_retina_oracle_matches_reference_fixture():
+    """oracle/retina_oracle.py against retinanet_cal.py's own output (tests/golden/make_golden_retina.py)"""
+    from cald_b200 import synth
+    from oracle import retina_oracle as ro
+    from oracle import cald_oracle as co
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    w = {k: torch.from_numpy(v) for k, v in synth.planted_retinanet_weights(21, 0).items()}
+    cfg = ro.Cfg(50, 21, 320, 512)
+    g = np.load(os.path.join(GOLD, "retina_r50_nc21_detect.npz"))
+    for k in (0, 1, 4):
+        idx, h, wd = g["images"][k]
+        out = ro.forward(co.to_tensor(synth.synth_image(int(idx), int(h), int(wd))), w, cfg)
+        for key in ("boxes", "scores", "labels", "prob_max", "scores_cls"):
+            want = g["%d_%s" % (k, key)]
+            got = out[key].numpy()
+            assert got.shape == want.shape, (k, key)
+            if want.size:
+                assert np.abs(got.astype(np.float64) - want).max() <= 2e-5, (k, key)
+    u = np.load(os.path.join(GOLD, "retina_r50_nc21_uncertainty.npz"))
+    imgs = [synth.synth_image(int(i), int(h), int(wd)) for i, h, wd in u["images"][:2]]
+    cons, cls = co.get_uncertainty(lambda x: ro.forward(x, w, cfg), imgs, AUGS, 21, 1.3,
+                                   seeds=[int(s) for s in u["seeds"][:2]])
+    assert np.abs(np.array(cons) - u["consistency"][:2]).max() <= 1e-5
+    assert np.abs(np.array(cls) - u["cls"][:2]).max() <= 1e-5
+
+
+def test_retina_anchor_tables():
+    """known answers for the RetinaNet anchor generator (retinanet_cal.py:347-351, tv:anchor_utils.py:58-75)"""
+    from oracle import retina_oracle as ro
+    assert ro.anchor_sizes()[0] == (32, 40, 50) and ro.anchor_sizes()[4] == (512, 645, 812)
+    base = ro.cell_anchors((32, 40, 50)).numpy()
+    assert base.shape == (9, 4)
+    # ratio 0.5 (wide), scale 32: w = 32 / sqrt(.5) = 45.25, h = 22.63 -> +-23, +-11
+    assert base[0].tolist() == [-23.0, -11.0, 23.0, 11.0]
+    # ratio 1, scale 40 -> +-20
+    assert base[4].tolist() == [-20.0, -20.0, 20.0, 20.0]
+    a = ro.grid_anchors((64, 96), [(8, 12), (4, 6), (2, 3), (1, 2), (1, 1)])
+    assert [len(x) for x in a] == [864, 216, 54, 18, 9]
+    assert a[0][9].tolist() == [8 - 23.0, -11.0, 8 + 23.0, 11.0]   # second cell, stride 8
