@@ -32,6 +32,9 @@ AUGS = ['flip', 'cut_out', 'smaller_resize', 'rotation']
 GFLOP_PER_IMAGE = 2160.0  # 5 forwards x 432.0 GFLOP
 METRIC = "unlabeled images scored/sec (FRCNN R50-FPN, 800x1333)"
 WORKLOAD = "FRCNN R50-FPN nc=91, synthetic 1333x800 pool, 1 ref + 4 aug (F,C,D,R) forwards per image"
+# --model retinanet = BASELINE.json configs[2] (RetinaNet R50-FPN, retinanet_cal.py), same pool shape and augmentations
+METRIC_RETINA = "unlabeled images scored/sec (RetinaNet R50-FPN, 800x1333)"
+WORKLOAD_RETINA = "RetinaNet R50-FPN nc=91, synthetic 1333x800 pool, 1 ref + 4 aug (F,C,D,R) forwards per image"
 
 
 def peaks():
@@ -95,22 +98,34 @@ def make_pool(n, seed=0):
     return [synth.synth_image(i, H, W, seed) for i in range(n)]
 
 
-def oracle_forward_fn():
+def planted(model):
+    from cald_b200 import synth
+    if model == "retinanet":
+        return synth.planted_retinanet_weights(NUM_CLASSES, 0, cls_bias_shift=-11.0)
+    return synth.planted_frcnn_weights(50, NUM_CLASSES, 0)
+
+
+def oracle_forward_fn(model="frcnn"):
     """CPU port (oracle/) of the reference path -- the checker, used here only as the timed CPU baseline."""
     import torch
     from cald_b200 import synth
     from oracle import frcnn_oracle as fo
+    if model == "retinanet":
+        from oracle import retina_oracle as ro
+        w = {k: torch.from_numpy(v) for k, v in planted(model).items()}
+        cfg = ro.Cfg(50, NUM_CLASSES, MIN_SIZE, MAX_SIZE)
+        return lambda x: ro.forward(x, w, cfg)
     w = {k: torch.from_numpy(v) for k, v in synth.planted_frcnn_weights(50, NUM_CLASSES, 0).items()}
     cfg = fo.Cfg(50, NUM_CLASSES, MIN_SIZE, MAX_SIZE)
     return lambda x: fo.forward(x, w, cfg)
 
 
-def cpu_baseline(n_images, threads=None):
+def cpu_baseline(n_images, threads=None, model="frcnn"):
     import torch
     from oracle import cald_oracle as co
     if threads:
         torch.set_num_threads(threads)
-    fwd = oracle_forward_fn()
+    fwd = oracle_forward_fn(model)
     imgs = make_pool(n_images + 1, seed=7)
     random.seed(0)
     co.score_image(fwd, imgs[0][:200, :334].copy(), AUGS, NUM_CLASSES, 1.3)  # warm-up on a small crop
@@ -127,7 +142,7 @@ def run_reference(args, rank):
         return
     import torch
     from oracle import cald_oracle as co
-    fwd = oracle_forward_fn()
+    fwd = oracle_forward_fn(args.model)
     imgs = make_pool(args.warmup + args.steps, seed=11)
     random.seed(0)
     for im in imgs[:args.warmup]:
@@ -140,10 +155,10 @@ def run_reference(args, rank):
     cores = torch.get_num_threads()
     sample = "%d images (1 per step), oracle port of cald_train.get_uncertainty on torch CPU fp32" % args.steps
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC_RETINA if args.model == "retinanet" else METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_step": 1},
+        "config": {"workload": WORKLOAD_RETINA if args.model == "retinanet" else WORKLOAD, "images_per_step": 1},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -156,6 +171,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--model", default="frcnn", choices=["frcnn", "retinanet"],
+                    help="frcnn = BASELINE.json configs[1] (the headline); retinanet = configs[2]")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=1)
@@ -179,12 +196,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from cald_b200 import api, synth
-    from cald_b200.engine import Engine, PREC_BF16, PREC_BF16X3, expand_augs
+    from cald_b200.engine import Engine, PREC_BF16, PREC_BF16X3, ARCH_FRCNN, ARCH_RETINANET, expand_augs
     kinds = expand_augs(AUGS)
+    retina = args.model == "retinanet"
     eng = Engine(depth=50, num_classes=NUM_CLASSES, min_size=MIN_SIZE, max_size=MAX_SIZE, device=local_rank,
                  precision=PREC_BF16 if args.precision == "bf16" else PREC_BF16X3,
-                 max_views_per_pass=args.batch * len(AUGS))
-    eng.load_state_dict(synth.planted_frcnn_weights(50, NUM_CLASSES, 0))
+                 max_views_per_pass=args.batch * len(AUGS), arch_id=ARCH_RETINANET if retina else ARCH_FRCNN)
+    eng.load_state_dict(planted(args.model))
 
     B = args.batch
     n_steps_total = args.warmup + args.steps
@@ -280,11 +298,11 @@ def main():
     peak_tf, peak_hbm, peak_src = peaks()
     achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
     out = {
-        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC_RETINA if retina else METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split-bf16, fp32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_step_per_gpu": B, "views_per_image": 1 + len(AUGS),
+        "config": {"workload": WORKLOAD_RETINA if retina else WORKLOAD, "images_per_step_per_gpu": B, "views_per_image": 1 + len(AUGS),
                    "precision": args.precision,
                    "l2": "working set per step (activations of %d views, >10 GB) far exceeds the 126 MB L2; "
                          "each step scores different images" % (B * (1 + len(AUGS)))},
@@ -302,7 +320,7 @@ def main():
                              "time; bf16x3 issues 3 MMAs per algorithmic MAC"},
     }
     if not args.no_cpu_baseline:
-        v, cores = cpu_baseline(args.cpu_images)
+        v, cores = cpu_baseline(args.cpu_images, model=args.model)
         out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                                "sample": "%d image(s) of the same workload, oracle port (torch CPU fp32)" % args.cpu_images}
     print(json.dumps(out))

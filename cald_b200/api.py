@@ -29,10 +29,10 @@ def _aug_kinds(augs):
     for a in augs:
         if a not in _AUG_WHITELIST:
             print('{} is not in the pre-set augmentations!'.format(a))  # cald_train.py:95
-    unsupported = [a for a in augs if a in _AUG_WHITELIST and a not in _eng.SUPPORTED_AUGS]
-    if unsupported:
-        # colour augmentations (cald_helper.py:56-69); the reference's own 'multi_color_adjust' raises NameError
-        raise NotImplementedError("augmentations not implemented by the B200 engine yet: %s" % unsupported)
+    if 'multi_color_adjust' in augs:
+        # cald_train.py:145-148 appends `reference_boxes`, a name that does not exist: the reference itself raises here
+        raise NameError("name 'reference_boxes' is not defined (cald_train.py:148: 'multi_color_adjust' is "
+                        "unreachable in the reference)")
     return _eng.expand_augs(augs)
 
 
@@ -91,16 +91,23 @@ def score_images(eng, images, augs, chunk=64):
     generator exactly as GaussianNoise / SaltPepperNoise would."""
     views = _aug_kinds(augs)
     n_cut = sum(1 for k, _ in views if k == _eng.AUG_CUTOUT)
+    n_swap = sum(1 for k, _ in views if k == _eng.AUG_COLOR_SWAP)
     has_noise = any(k in _eng.NOISE_KINDS for k, _ in views)
+    if n_swap and n_cut:
+        # ColorSwap's random.randint precedes the same image's cutout draws in python's RNG stream and the number of
+        # cutout draws is data dependent: keep the stream exact by scoring one image per call
+        chunk = 1
     cons_all, cls_all = [], []
     for pos in range(0, len(images), chunk):
         batch = images[pos:pos + chunk]
+        # cald_helper.ColorSwap: perms[random.randint(0, len(perms) - 1)], one draw per (image, swap view)
+        swaps = [random.randint(0, 5) for _ in range(n_swap * len(batch))] if n_swap else None
         u = None
         if n_cut:
             state = random.getstate()
             u = np.array([random.random() for _ in range(200 * n_cut * len(batch))], dtype=np.float64)
         noise = _draw_noise(batch, views) if has_noise else None
-        cons, cls, used = eng.score(batch, views, bp, u, noise)
+        cons, cls, used = eng.score(batch, views, bp, u, noise, swaps)
         if n_cut:
             random.setstate(state)
             for _ in range(used):

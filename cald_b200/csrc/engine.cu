@@ -782,6 +782,7 @@ struct HostView {
   const float* noise = nullptr;  // device planes [3][sh][sw]
   int noise_mode = 0;
   float n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+  int perm = PERM_IDENTITY;
 };
 
 void resized_hw(const cald_config& c, int h, int w, int& rh, int& rw) {
@@ -802,7 +803,8 @@ void detect_views(cald_engine* e, const std::vector<HostView>& views, const CutR
     int rh, rw;
     resized_hw(e->cfg, views[i].sh, views[i].sw, rh, rw);
     vd[i] = ViewDesc{views[i].src, views[i].sh, views[i].sw, rh, rw, views[i].flip, views[i].cut_slot,
-                     views[i].noise, views[i].noise_mode, views[i].n0, views[i].n1, views[i].n2, views[i].n3};
+                     views[i].noise, views[i].noise_mode, views[i].n0, views[i].n1, views[i].n2, views[i].n3,
+                     views[i].perm};
     hw[i * 2] = rh; hw[i * 2 + 1] = rw;
     if (e->retina) {  // tv:transform.py:306-311: fp32 tensors divided in fp32
       ratio[i * 2] = (float)views[i].sh / (float)rh;
@@ -927,6 +929,31 @@ extern "C" int cald_op_aug_image(int kind, const uint8_t* img, int h, int w, uin
   }
 }
 
+// stage-level entry point: ColorAdjust(image, factor) on the device (cald_helper.py:65-69)
+extern "C" int cald_op_color_adjust(const uint8_t* img, int h, int w, double factor, uint8_t* out) {
+  try {
+    const long long npix = (long long)h * w;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    unsigned long long* d_sum = nullptr;
+    CALD_CUDA_CHECK(cudaMalloc((void**)&d_in, npix * 3));
+    CALD_CUDA_CHECK(cudaMalloc((void**)&d_out, npix * 3));
+    CALD_CUDA_CHECK(cudaMalloc((void**)&d_sum, 8));
+    CALD_CUDA_CHECK(cudaMemcpy(d_in, img, npix * 3, cudaMemcpyHostToDevice));
+    CALD_CUDA_CHECK(cudaMemset(d_sum, 0, 8));
+    const int blocks = (int)std::min<long long>((npix + 255) / 256, 148 * 8);
+    pil_brightness_kernel<<<blocks, 256>>>(d_in, d_out, npix, (float)factor, d_sum);
+    pil_contrast_saturation_kernel<<<blocks, 256>>>(d_out, npix, (float)factor, d_sum);
+    CALD_CUDA_CHECK(cudaGetLastError());
+    CALD_CUDA_CHECK(cudaMemcpy(out, d_out, npix * 3, cudaMemcpyDeviceToHost));
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_sum);
+    return 0;
+  } catch (const std::exception& ex) {
+    g_create_err = ex.what();
+    cudaGetLastError();
+    return -1;
+  }
+}
+
 namespace {
 // Pillow-exact resize of a device u8 image (horizontal pass then vertical pass).
 uint8_t* pil_resize_device(cald_engine* e, const uint8_t* src, int h, int w, int oh, int ow, int filter) {
@@ -1008,7 +1035,8 @@ __global__ void u8_minmax_kernel(const uint8_t* __restrict__ img, long long n, i
 
 void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const int* hs, const int* ws,
                  const std::vector<cald_aug>& augs, double bp, const double* d_u, int n_u, int* d_cursor,
-                 const float* const* d_noise /* [B][n_noise] device planes */, double* out_cons, double* out_cls) {
+                 const float* const* d_noise /* [B][n_noise] device planes */,
+                 const int* swap_perms /* [B][n_swap] host, or null */, double* out_cons, double* out_cls) {
   Arena& ar = e->arena;
   cudaStream_t st = e->st;
   const int A = (int)augs.size();
@@ -1039,6 +1067,8 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
     if (a.kind == CALD_AUG_GAUSS || a.kind == CALD_AUG_SALTPEPPER) n_noise++;
   }
   const int n_cut = (int)cut_nums.size();
+  int n_swap = 0;
+  for (const cald_aug& a : augs) n_swap += (a.kind == CALD_AUG_COLOR_SWAP);
   for (int c : cut_nums) if (c < 1 || c > MAX_CUT) throw std::runtime_error("cutout: cut_num must be 1..4");
   CutRects* d_cuts = (CutRects*)ar.alloc((size_t)B * std::max(1, n_cut) * sizeof(CutRects));
   CALD_CUDA_CHECK(cudaMemsetAsync(d_cuts, 0, (size_t)B * std::max(1, n_cut) * sizeof(CutRects), st));
@@ -1075,7 +1105,7 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
   std::vector<AugGeom> geom((size_t)B * A);
   std::vector<uint8_t*> temps;
   for (int b = 0; b < B; ++b) {
-    int cut_i = 0, noise_i = 0;
+    int cut_i = 0, noise_i = 0, swap_i = 0;
     for (int a = 0; a < A; ++a) {
       AugGeom& g = geom[(size_t)b * A + a];
       memset(&g, 0, sizeof(g));
@@ -1122,6 +1152,31 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
             hv.n2 = (float)h_mm[b * 2 + 1] / 255.0f;  // salt = max(image)
             hv.n3 = (float)h_mm[b * 2] / 255.0f;      // pepper = min(image)
           }
+          break;
+        }
+        case CALD_AUG_COLOR_ADJUST: {
+          g.kind = AUG_IDENT;
+          const long long npix = (long long)hs[b] * ws[b];
+          uint8_t* t = (uint8_t*)ar.alloc((size_t)npix * 3);
+          unsigned long long* d_sum = (unsigned long long*)ar.alloc(8);
+          CALD_CUDA_CHECK(cudaMemsetAsync(d_sum, 0, 8, st));
+          const int blocks = (int)std::min<long long>((npix + 255) / 256, (long long)e->conv.num_sms * 8);
+          pil_brightness_kernel<<<blocks, 256, 0, st>>>(d_images[b], t, npix, (float)prm, d_sum);
+          pil_contrast_saturation_kernel<<<blocks, 256, 0, st>>>(t, npix, (float)prm, d_sum);
+          CALD_CUDA_CHECK(cudaGetLastError());
+          e->launches += 2;
+          ar.free(d_sum);  // stream-ordered reuse: the kernels above are already enqueued
+          temps.push_back(t);
+          hv.src = t;
+          break;
+        }
+        case CALD_AUG_COLOR_SWAP: {
+          // image[swap, :, :] with swap = perms[random.randint(0, 5)] drawn by the caller (cald_helper.py:56-62)
+          static const int perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+          g.kind = AUG_IDENT;
+          const int pi = swap_perms ? swap_perms[(size_t)b * n_swap + swap_i++] : (int)prm;
+          if (pi < 0 || pi > 5) throw std::runtime_error("color_swap: permutation index must be 0..5");
+          hv.perm = perms[pi][0] | (perms[pi][1] << 2) | (perms[pi][2] << 4);
           break;
         }
         default: throw std::runtime_error("unsupported augmentation kind");
@@ -1286,7 +1341,7 @@ int cald_config_default(cald_config* cfg, int arch, int depth, int num_classes, 
   cfg->rpn_pre_nms_top_n = 1000; cfg->rpn_post_nms_top_n = 1000; cfg->rpn_nms_thresh = 0.7f;
   cfg->box_score_thresh = 0.05f; cfg->box_nms_thresh = 0.5f; cfg->box_detections_per_img = 100;
   if (arch == CALD_ARCH_RETINANET) cfg->box_detections_per_img = 300;  /* per class, retinanet_cal.py:333,463 */
-  cfg->retina_max_detections = 4096;
+  cfg->retina_max_detections = 16384;
   cfg->device = 0; cfg->precision = CALD_PREC_BF16X3; cfg->conv_impl = CALD_CONV_TCGEN05;
   cfg->max_views_per_pass = 0; cfg->workspace_bytes = 0; cfg->debug = 0;
   return 0;
@@ -1390,16 +1445,19 @@ int cald_load_weights(cald_engine* e, int n, const char* const* names, const flo
 
 static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, bool on_device, const int* heights,
                       const int* widths, int n_augs, const cald_aug* aug_list, double bp, const double* rng_uniforms,
-                      int n_uniforms, int* uniforms_consumed, const float* const* noise, double* out_consistency,
-                      double* out_cls) {
+                      int n_uniforms, int* uniforms_consumed, const float* const* noise, const int* swap_perms,
+                      double* out_consistency, double* out_cls) {
   API_TRY(e)
   check_ready(e);
   e->arena.reset();
   e->last_per_view.clear();
   e->last_A = n_augs;
   std::vector<cald_aug> augs(aug_list, aug_list + n_augs);
-  int n_noise = 0;
-  for (const cald_aug& a : augs) if (a.kind == CALD_AUG_GAUSS || a.kind == CALD_AUG_SALTPEPPER) n_noise++;
+  int n_noise = 0, n_swap = 0;
+  for (const cald_aug& a : augs) {
+    if (a.kind == CALD_AUG_GAUSS || a.kind == CALD_AUG_SALTPEPPER) n_noise++;
+    if (a.kind == CALD_AUG_COLOR_SWAP) n_swap++;
+  }
   if (n_noise && !noise) throw std::runtime_error("noise augmentation requested but noise == NULL");
   double* d_u = nullptr;
   int* d_cursor = (int*)e->arena.alloc(4);
@@ -1435,7 +1493,8 @@ static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, 
         }
     }
     score_chunk(e, B, dptr, heights + pos, widths + pos, augs, bp, d_u, n_uniforms, d_cursor,
-                n_noise ? nz.data() : nullptr, out_consistency + pos, out_cls + (size_t)pos * (e->C - 1));
+                n_noise ? nz.data() : nullptr, swap_perms ? swap_perms + (size_t)pos * n_swap : nullptr,
+                out_consistency + pos, out_cls + (size_t)pos * (e->C - 1));
     for (float* d : nz_owned) e->arena.free(d);
     if (di.slab) e->arena.free(di.slab);
   }
@@ -1449,16 +1508,17 @@ static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, 
 
 int cald_score(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
                int n_augs, const cald_aug* augs, double bp, const double* rng_uniforms, int n_uniforms,
-               int* uniforms_consumed, const float* const* noise, double* out_consistency, double* out_cls) {
+               int* uniforms_consumed, const float* const* noise, const int* swap_perms, double* out_consistency,
+               double* out_cls) {
   return score_impl(e, n_images, images, false, heights, widths, n_augs, augs, bp, rng_uniforms, n_uniforms,
-                    uniforms_consumed, noise, out_consistency, out_cls);
+                    uniforms_consumed, noise, swap_perms, out_consistency, out_cls);
 }
 int cald_score_device(cald_engine* e, int n_images, const uint8_t* const* d_images, const int* heights,
                       const int* widths, int n_augs, const cald_aug* augs, double bp, const double* rng_uniforms,
-                      int n_uniforms, int* uniforms_consumed, const float* const* d_noise, double* out_consistency,
-                      double* out_cls) {
+                      int n_uniforms, int* uniforms_consumed, const float* const* d_noise, const int* swap_perms,
+                      double* out_consistency, double* out_cls) {
   return score_impl(e, n_images, d_images, true, heights, widths, n_augs, augs, bp, rng_uniforms, n_uniforms,
-                    uniforms_consumed, d_noise, out_consistency, out_cls);
+                    uniforms_consumed, d_noise, swap_perms, out_consistency, out_cls);
 }
 
 int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,

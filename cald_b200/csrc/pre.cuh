@@ -24,7 +24,9 @@ struct ViewDesc {
   const float* noise;   // null for the other views
   int noise_mode;       // 1: x + noise * std / 255     2: salt (noise < lo) / pepper (noise > hi)
   float n0, n1, n2, n3; // mode 1: std            mode 2: lo, hi, salt value, pepper value
+  int perm;             // ColorSwap (cald_helper.py:56-62): source channel of output channel c = (perm >> 2c) & 3
 };
+constexpr int PERM_IDENTITY = 0 | (1 << 2) | (2 << 4);
 
 struct CutRects {       // per image
   int n;
@@ -41,7 +43,8 @@ __device__ __forceinline__ float src_pixel(const ViewDesc& d, const CutRects* cu
       zero |= (x >= cut->rect[k][0] && x < cut->rect[k][2] && y >= cut->rect[k][1] && y < cut->rect[k][3]);
   }
   int sx = d.flip ? (d.sw - 1 - x) : x;
-  v = zero ? 0.f : ((float)d.src[((long long)y * d.sw + sx) * 3 + c] / 255.f);
+  const int sc = (d.perm >> (2 * c)) & 3;
+  v = zero ? 0.f : ((float)d.src[((long long)y * d.sw + sx) * 3 + sc] / 255.f);
   if (d.noise) {
     const float nz = d.noise[((long long)c * d.sh + y) * d.sw + x];
     if (d.noise_mode == 1) {
@@ -133,6 +136,51 @@ __global__ void view_stem_input_kernel(const ViewDesc* __restrict__ views, const
     uint4* dl = reinterpret_cast<uint4*>(olo + off);
     dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+  }
+}
+
+// ---------------------------------------------------------------- Pillow-exact colour enhancement
+// cald_helper.ColorAdjust (cald_helper.py:65-69) = torchvision F.adjust_brightness -> adjust_contrast ->
+// adjust_saturation on the PIL image = PIL.ImageEnhance {Brightness, Contrast, Color}: Image.blend(degenerate, image,
+// factor), libImaging/Blend.c:  temp = (float)((int)in1 + alpha * ((int)in2 - (int)in1)); alpha in [0,1] -> (UINT8)temp,
+// otherwise clip to [0,255] first.  Luma = libImaging/Convert.c rgb2l: (R*19595 + G*38470 + B*7471 + 0x8000) >> 16.
+__device__ __forceinline__ int pil_blend(int in1, int in2, float alpha, bool interp) {
+  const float temp = (float)in1 + alpha * (float)(in2 - in1);
+  if (interp) return (int)(uint8_t)(int)temp;
+  if (temp <= 0.f) return 0;
+  if (temp >= 255.f) return 255;
+  return (int)temp;
+}
+__device__ __forceinline__ int pil_luma(int r, int g, int b) { return (r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16; }
+
+// pass 1: brightness (degenerate = black) -> out; sum of the brightened image's luma -> luma_sum (for Contrast's mean)
+__global__ void pil_brightness_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long npix,
+                                      float alpha, unsigned long long* __restrict__ luma_sum) {
+  const bool interp = alpha >= 0.f && alpha <= 1.f;
+  unsigned long long local = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    const int r = pil_blend(0, in[i * 3], alpha, interp), g = pil_blend(0, in[i * 3 + 1], alpha, interp),
+              b = pil_blend(0, in[i * 3 + 2], alpha, interp);
+    out[i * 3] = (uint8_t)r; out[i * 3 + 1] = (uint8_t)g; out[i * 3 + 2] = (uint8_t)b;
+    local += (unsigned long long)pil_luma(r, g, b);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(luma_sum, local);
+}
+// pass 2 (in place): contrast against the rounded mean luma, then saturation against the per-pixel luma
+__global__ void pil_contrast_saturation_kernel(uint8_t* __restrict__ img, long long npix, float alpha,
+                                               const unsigned long long* __restrict__ luma_sum) {
+  const bool interp = alpha >= 0.f && alpha <= 1.f;
+  // ImageEnhance.Contrast: int(ImageStat.Stat(L).mean[0] + 0.5), python floats (double)
+  const int mean = (int)((double)luma_sum[0] / (double)npix + 0.5);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    const int r = pil_blend(mean, img[i * 3], alpha, interp), g = pil_blend(mean, img[i * 3 + 1], alpha, interp),
+              b = pil_blend(mean, img[i * 3 + 2], alpha, interp);
+    const int l = pil_luma(r, g, b);
+    img[i * 3] = (uint8_t)pil_blend(l, r, alpha, interp);
+    img[i * 3 + 1] = (uint8_t)pil_blend(l, g, alpha, interp);
+    img[i * 3 + 2] = (uint8_t)pil_blend(l, b, alpha, interp);
   }
 }
 

@@ -11,6 +11,7 @@ ARCH_FRCNN, ARCH_RETINANET = 0, 1
 PREC_BF16X3, PREC_BF16 = 0, 1
 CONV_TCGEN05, CONV_SIMT = 0, 1
 AUG_FLIP, AUG_CUTOUT, AUG_RESIZE, AUG_ROTATION, AUG_GAUSS, AUG_SALTPEPPER = 0, 1, 2, 3, 4, 5
+AUG_COLOR_ADJUST, AUG_COLOR_SWAP = 6, 7
 AUG_SMALLER_RESIZE = AUG_RESIZE
 NOISE_KINDS = (AUG_GAUSS, AUG_SALTPEPPER)
 
@@ -30,6 +31,10 @@ def expand_augs(names):
         v.append((AUG_GAUSS, 16.0))
     if 'multi_ga' in names:
         v += [(AUG_GAUSS, float(i * 8)) for i in range(1, 7)]
+    if 'color_adjust' in names:
+        v.append((AUG_COLOR_ADJUST, 1.5))
+    if 'color_swap' in names:
+        v.append((AUG_COLOR_SWAP, 0.0))
     if 'sp' in names:
         v.append((AUG_SALTPEPPER, 0.1))
     if 'multi_sp' in names:
@@ -49,8 +54,8 @@ def expand_augs(names):
     return v
 
 
-SUPPORTED_AUGS = ('flip', 'ga', 'multi_ga', 'sp', 'multi_sp', 'cut_out', 'multi_cut_out', 'multi_resize',
-                  'larger_resize', 'smaller_resize', 'rotation')
+SUPPORTED_AUGS = ('flip', 'ga', 'multi_ga', 'color_adjust', 'color_swap', 'sp', 'multi_sp', 'cut_out',
+                  'multi_cut_out', 'multi_resize', 'larger_resize', 'smaller_resize', 'rotation')
 
 
 class Config(ctypes.Structure):
@@ -153,9 +158,10 @@ class Engine:
         views = [(v, 0.0) if isinstance(v, int) else v for v in views]
         return (Aug * max(1, len(views)))(*[Aug(int(k), float(p)) for k, p in views]), len(views)
 
-    def score(self, images, views, bp=1.3, uniforms=None, noise=None):
+    def score(self, images, views, bp=1.3, uniforms=None, noise=None, swap_perms=None):
         """views: list of (kind, param) (see expand_augs); noise: list of float32 [3,H,W] planes, one per
-        (image, noise view) in image-major order.  -> (consistency float64[n], cls float64[n, C-1], consumed)."""
+        (image, noise view) in image-major order; swap_perms: int per (image, color_swap view).
+        -> (consistency float64[n], cls float64[n, C-1], consumed)."""
         imgs, ptrs, hs, ws = _u8_list(images)
         n = len(imgs)
         a, na = self._aug_array(views)
@@ -165,15 +171,19 @@ class Engine:
         if noise:
             nz_keep = [np.ascontiguousarray(z, dtype=np.float32) for z in noise]
             nz_ptrs = (POINTER(c_float) * len(nz_keep))(*[z.ctypes.data_as(POINTER(c_float)) for z in nz_keep])
+        sp = None if swap_perms is None else np.ascontiguousarray(swap_perms, dtype=np.int32)
         consumed = c_int(0)
         cons = np.zeros(n, dtype=np.float64)
         cls = np.zeros((n, self.num_classes - 1), dtype=np.float64)
         self._L.cald_score.argtypes = [c_void_p, c_int, POINTER(POINTER(c_uint8)), POINTER(c_int), POINTER(c_int),
                                        c_int, POINTER(Aug), c_double, POINTER(c_double), c_int, POINTER(c_int),
-                                       POINTER(POINTER(c_float)), POINTER(c_double), POINTER(c_double)]
+                                       POINTER(POINTER(c_float)), POINTER(c_int), POINTER(c_double),
+                                       POINTER(c_double)]
         self._check(self._L.cald_score(self._h, n, ptrs, hs, ws, na, a, float(bp),
                                        None if u is None else u.ctypes.data_as(POINTER(c_double)), nu,
-                                       ctypes.byref(consumed), nz_ptrs, cons.ctypes.data_as(POINTER(c_double)),
+                                       ctypes.byref(consumed), nz_ptrs,
+                                       None if sp is None else sp.ctypes.data_as(POINTER(c_int)),
+                                       cons.ctypes.data_as(POINTER(c_double)),
                                        cls.ctypes.data_as(POINTER(c_double))))
         return cons, cls, consumed.value
 
@@ -190,11 +200,11 @@ class Engine:
         cls = np.zeros((n, self.num_classes - 1), dtype=np.float64)
         self._L.cald_score_device.argtypes = [c_void_p, c_int, POINTER(POINTER(c_uint8)), POINTER(c_int),
                                               POINTER(c_int), c_int, POINTER(Aug), c_double, POINTER(c_double),
-                                              c_int, POINTER(c_int), POINTER(POINTER(c_float)), POINTER(c_double),
-                                              POINTER(c_double)]
+                                              c_int, POINTER(c_int), POINTER(POINTER(c_float)), POINTER(c_int),
+                                              POINTER(c_double), POINTER(c_double)]
         self._check(self._L.cald_score_device(self._h, n, ptrs, chs, cws, na, a, float(bp),
                                               None if u is None else u.ctypes.data_as(POINTER(c_double)),
-                                              0 if u is None else u.size, ctypes.byref(consumed), None,
+                                              0 if u is None else u.size, ctypes.byref(consumed), None, None,
                                               cons.ctypes.data_as(POINTER(c_double)),
                                               cls.ctypes.data_as(POINTER(c_double))))
         return cons, cls, consumed.value

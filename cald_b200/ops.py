@@ -52,3 +52,20 @@ def aug_image(kind, img_u8):
         L.cald_last_error.argtypes = [ctypes.c_void_p]
         raise RuntimeError(L.cald_last_error(None).decode())
     return out[:oh.value * ow.value * 3].reshape(oh.value, ow.value, 3)
+
+
+def color_adjust(img_u8, factor):
+    """Device ColorAdjust (cald_helper.py:65-69): PIL brightness -> contrast -> saturation, u8 in, u8 out."""
+    img = np.ascontiguousarray(img_u8, dtype=np.uint8)
+    h, w = img.shape[:2]
+    out = np.zeros_like(img)
+    L = lib()
+    L.cald_op_color_adjust.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                       ctypes.POINTER(ctypes.c_uint8)]
+    rc = L.cald_op_color_adjust(img.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), h, w, float(factor),
+                                out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    if rc != 0:
+        L.cald_last_error.restype = ctypes.c_char_p
+        L.cald_last_error.argtypes = [ctypes.c_void_p]
+        raise RuntimeError(L.cald_last_error(None).decode())
+    return out

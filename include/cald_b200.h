@@ -34,7 +34,9 @@ enum {
   CALD_AUG_RESIZE = 2,      /* resize(ratio = param), PIL BILINEAR cald_helper.py:47-53   */
   CALD_AUG_ROTATION = 3,    /* rotate(angle = param degrees)       cald_helper.py:135-223 */
   CALD_AUG_GAUSS = 4,       /* GaussianNoise(std = param)          cald_helper.py:72-75   */
-  CALD_AUG_SALTPEPPER = 5   /* SaltPepperNoise(prob = param)       cald_helper.py:78-85   */
+  CALD_AUG_SALTPEPPER = 5,  /* SaltPepperNoise(prob = param)       cald_helper.py:78-85   */
+  CALD_AUG_COLOR_ADJUST = 6,/* ColorAdjust(factor = param): PIL brightness -> contrast -> saturation, cald_helper.py:65-69 */
+  CALD_AUG_COLOR_SWAP = 7   /* ColorSwap: channel permutation perms[i] cald_helper.py:56-62; i from swap_perms, else param */
 };
 #define CALD_AUG_SMALLER_RESIZE CALD_AUG_RESIZE
 typedef struct {
@@ -86,10 +88,13 @@ int cald_load_weights(cald_engine* e, int n, const char* const* names, const flo
  * rng_uniforms: raw random.random() doubles from python's generator (4 per cutout try, drawn in stream order);
  *   uniforms_consumed returns how many the scoring consumed so the caller can advance its generator exactly as
  *   cald_helper.cutout would have (cald_helper.py:106-114).
+ * swap_perms: for COLOR_SWAP views, the index random.randint(0, 5) the caller drew for each (image, swap view), image-major;
+ *   NULL = use the view's param for every image.
  * out_consistency[n]: np.mean(consistency_aug) per image; out_cls[n][num_classes-1]: mean class-max vector. */
 int cald_score(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
                int n_augs, const cald_aug* augs, double bp, const double* rng_uniforms, int n_uniforms,
-               int* uniforms_consumed, const float* const* noise, double* out_consistency, double* out_cls);
+               int* uniforms_consumed, const float* const* noise, const int* swap_perms, double* out_consistency,
+               double* out_cls);
 
 /* One detector forward per image: task_model([F.to_tensor(img)])[0] (frcnn_la.py:131-141).
  * Outputs are fixed-capacity [n][cap] with counts[n]; cap = box_detections_per_img.
@@ -123,8 +128,8 @@ int cald_event_elapsed_ms(cald_engine* e, int slot_a, int slot_b, float* ms);
 /* Same as cald_score but the u8 images already live in device memory (device pointers). */
 int cald_score_device(cald_engine* e, int n_images, const uint8_t* const* d_images, const int* heights,
                       const int* widths, int n_augs, const cald_aug* augs, double bp, const double* rng_uniforms,
-                      int n_uniforms, int* uniforms_consumed, const float* const* d_noise, double* out_consistency,
-                      double* out_cls);
+                      int n_uniforms, int* uniforms_consumed, const float* const* d_noise, const int* swap_perms,
+                      double* out_consistency, double* out_cls);
 
 #ifdef __cplusplus
 }

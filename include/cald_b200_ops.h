@@ -41,6 +41,10 @@ int cald_op_conv2d(const float* x, int n, int h, int w, int cin, const float* we
  * img: u8 [h][w][3].  out must hold h*w*3 bytes; the produced size is returned in out_h / out_w. */
 int cald_op_aug_image(int kind, const uint8_t* img, int h, int w, uint8_t* out, int* out_h, int* out_w);
 
+/* cald_helper.ColorAdjust(image, factor) (cald/cald_helper.py:65-69): PIL.ImageEnhance Brightness -> Contrast -> Color
+ * with the same factor, bit-exact u8 arithmetic of libImaging/Blend.c / Convert.c.  img, out: u8 [h][w][3]. */
+int cald_op_color_adjust(const uint8_t* img, int h, int w, double factor, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -154,6 +154,20 @@ def salt_pepper(img_u8, prob):
     return t
 
 
+COLOR_PERMS = ((0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0))
+
+
+def color_swap(img_u8, rng=random):
+    """cald_helper.py:56-62: one random.randint draw, then a channel permutation of the tensor."""
+    swap = COLOR_PERMS[rng.randint(0, len(COLOR_PERMS) - 1)]
+    return to_tensor(img_u8)[list(swap), :, :]
+
+
+def color_adjust(img_u8, factor):
+    """cald_helper.py:65-69: PIL brightness -> contrast -> saturation (oracle/pil_oracle.py), then to_tensor."""
+    return to_tensor(pil_oracle.cald_color_adjust(img_u8, factor))
+
+
 # ------------------------------------------------------------------ reduction
 def js_divergence(p, q):
     """cald_train.py:211-216: scipy.stats.entropy semantics on float32 vectors.
@@ -216,8 +230,12 @@ def make_views(img_u8, ref_boxes, augs, rng=random):
     if 'multi_ga' in augs:
         for i in range(1, 7):
             views.append((gaussian_noise(img_u8, i * 8), ref_boxes))
-    if 'color_adjust' in augs or 'color_swap' in augs or 'multi_color_adjust' in augs:
-        raise NotImplementedError("colour augmentations are outside the oracle (SURVEY.md a9)")
+    if 'color_adjust' in augs:
+        views.append((color_adjust(img_u8, 1.5), ref_boxes))
+    if 'color_swap' in augs:
+        views.append((color_swap(img_u8, rng), ref_boxes))
+    if 'multi_color_adjust' in augs:
+        raise NameError("name 'reference_boxes' is not defined")  # cald_train.py:148, as in the reference
     if 'sp' in augs:
         views.append((salt_pepper(img_u8, 0.1), ref_boxes))
     if 'multi_sp' in augs:

@@ -164,3 +164,48 @@ def cald_resize_image(img, ratio):
     """The image half of cald_helper.resize (cald_helper.py:47-53)."""
     h, w = img.shape[:2]
     return resize(img, int(w * ratio), int(h * ratio), "bilinear")
+
+
+# ---------------------------------------------------------------- colour enhancement (cald_helper.py:56-69)
+# torchvision F.adjust_brightness / adjust_contrast / adjust_saturation on a PIL image are PIL.ImageEnhance
+# Brightness / Contrast / Color: Image.blend(degenerate, image, factor) with (libImaging/Blend.c)
+#     temp = (float)((int)in1 + alpha * ((int)in2 - (int)in1))        alpha is a C float
+#     0 <= alpha <= 1: out = (UINT8)temp            otherwise: clip to [0, 255], then (UINT8)temp
+# and degenerate = black (Brightness) | grey of the rounded mean luma (Contrast) | per-pixel luma (Color), where
+# luma = convert("L"): (R*19595 + G*38470 + B*7471 + 0x8000) >> 16 (libImaging/Convert.c rgb2l).
+def luma(img):
+    r, g, b = (img[..., i].astype(np.int64) for i in range(3))
+    return ((r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16).astype(np.uint8)
+
+
+def blend(deg, img, alpha):
+    a = np.float32(alpha)
+    in1 = deg.astype(np.int32)
+    in2 = img.astype(np.int32)
+    temp = in1.astype(np.float32) + a * (in2 - in1).astype(np.float32)
+    if 0.0 <= alpha <= 1.0:
+        return temp.astype(np.int32).astype(np.uint8)
+    return np.where(temp <= 0, 0, np.where(temp >= 255, 255, temp.astype(np.int32))).astype(np.uint8)
+
+
+def adjust_brightness(img, factor):
+    return blend(np.zeros_like(img), img, factor)
+
+
+def contrast_mean(img):
+    """ImageEnhance.Contrast: int(ImageStat.Stat(image.convert("L")).mean[0] + 0.5)  (python float mean)"""
+    l = luma(img)
+    return int(float(int(l.astype(np.int64).sum())) / float(l.size) + 0.5)
+
+
+def adjust_contrast(img, factor):
+    return blend(np.full_like(img, contrast_mean(img)), img, factor)
+
+
+def adjust_saturation(img, factor):
+    return blend(np.repeat(luma(img)[..., None], 3, axis=2), img, factor)
+
+
+def cald_color_adjust(img, factor):
+    """cald_helper.ColorAdjust: brightness -> contrast -> saturation with the same factor, on u8."""
+    return adjust_saturation(adjust_contrast(adjust_brightness(img, factor), factor), factor)

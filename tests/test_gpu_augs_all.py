@@ -1,5 +1,6 @@
 """The remaining augmentation kinds of the reference whitelist (cald_train.py:93-94) vs the oracle:
-Gaussian / salt-pepper noise (torch CPU RNG), multi_cut_out (python RNG, 1..4 cuts), larger / multi resize."""
+Gaussian / salt-pepper noise (torch CPU RNG), multi_cut_out (python RNG, 1..4 cuts), larger / multi resize,
+ColorAdjust (Pillow-exact enhancement on the device) and ColorSwap (python RNG, drawn before the cutout draws)."""
 import random
 
 import numpy as np
@@ -23,7 +24,8 @@ def setup():
 
 
 @pytest.mark.parametrize("augs", [['ga', 'sp'], ['multi_cut_out', 'cut_out'], ['larger_resize', 'multi_resize'],
-                                  ['flip', 'ga', 'cut_out', 'smaller_resize', 'rotation', 'sp']])
+                                  ['flip', 'ga', 'cut_out', 'smaller_resize', 'rotation', 'sp'],
+                                  ['color_adjust', 'color_swap'], ['color_swap', 'cut_out', 'color_adjust', 'flip']])
 def test_aug_kinds_match_oracle(setup, augs):
     eng, fwd, synth = setup
     from cald_b200 import api
@@ -48,3 +50,10 @@ def test_aug_kinds_match_oracle(setup, augs):
     for g, wv in zip(got_cls, want_cls):
         d = np.abs(g - wv)
         assert (d > 1e-3).sum() <= 1 and d.max() <= 2e-2
+
+
+def test_multi_color_adjust_raises_like_the_reference(setup):
+    eng, fwd, synth = setup
+    from cald_b200 import api
+    with pytest.raises(NameError):
+        api.score_images(eng, [synth.synth_image(0, 160, 240)], ['multi_color_adjust'])

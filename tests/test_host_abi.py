@@ -77,8 +77,11 @@ def test_aug_order_follows_reference():
     assert v == [(E.AUG_GAUSS, 16.0), (E.AUG_SALTPEPPER, 0.1)] + [(E.AUG_CUTOUT, float(i)) for i in range(1, 5)] + \
         [(E.AUG_RESIZE, i * 0.1) for i in range(7, 10)]
     assert len(api._aug_kinds(['multi_ga', 'multi_sp'])) == 12
-    with pytest.raises(NotImplementedError):
-        api._aug_kinds(['color_swap'])
+    # colour views sit between the Gaussian and the salt-pepper views (cald_train.py:136-149)
+    assert api._aug_kinds(['sp', 'color_swap', 'ga', 'color_adjust']) == \
+        [(E.AUG_GAUSS, 16.0), (E.AUG_COLOR_ADJUST, 1.5), (E.AUG_COLOR_SWAP, 0.0), (E.AUG_SALTPEPPER, 0.1)]
+    with pytest.raises(NameError):  # cald_train.py:148 references an undefined name: unreachable upstream too
+        api._aug_kinds(['multi_color_adjust'])
 
 
 def test_shard_partition_covers_pool_in_order():

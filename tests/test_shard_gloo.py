@@ -14,7 +14,7 @@ class FakeEngine:
     """stands in for the CUDA engine: score = mean pixel, class vector = per-channel stats"""
     num_classes = 4
 
-    def score(self, images, kinds, bp, u, noise=None):
+    def score(self, images, kinds, bp, u, noise=None, swap_perms=None):
         cons = np.array([float(im.mean()) for im in images])
         cls = np.stack([np.array([im[..., c].max() for c in range(3)], dtype=np.float64) for im in images])
         return cons, cls, 0
