@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=1)
+    ap.add_argument("--workspace-gb", type=float, default=0.0, help="device arena size (0 = half of free memory)")
     ap.add_argument("--layers", default=None, help="write the per-layer conv timing table (TSV) to this path")
     args = ap.parse_args()
 
@@ -201,7 +202,8 @@ def main():
     retina = args.model == "retinanet"
     eng = Engine(depth=50, num_classes=NUM_CLASSES, min_size=MIN_SIZE, max_size=MAX_SIZE, device=local_rank,
                  precision=PREC_BF16 if args.precision == "bf16" else PREC_BF16X3,
-                 max_views_per_pass=args.batch * len(AUGS), arch_id=ARCH_RETINANET if retina else ARCH_FRCNN)
+                 max_views_per_pass=args.batch * len(AUGS), arch_id=ARCH_RETINANET if retina else ARCH_FRCNN,
+                 workspace_bytes=int(args.workspace_gb * (1 << 30)))
     eng.load_state_dict(planted(args.model))
 
     B = args.batch

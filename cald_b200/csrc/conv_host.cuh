@@ -142,6 +142,8 @@ struct ConvEngine {
     return ident[slot];
   }
   int kc = 8;              // split mode: k-blocks (of 64) per accumulation chunk; 0 = never chunk
+  int chunk_above_kb = 40; // chunk only contractions longer than this many k-blocks (K > 2560): up to there the
+                           // cross-term-separated accumulator (igemm.cuh XSEP) is as accurate and faster
   long long launches = 0;  // kernels launched (bench's gpu_launches)
   double flops = 0;        // algorithmic 2*MAC of the launches
   // optional per-launch timing with CUDA events on the launching stream (bench.py roofline)
@@ -350,7 +352,7 @@ struct ConvEngine {
       p.res_mode = RES_NONE;  // the epilogue no longer sees a residual
     }
     const int num_kb = w.taps * (w.cin / 64) + p.res_kb;
-    const bool chunked = split && kc > 0 && num_kb > kc && BN <= 128;
+    const bool chunked = split && kc > 0 && num_kb > kc && num_kb > chunk_above_kb && BN <= 128;
     p.kc = chunked ? kc : num_kb;
     if (profiling) {
       // algorithmic HBM bytes: every operand element once at its stored width (activations 4 B split / 2 B bf16)

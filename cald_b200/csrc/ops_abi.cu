@@ -107,6 +107,17 @@ extern "C" int cald_op_conv2d(const float* x, int n, int h, int w, int cin, cons
     y = alloc_act(ar, n, ho, wo, cw.cout_pad, split);
   }
   eng.run(in, cw, y, o, st);
+  if (getenv("CALD_OP_TIMING")) {
+    // experiment hook (tools/conv_micro.py): re-run the launch a few times bracketed by CUDA events
+    eng.profiling = true;
+    for (int it = 0; it < 6; ++it) eng.run(in, cw, y, o, st);
+    CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+    double fl = 0;
+    long long nl = 0;
+    double ms = eng.drain_profile(&fl, &nl);
+    fprintf(stderr, "[conv-timing] %.4f ms/launch  %.1f TFLOP/s algorithmic\n", ms / nl, fl / ms / 1e9);
+    eng.profiling = false;
+  }
   std::vector<float> hy(y.plane_elems());
   float* dy = (float*)ar.alloc(hy.size() * 4);
   split_to_f32(y, dy, st);

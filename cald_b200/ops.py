@@ -69,3 +69,4 @@ def color_adjust(img_u8, factor):
         L.cald_last_error.argtypes = [ctypes.c_void_p]
         raise RuntimeError(L.cald_last_error(None).decode())
     return out
+

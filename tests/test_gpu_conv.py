@@ -107,3 +107,4 @@ def test_conv_large_k_chunked_accumulation():
     assert errs[4] <= 1e-5, errs
     got = ops.conv2d(x, wt, None, prec=0, impl=0)  # engine default
     assert np.abs(got - want).max() <= 1e-5 * scale
+
