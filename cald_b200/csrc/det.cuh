@@ -109,10 +109,23 @@ __global__ void __launch_bounds__(1024) topk_select_kernel(TopkGroups G, unsigne
       for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
       __syncthreads();
       const unsigned long long prefix = s_prefix, mask = s_mask;
+      // Objectness keys of one level share their leading bytes, so one atomicAdd per key would serialise the whole
+      // CTA on one or two bins: each thread run-length-merges equal consecutive bins and flushes once per run.
+      int last = -1, run = 0;
       for (int i = tid; i < n; i += blockDim.x) {
-        unsigned long long key = keys[i];
-        if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 255)], 1);
+        const unsigned long long key = keys[i];
+        if ((key & mask) == prefix) {
+          const int bin = (int)((key >> shift) & 255);
+          if (bin == last) {
+            ++run;
+          } else {
+            if (run) atomicAdd(&hist[last], run);
+            last = bin;
+            run = 1;
+          }
+        }
       }
+      if (run) atomicAdd(&hist[last], run);
       __syncthreads();
       if (tid == 0) {
         int kk = s_k, cum = 0, b = 0;
@@ -232,8 +245,10 @@ constexpr int NMS_SMEM = TOPK_MAX * 16 * 8 + TOPK_MAX * 16;
 __device__ inline void block_nms_1024(const float4* sbox, unsigned long long* mask, int n, double thresh,
                                       int* keep_idx /*smem or global, cap 1024*/, int* keep_count) {
   const int words = (n + 63) >> 6;
+  // item -> (column word cw, row i) with i fastest: the lanes of a warp share cw, so every sbox[j] read below is a
+  // shared-memory broadcast (with cw fastest the 32 lanes would read float4s 1 KB apart: a 32-way bank conflict)
   for (int item = threadIdx.x; item < n * words; item += blockDim.x) {
-    int i = item / words, cw = item % words;
+    int cw = item / n, i = item - cw * n;
     unsigned long long m = 0;
     if (cw * 64 + 63 > i) {
       float4 bi = sbox[i];

@@ -12,7 +12,7 @@
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Split-bf16 ("bf16x3") arithmetic: A = A_hi + A_lo, B = B_hi + B_lo, product = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi.
-// Non-chunked launches keep the small cross terms in their OWN accumulator columns (XSEP): one N = 2*BLOCK_N MMA
+// Launches with BLOCK_N <= 128 keep the small cross terms in their OWN accumulator columns (XSEP): one N = 2*BLOCK_N MMA
 // multiplies A_hi by the concatenation [B_hi | B_lo] (B_lo sits right behind B_hi in the stage), a second N = BLOCK_N
 // MMA adds A_lo*B_hi into the cross columns, and the epilogue sums the two halves in fp32.  That is two wide
 // instructions instead of three narrow ones per k-step (the tensor pipe is ~1.6x more efficient at N = 256 than at
@@ -147,7 +147,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmI, const __grid_constant__ ConvParams p) {
   using Cfg = IgemmCfg<BLOCK_N, SPLIT>;
-  constexpr bool XSEP = SPLIT && !CHUNKED && BLOCK_N <= 128;  // cross terms in their own accumulator columns
+  constexpr bool XSEP = SPLIT && BLOCK_N <= 128;  // cross terms in their own accumulator columns
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -335,6 +335,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 32; ++i) accv[cc + i] = __uint_as_float(r[i]);
             } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) accv[cc + i] += __uint_as_float(r[i]);
+            }
+            if (XSEP) {  // the chunk's cross-term columns
+              tmem_ld32(t0 + BLOCK_N + cc, r);
 #pragma unroll
               for (int i = 0; i < 32; ++i) accv[cc + i] += __uint_as_float(r[i]);
             }
