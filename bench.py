@@ -120,11 +120,19 @@ def oracle_forward_fn(model="frcnn"):
     return lambda x: fo.forward(x, w, cfg)
 
 
+def host_threads():
+    """All host cores this process may use.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which
+    would silently make the CPU arm single-threaded: set the count explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(n_images, threads=None, model="frcnn"):
     import torch
     from oracle import cald_oracle as co
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_threads())
     fwd = oracle_forward_fn(model)
     imgs = make_pool(n_images + 1, seed=7)
     random.seed(0)
@@ -142,6 +150,7 @@ def run_reference(args, rank):
         return
     import torch
     from oracle import cald_oracle as co
+    torch.set_num_threads(host_threads())
     fwd = oracle_forward_fn(args.model)
     imgs = make_pool(args.warmup + args.steps, seed=11)
     random.seed(0)
@@ -169,7 +178,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
+    ap.add_argument("--batch", type=int, default=16, help="images per step per GPU")
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--model", default="frcnn", choices=["frcnn", "retinanet"],
                     help="frcnn = BASELINE.json configs[1] (the headline); retinanet = configs[2]")
