@@ -132,6 +132,55 @@ def get_uncertainty(task_model, unlabeled_loader, augs, num_cls, device=0, **eng
     return score_images(eng, images, augs)
 
 
+def _loader_images(unlabeled_loader):
+    """Images of a reference-style loader (tuple_of_images, tuple_of_targets) as u8 HWC arrays.  The baseline scripts
+    feed ToTensor()'d float tensors (lt_c_train.py:109-111); those came from u8 pixels, so x * 255 is exact."""
+    out = []
+    for imgs, _ in unlabeled_loader:
+        for image in imgs:
+            if hasattr(image, "detach"):  # torch CHW float in [0, 1]
+                a = image.detach().cpu().numpy()
+                out.append(np.ascontiguousarray(np.rint(a * 255.0).astype(np.uint8).transpose(1, 2, 0)))
+            else:
+                out.append(_to_u8(image))
+    return out
+
+
+def lt_c_uncertainty(task_model, unlabeled_loader, device=0, chunk=64, **engine_kw):
+    """Drop-in for lt_c_train.get_uncertainty (lt_c_train.py:105-121): list of float, loader order."""
+    eng = engine_for(task_model, _num_classes(task_model), device, **engine_kw)
+    images = _loader_images(unlabeled_loader)
+    out = []
+    for pos in range(0, len(images), chunk):
+        out.extend(float(v) for v in eng.score_ltc(images[pos:pos + chunk]))
+    return out
+
+
+def ls_c_uncertainty(task_model, unlabeled_loader, aves=None, device=0, chunk=16, **engine_kw):
+    """Drop-in for ls_c_train.get_uncertainty (ls_c_train.py:108-155): list of float, loader order.  Draws the six
+    torch.randn planes per image from torch's global CPU generator in the reference's order."""
+    import torch
+    eng = engine_for(task_model, _num_classes(task_model), device, **engine_kw)
+    images = _loader_images(unlabeled_loader)
+    out = []
+    for pos in range(0, len(images), chunk):
+        batch = images[pos:pos + chunk]
+        noise = []
+        for im in batch:
+            # NOTE: the reference draws nothing for an image without reference detections (ls_c_train.py:118-120);
+            # the engine cannot know that before the forward, so the torch stream differs after such an image.
+            noise += [torch.randn((3, im.shape[0], im.shape[1])).numpy() for _ in range(6)]
+        out.extend(float(v) for v in eng.score_lsc(batch, noise))
+    return out
+
+
+def _num_classes(task_model):
+    sd = task_model.state_dict()
+    if "roi_heads.box_predictor.cls_score.weight" in sd:
+        return int(sd["roi_heads.box_predictor.cls_score.weight"].shape[0])
+    return int(sd["head.classification_head.cls_logits.weight"].shape[0]) // 9
+
+
 def cls_kldiv(labeled_loader, cls_corrs, budget, cycle=0):
     """cald_train.py:234-271 (class-balance stage); host-side, O(budget * candidates * classes)."""
     import torch

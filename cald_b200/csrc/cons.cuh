@@ -269,4 +269,104 @@ __global__ void __launch_bounds__(32 * CONS_WARPS) consistency_kernel(ConsArgs a
   }
 }
 
+// ================================================================ baseline scorers on the same detections
+// ---------------------------------------------------------------- LT/C: localisation tightness (lt_c_train.py:89-121)
+// per image: min(1.0, min over detections |calcu_iou(box, prop) + prob_max - 1|) with the script's own IoU
+// (+1 on the intersection sides and on the height of each area only, lt_c_train.py:95-102).  grid = views, block = 128.
+__global__ void ltc_kernel(DetOut det, int det_cap, float* __restrict__ out) {
+  __shared__ float s_min[4];
+  const int v = blockIdx.x;
+  const int n = det.count[v];
+  float best = INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float4 a = det.boxes[(long long)v * det_cap + i];
+    const float4 b = det.props[(long long)v * det_cap + i];
+    const float width = (fminf(a.z, b.z) - fmaxf(a.x, b.x)) + 1.f;
+    const float height = (fminf(a.w, b.w) - fmaxf(a.y, b.y)) + 1.f;
+    float iou = 0.f;
+    if (!(width <= 0.f || height <= 0.f)) {
+      const float aa = (a.z - a.x) * ((a.w - a.y) + 1.f);
+      const float ba = (b.z - b.x) * ((b.w - b.y) + 1.f);
+      const float inter = width * height;
+      iou = inter / ((aa + ba) - inter);
+    }
+    const float u = fabsf((iou + det.prob_max[(long long)v * det_cap + i]) - 1.f);
+    if (u < best) best = u;  // python min(): a NaN candidate is never taken
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 1.0f;  // uncertainty starts at 1.0
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) if (s_min[w] < m) m = s_min[w];
+    out[v] = m;
+  }
+}
+
+// ---------------------------------------------------------------- LS+C: localisation stability (ls_c_train.py:108-155)
+// keys for torch.topk(prob_max, 30): descending prob_max, ties -> lower index.  grid = views.
+__global__ void lsc_keys_kernel(DetOut det, int det_cap, unsigned long long* __restrict__ keys) {
+  const int v = blockIdx.x;
+  const int n = det.count[v];
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    keys[(long long)v * det_cap + i] =
+        ((unsigned long long)desc_key(det.prob_max[(long long)v * det_cap + i]) << 32) | (unsigned)i;
+}
+// grid = B, block = 32 * CONS_WARPS.  sel: sorted top-30 keys of the reference view (topk_select_kernel output,
+// stride TOPK_MAX); aug detections: view index b*A + a.  out[b] = sum(pm * mean_a maxIoU) / sum(pm) - max(1 - pm).
+constexpr int LSC_REF = 30;
+__global__ void __launch_bounds__(32 * CONS_WARPS) lsc_kernel(DetOut ref, DetOut aug, int det_cap, int A,
+                                                              const unsigned long long* __restrict__ sel,
+                                                              double* __restrict__ out) {
+  __shared__ float s_iou[LSC_REF][8];  // [ref box][aug view], A <= 8
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nd = ref.count[b];
+  const int nref = nd > LSC_REF ? LSC_REF : nd;
+  for (int t = warp; t < nref * A; t += CONS_WARPS) {
+    const int r = t / A, a = t - r * A;
+    const int src = nd > LSC_REF ? (int)(sel[(long long)b * TOPK_MAX + r] & 0xffffffffu) : r;
+    const float4 ab = ref.boxes[(long long)b * det_cap + src];
+    const long long ba = (long long)b * A + a;
+    const int na = aug.count[ba];
+    const float a_area = (ab.z - ab.x) * (ab.w - ab.y);
+    float mx = -INFINITY;
+    for (int j = lane; j < na; j += 32) {
+      const float4 bb = aug.boxes[ba * det_cap + j];
+      const float width = fminf(ab.z, bb.z) - fmaxf(ab.x, bb.x);
+      const float height = fminf(ab.w, bb.w) - fmaxf(ab.y, bb.y);
+      const float b_area = (bb.z - bb.x) * (bb.w - bb.y);
+      const float inter = width * height;
+      float iou = inter / (a_area + b_area - inter);
+      if (width < 0.f) iou = 0.f;
+      if (height < 0.f) iou = 0.f;
+      if (iou != iou || iou > mx) mx = (mx != mx) ? mx : iou;  // torch.max propagates NaN
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      if (om != om || (mx == mx && om > mx)) mx = om;
+    }
+    if (lane == 0) s_iou[r][a] = na > 0 ? mx : 0.f;  // an augmented view without boxes adds nothing (ls_c_train.py:136-137)
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (nd == 0) { out[b] = 0.0; return; }  // ls_c_train.py:118-120
+    double num = 0.0, den = 0.0;
+    float u = -INFINITY;
+    for (int r = 0; r < nref; ++r) {
+      const int src = nd > LSC_REF ? (int)(sel[(long long)b * TOPK_MAX + r] & 0xffffffffu) : r;
+      const float pm = ref.prob_max[(long long)b * det_cap + src];
+      double st = 0.0;
+      for (int a = 0; a < A; ++a) st += (double)s_iou[r][a];  // python float accumulation of .item() values
+      st /= 6.0;                                               // the script divides by the literal 6.0
+      num += (double)pm * st;
+      den += (double)pm;
+      u = fmaxf(u, 1.f - pm);
+    }
+    out[b] = num / den - (double)u;
+  }
+}
+
 }  // namespace cald

@@ -1036,7 +1036,8 @@ __global__ void u8_minmax_kernel(const uint8_t* __restrict__ img, long long n, i
 void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const int* hs, const int* ws,
                  const std::vector<cald_aug>& augs, double bp, const double* d_u, int n_u, int* d_cursor,
                  const float* const* d_noise /* [B][n_noise] device planes */,
-                 const int* swap_perms /* [B][n_swap] host, or null */, double* out_cons, double* out_cls) {
+                 const int* swap_perms /* [B][n_swap] host, or null */, double* out_cons, double* out_cls,
+                 int scorer = 0 /* 0: CALD consistency, 1: LS+C stability (ls_c_train.py:108-155) */) {
   Arena& ar = e->arena;
   cudaStream_t st = e->st;
   const int A = (int)augs.size();
@@ -1196,6 +1197,33 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
     e->trace("aug_prep_enqueued");
     detect_views(e, av, d_cuts, aug);
     e->trace("aug_pass_enqueued");
+    if (scorer == 1) {
+      // LS+C: top-30 reference boxes by prob_max, mean over the A noise views of the best IoU, prob_max-weighted mean
+      if (A > 8) throw std::runtime_error("LS+C: at most 8 augmented views");
+      unsigned long long* keys = (unsigned long long*)ar.alloc((size_t)B * dc * 8);
+      unsigned long long* top = (unsigned long long*)ar.alloc((size_t)B * TOPK_MAX * 8);
+      int* top_count = (int*)ar.alloc((size_t)B * 4);
+      double* d_out = (double*)ar.alloc((size_t)B * 8);
+      lsc_keys_kernel<<<B, 128, 0, st>>>(ref.det, dc, keys);
+      TopkGroups tg;
+      memset(&tg, 0, sizeof(tg));
+      tg.keys = keys; tg.stride_outer = dc; tg.inner = 1; tg.dyn_n = ref.det.count; tg.k = LSC_REF;
+      topk_select_kernel<<<B, 1024, 0, st>>>(tg, top, top_count);
+      lsc_kernel<<<B, 32 * CONS_WARPS, 0, st>>>(ref.det, aug.det, dc, A, top, d_out);
+      CALD_CUDA_CHECK(cudaGetLastError());
+      e->launches += 3;
+      CALD_CUDA_CHECK(cudaMemcpyAsync(out_cons, d_out, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+      CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+      check_overflow(e);
+      ar.free(keys); ar.free(top); ar.free(top_count); ar.free(d_out);
+      ar.free(d_geom); ar.free(d_augb);
+      free_viewset(e, aug);
+      for (uint8_t* t : temps) ar.free(t);
+      ar.free(d_img_hw); ar.free(d_cuts); ar.free(d_cls);
+      ar.free(rs.n); ar.free(rs.n_det); ar.free(rs.boxes); ar.free(rs.prob_max); ar.free(rs.prop_idx);
+      free_viewset(e, ref);
+      return;
+    }
     class_max_kernel<<<B * A, 128, ncls1 * 4, st>>>(aug.det, dc, ncls1, e->d_lut, 0, d_cls + (size_t)B * ncls1);
     d_cons = (float*)ar.alloc((size_t)B * A * 4);
     ConsArgs ca;
@@ -1446,7 +1474,7 @@ int cald_load_weights(cald_engine* e, int n, const char* const* names, const flo
 static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, bool on_device, const int* heights,
                       const int* widths, int n_augs, const cald_aug* aug_list, double bp, const double* rng_uniforms,
                       int n_uniforms, int* uniforms_consumed, const float* const* noise, const int* swap_perms,
-                      double* out_consistency, double* out_cls) {
+                      double* out_consistency, double* out_cls, int scorer = 0) {
   API_TRY(e)
   check_ready(e);
   e->arena.reset();
@@ -1494,7 +1522,7 @@ static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, 
     }
     score_chunk(e, B, dptr, heights + pos, widths + pos, augs, bp, d_u, n_uniforms, d_cursor,
                 n_noise ? nz.data() : nullptr, swap_perms ? swap_perms + (size_t)pos * n_swap : nullptr,
-                out_consistency + pos, out_cls + (size_t)pos * (e->C - 1));
+                out_consistency + pos, out_cls ? out_cls + (size_t)pos * (e->C - 1) : nullptr, scorer);
     for (float* d : nz_owned) e->arena.free(d);
     if (di.slab) e->arena.free(di.slab);
   }
@@ -1519,6 +1547,45 @@ int cald_score_device(cald_engine* e, int n_images, const uint8_t* const* d_imag
                       double* out_consistency, double* out_cls) {
   return score_impl(e, n_images, d_images, true, heights, widths, n_augs, augs, bp, rng_uniforms, n_uniforms,
                     uniforms_consumed, d_noise, swap_perms, out_consistency, out_cls);
+}
+
+int cald_score_lsc(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
+                   const float* const* noise, double* out_stability) {
+  // ls_c_train.get_uncertainty: 6 Gaussian-noise views with std 8, 16, ..., 48 (ls_c_train.py:127-129)
+  cald_aug views[6];
+  for (int i = 0; i < 6; ++i) { views[i].kind = CALD_AUG_GAUSS; views[i].param = 8.0 * (i + 1); }
+  return score_impl(e, n_images, images, false, heights, widths, 6, views, 0.0, nullptr, 0, nullptr, noise, nullptr,
+                    out_stability, nullptr, 1);
+}
+
+int cald_score_ltc(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
+                   double* out_uncertainty) {
+  API_TRY(e)
+  check_ready(e);
+  if (e->retina) throw std::runtime_error("LT/C needs the proposals of a Faster R-CNN ('props', frcnn_la.py:131-141)");
+  e->arena.reset();
+  const int dc = e->det_cap;
+  const int maxv = e->cfg.max_views_per_pass > 0 ? e->cfg.max_views_per_pass : 8;
+  for (int pos = 0; pos < n_images; pos += maxv) {
+    const int B = std::min(maxv, n_images - pos);
+    DeviceImages di = upload_images(e, B, images + pos, heights + pos, widths + pos);
+    std::vector<HostView> hv(B);
+    for (int b = 0; b < B; ++b) hv[b] = HostView{di.ptr[b], heights[pos + b], widths[pos + b], 0, -1};
+    ViewSet vs = alloc_viewset(e, B);
+    detect_views(e, hv, nullptr, vs);
+    float* d_out = (float*)e->arena.alloc((size_t)B * 4);
+    ltc_kernel<<<B, 128, 0, e->st>>>(vs.det, dc, d_out);
+    CALD_CUDA_CHECK(cudaGetLastError());
+    KLAUNCH(e);
+    std::vector<float> h(B);
+    CALD_CUDA_CHECK(cudaMemcpyAsync(h.data(), d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, e->st));
+    CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
+    for (int b = 0; b < B; ++b) out_uncertainty[pos + b] = (double)h[b];
+    e->arena.free(d_out);
+    free_viewset(e, vs);
+    e->arena.free(di.slab);
+  }
+  API_CATCH(e)
 }
 
 int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,

@@ -209,6 +209,31 @@ class Engine:
                                               cls.ctypes.data_as(POINTER(c_double))))
         return cons, cls, consumed.value
 
+    def score_lsc(self, images, noise):
+        """LS+C stability (ls_c_train.py:108-155).  noise: 6 float32 [3,H,W] torch.randn planes per image,
+        image-major (std 8, 16, ..., 48 is applied by the engine).  -> float64[n]."""
+        imgs, ptrs, hs, ws = _u8_list(images)
+        n = len(imgs)
+        nz_keep = [np.ascontiguousarray(z, dtype=np.float32) for z in noise]
+        if len(nz_keep) != 6 * n:
+            raise ValueError("LS+C needs 6 noise planes per image")
+        nz_ptrs = (POINTER(c_float) * len(nz_keep))(*[z.ctypes.data_as(POINTER(c_float)) for z in nz_keep])
+        out = np.zeros(n, dtype=np.float64)
+        self._L.cald_score_lsc.argtypes = [c_void_p, c_int, POINTER(POINTER(c_uint8)), POINTER(c_int), POINTER(c_int),
+                                           POINTER(POINTER(c_float)), POINTER(c_double)]
+        self._check(self._L.cald_score_lsc(self._h, n, ptrs, hs, ws, nz_ptrs, out.ctypes.data_as(POINTER(c_double))))
+        return out
+
+    def score_ltc(self, images):
+        """LT/C uncertainty (lt_c_train.py:105-121), Faster R-CNN only.  -> float64[n]."""
+        imgs, ptrs, hs, ws = _u8_list(images)
+        n = len(imgs)
+        out = np.zeros(n, dtype=np.float64)
+        self._L.cald_score_ltc.argtypes = [c_void_p, c_int, POINTER(POINTER(c_uint8)), POINTER(c_int), POINTER(c_int),
+                                           POINTER(c_double)]
+        self._check(self._L.cald_score_ltc(self._h, n, ptrs, hs, ws, out.ctypes.data_as(POINTER(c_double))))
+        return out
+
     def last_per_view(self, n_images, n_augs):
         out = np.zeros(n_images * n_augs, dtype=np.float32)
         self._L.cald_last_per_view.argtypes = [c_void_p, POINTER(c_float), c_int]

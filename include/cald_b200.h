@@ -96,6 +96,17 @@ int cald_score(cald_engine* e, int n_images, const uint8_t* const* images, const
                int* uniforms_consumed, const float* const* noise, const int* swap_perms, double* out_consistency,
                double* out_cls);
 
+/* The two detection-only baseline scorers of the reference, on the same engine:
+ * LS+C  ls_c_train.get_uncertainty (ls_c_train.py:108-155): stability of the 30 most confident reference boxes under
+ *       6 Gaussian-noise views (std 8..48) minus max(1 - prob_max).  noise: torch.randn(image.size()) planes, 6 per
+ *       image, image-major (as for CALD_AUG_GAUSS).  Ties of prob_max at the top-30 cut resolve to the lower index.
+ * LT/C  lt_c_train.get_uncertainty (lt_c_train.py:105-121): min(1, min |calcu_iou(box, prop) + prob_max - 1|) of one
+ *       Faster R-CNN forward per image. */
+int cald_score_lsc(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
+                   const float* const* noise, double* out_stability);
+int cald_score_ltc(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,
+                   double* out_uncertainty);
+
 /* One detector forward per image: task_model([F.to_tensor(img)])[0] (frcnn_la.py:131-141).
  * Outputs are fixed-capacity [n][cap] with counts[n]; cap = box_detections_per_img.
  * scores_cls is [n][cap][num_classes].  Any output pointer may be NULL. */

@@ -292,6 +292,63 @@ def get_uncertainty(forward_fn, images_u8, augs, num_cls, bp=1.3, seeds=None):
     return cons_all, cls_all
 
 
+# ------------------------------------------------------------------ baseline scorers
+def ltc_uncertainty(forward_fn, images_u8):
+    """lt_c_train.get_uncertainty (lt_c_train.py:89-121), including its own calcu_iou."""
+    def calcu_iou(a, b):
+        width = min(a[2], b[2]) - max(a[0], b[0]) + 1
+        height = min(a[3], b[3]) - max(a[1], b[1]) + 1
+        if width <= 0 or height <= 0:
+            return 0
+        aa = (a[2] - a[0]) * (a[3] - a[1] + 1)
+        ba = (b[2] - b[0]) * (b[3] - b[1] + 1)
+        inter = width * height
+        return inter / (aa + ba - inter)
+    out = []
+    for img in images_u8:
+        det = forward_fn(to_tensor(img))
+        unc = 1.0
+        for box, prop, pm in zip(det["boxes"], det["props"], det["prob_max"]):
+            unc = min(unc, torch.abs(calcu_iou(box, prop) + pm - 1).item())
+        out.append(unc)
+    return out
+
+
+def lsc_stability(forward_fn, images_u8):
+    """ls_c_train.get_uncertainty (ls_c_train.py:108-155): six Gaussian views drawn from torch's global generator."""
+    out = []
+    for img in images_u8:
+        det = forward_fn(to_tensor(img))
+        boxes, pm = det["boxes"], det["prob_max"]
+        if boxes.shape[0] == 0:
+            out.append(0.0)
+            continue
+        if len(boxes) > 30:
+            inds = torch.topk(pm, 30)[1]
+            boxes, pm = boxes[inds], pm[inds]
+        stab = [0.0] * len(boxes)
+        u = torch.max(1 - pm).item()
+        views = [gaussian_noise(img, i * 8) for i in range(1, 7)]
+        for v in views:
+            b = forward_fn(v)["boxes"]
+            if len(b) == 0:
+                continue
+            for i, ab in enumerate(boxes):
+                width = torch.min(ab[2], b[:, 2]) - torch.max(ab[0], b[:, 0])
+                height = torch.min(ab[3], b[:, 3]) - torch.max(ab[1], b[:, 1])
+                aa = (ab[2] - ab[0]) * (ab[3] - ab[1])
+                ba = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+                inter = width * height
+                iou = inter / (aa + ba - inter)
+                iou[width < 0] = 0.0
+                iou[height < 0] = 0.0
+                stab[i] += torch.max(iou).item()
+        stab = np.array(stab) / 6.0
+        p = pm.numpy()
+        out.append(np.sum(p * stab) / np.sum(p) - u)
+    return out
+
+
 # ------------------------------------------------------------------ selection
 def cls_kldiv(label_hist_rows, cls_corrs, budget, uniform=False):
     """cald_train.py:234-271 given the per-labeled-image class histograms (rows)."""

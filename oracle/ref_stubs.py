@@ -94,6 +94,19 @@ def retinanet_module():
     return m
 
 
+def baseline_module(name):
+    """'lt_c_train' or 'ls_c_train', unmodified.  ls_c_train.py:52 imports ``cal4od.cal4od_helper``, a module that does
+    not exist in the reference tree; it is aliased to cald.cald_helper, the file the script was
+    evidently written against (it only needs GaussianNoise)."""
+    load()
+    import importlib
+    import cald.cald_helper as hp
+    pkg = _mod("cal4od")
+    pkg.cal4od_helper = hp
+    sys.modules["cal4od.cal4od_helper"] = hp
+    return importlib.import_module(name)
+
+
 def helper_module():
     load()
     import cald.cald_helper as m

@@ -128,3 +128,16 @@ def test_retina_anchor_tables():
     a = ro.grid_anchors((64, 96), [(8, 12), (4, 6), (2, 3), (1, 2), (1, 1)])
     assert [len(x) for x in a] == [864, 216, 54, 18, 9]
     assert a[0][9].tolist() == [8 - 23.0, -11.0, 8 + 23.0, 11.0]   # second cell, stride 8
+
+
+def test_baseline_scorers_oracle_matches_reference_fixture(model):
+    """LT/C and LS+C restatements against lt_c_train / ls_c_train.get_uncertainty (make_golden_baselines.py)"""
+    fwd, synth = model
+    from oracle import cald_oracle as co
+    g = np.load(os.path.join(GOLD, "baseline_scorers.npz"))
+    imgs = [synth.synth_image(int(i), int(h), int(w)) for i, h, w in g["images"]]
+    got = co.ltc_uncertainty(fwd, imgs[:3])
+    assert np.abs(np.array(got) - g["ltc"][:3]).max() <= 1e-5
+    torch.manual_seed(int(g["lsc_seed"]))
+    got = co.lsc_stability(fwd, imgs[:1])
+    assert abs(got[0] - g["lsc"][0]) <= 1e-4
