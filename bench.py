@@ -29,7 +29,6 @@ H, W = 800, 1333
 NUM_CLASSES = 91
 MIN_SIZE, MAX_SIZE = 800, 1333
 AUGS = ['flip', 'cut_out', 'smaller_resize', 'rotation']
-GFLOP_PER_IMAGE = 2160.0  # 5 forwards x 432.0 GFLOP
 METRIC = "unlabeled images scored/sec (FRCNN R50-FPN, 800x1333)"
 WORKLOAD = "FRCNN R50-FPN nc=91, synthetic 1333x800 pool, 1 ref + 4 aug (F,C,D,R) forwards per image"
 # --model retinanet = BASELINE.json configs[2] (RetinaNet R50-FPN, retinanet_cal.py), same pool shape and augmentations
@@ -330,7 +329,7 @@ def main():
                      "note": "achieved = algorithmic 2*MAC of the reference convs/GEMMs / summed CUDA-event kernel "
                              "time; bf16x3 issues 3 MMAs per algorithmic MAC"},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
         v, cores = cpu_baseline(args.cpu_images, model=args.model)
         out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                                "sample": "%d image(s) of the same workload, oracle port (torch CPU fp32)" % args.cpu_images}

@@ -103,6 +103,7 @@ struct ConvParams {
   int c_lo_img;        // image-index offset of the lo plane in the output tensor map
   int res_kb;          // residual-as-MMA: extra identity k-blocks per tile (BLOCK_N / 64), else 0
   int r_lo_img;        // image-index offset of the lo plane in the residual tensor map
+  int a_scale;         // 1, or 2 for a stride-2 1x1 conv: the A tensor map walks the input with element stride 2
 };
 
 // ATen nearest-neighbour source index (UpSampleKernel: nearest_idx), float scale.

@@ -41,6 +41,9 @@ struct ConvOpts {
   // k-block `dy` is the 64-element window (4 pixels x 16 ch) starting at pixel (oy + dy, ox): an overlapping-stride
   // tensor map (pixel stride 32 B, box width 128 B) lets TMA gather it without an im2col buffer.
   bool stem_window = false;
+  // 1x1 conv with stride 2 (ResNet downsample shortcut, tv:models/resnet.py): `in` is the full-resolution tensor and
+  // the TMA tensor map itself skips every other pixel (element strides 2, 2), so no subsampled copy is materialised
+  bool in_stride2 = false;
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -61,12 +64,13 @@ inline PFN_encodeTiled get_encode_tiled() {
 
 // 4-D bf16 tensor map, innermost box = 64 elements (128 B) with 128B swizzle.
 inline CUtensorMap make_tmap(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t b1,
-                             uint32_t b2) {
+                             uint32_t b2, uint32_t estride = 1) {
   CUtensorMap tm;
   cuuint64_t dims[4] = {d0, d1, d2, d3};
   cuuint64_t strides[3] = {d0 * 2, d0 * d1 * 2, d0 * d1 * d2 * 2};
-  cuuint32_t box[4] = {64, b1, b2, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  // with an element stride s the box is given in un-strided elements: s * n of them deliver n
+  cuuint32_t box[4] = {64, b1 * estride, b2 * estride, 1};
+  cuuint32_t es[4] = {1, estride, estride, 1};
   CUresult r = get_encode_tiled()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
                                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -213,7 +217,8 @@ struct ConvEngine {
     if (in.split != split) throw std::runtime_error("conv: activation precision mode mismatch");
     ConvParams p;
     memset(&p, 0, sizeof(p));
-    const bool spatial = (w.taps == 9) || o.out_phase || o.res_mode == RES_NEAREST || o.stem_window;
+    const bool spatial = (w.taps == 9) || o.out_phase || o.res_mode == RES_NEAREST || o.stem_window || o.in_stride2;
+    p.a_scale = o.in_stride2 ? 2 : 1;
     p.Cin = w.cin;
     p.taps = w.taps;
     p.Cout = w.cout_pad;
@@ -227,6 +232,8 @@ struct ConvEngine {
         for (int t = 0; t < 4; ++t) { p.tap_dy[t] = t; p.tap_dx[t] = 0; p.tap_img[t] = 0; }
       } else if (w.taps == 1) {
         if (in.phases != 1) throw std::runtime_error("conv: 1x1 needs a plain input");
+        if (o.in_stride2 && (out.h != (in.h + 1) / 2 || out.w != (in.w + 1) / 2))
+          throw std::runtime_error("conv: stride-2 1x1 output shape mismatch");
         p.tap_dy[0] = p.tap_dx[0] = p.tap_img[0] = 0;
       } else if (o.stride == 2) {
         if (in.phases != 4) throw std::runtime_error("conv: stride-2 3x3 needs a phase-split input");
@@ -318,7 +325,8 @@ struct ConvEngine {
       ta = make_tmap_strided(in.hi, 64, (uint64_t)in.w - 3, in.h, (uint64_t)in.n * (split ? 2 : 1), 32,
                              (uint64_t)in.w * 32, (uint64_t)in.h * in.w * 32, p.tw, p.th);
     else if (spatial)
-      ta = make_tmap(in.hi, in.c, in.w, in.h, (uint64_t)in.phases * in.n * (split ? 2 : 1), p.tw, p.th);
+      ta = make_tmap(in.hi, in.c, in.w, in.h, (uint64_t)in.phases * in.n * (split ? 2 : 1), p.tw, p.th,
+                     o.in_stride2 ? 2 : 1);
     else
       ta = make_tmap(in.hi, in.c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);
     tb = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, split ? 2 : 1, BN, 1);

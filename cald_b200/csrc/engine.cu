@@ -378,10 +378,8 @@ void run_body(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views, co
       if (b.has_ds) {
         ConvOpts o;
         if (b.stride == 2) {
-          Act xs = subsample2(ar, x, st);
-          e->launches += split ? 2 : 1;
-          idt = conv(e, xs, b.ds, V, ho, wo, o);
-          free_act(ar, xs);
+          o.in_stride2 = true;  // the A tensor map skips every other pixel: no subsampled copy
+          idt = conv(e, x, b.ds, V, ho, wo, o);
         } else {
           idt = conv(e, x, b.ds, V, ho, wo, o);
         }
@@ -1216,14 +1214,7 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
       CALD_CUDA_CHECK(cudaStreamSynchronize(st));
       check_overflow(e);
       ar.free(keys); ar.free(top); ar.free(top_count); ar.free(d_out);
-      ar.free(d_geom); ar.free(d_augb);
-      free_viewset(e, aug);
-      for (uint8_t* t : temps) ar.free(t);
-      ar.free(d_img_hw); ar.free(d_cuts); ar.free(d_cls);
-      ar.free(rs.n); ar.free(rs.n_det); ar.free(rs.boxes); ar.free(rs.prob_max); ar.free(rs.prop_idx);
-      free_viewset(e, ref);
-      return;
-    }
+    } else {
     class_max_kernel<<<B * A, 128, ncls1 * 4, st>>>(aug.det, dc, ncls1, e->d_lut, 0, d_cls + (size_t)B * ncls1);
     d_cons = (float*)ar.alloc((size_t)B * A * 4);
     ConsArgs ca;
@@ -1233,10 +1224,12 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
     consistency_kernel<<<dim3(A, B), 32 * CONS_WARPS, 0, st>>>(ca);
     CALD_CUDA_CHECK(cudaGetLastError());
     e->launches += 2;
+    }
     ar.free(d_geom);
     ar.free(d_augb);
   }
   // ---------------- results to host; final means in double as numpy does (cald_train.py:225-228)
+  if (scorer == 0) {
   std::vector<float> h_cons((size_t)B * std::max(A, 1)), h_cls((size_t)B * (1 + A) * ncls1);
   std::vector<int> h_ndet(B);
   if (A > 0) CALD_CUDA_CHECK(cudaMemcpyAsync(h_cons.data(), d_cons, (size_t)B * A * 4, cudaMemcpyDeviceToHost, st));
@@ -1263,7 +1256,8 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
       cls[c] = t / (1 + A);
     }
   }
-  if (A > 0) { free_viewset(e, aug); ar.free(d_cons); }
+  }
+  if (A > 0) { free_viewset(e, aug); if (d_cons) ar.free(d_cons); }
   for (uint8_t* t : temps) ar.free(t);
   ar.free(d_img_hw); ar.free(d_cuts); ar.free(d_cls);
   ar.free(rs.n); ar.free(rs.n_det); ar.free(rs.boxes); ar.free(rs.prob_max); ar.free(rs.prop_idx);

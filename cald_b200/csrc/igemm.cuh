@@ -225,7 +225,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int tap = kb / k_chunks;
           const int c0 = (kb - tap * k_chunks) * IG_BLOCK_K;
           mbar_expect_tx(fb, (SPLIT ? 2 : 1) * (p.a_bytes + Cfg::B_BYTES));
-          const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap], ai = img + p.tap_img[tap];
+          const int ax = x0 * p.a_scale + p.tap_dx[tap], ay = y0 * p.a_scale + p.tap_dy[tap], ai = img + p.tap_img[tap];
           const int bk = tap * p.Cin + c0, bn = nb * BLOCK_N;
           tma_load_4d(sa, &tmA, fb, c0, ax, ay, ai);
           tma_load_4d(sa + Cfg::OFF_B_HI, &tmB, fb, bk, bn, 0, 0);
@@ -500,7 +500,7 @@ __global__ void conv_simt_kernel(ConvParams p, SimtOperands o) {
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int ktot = p.taps * p.Cin;
   for (int tap = 0; tap < p.taps; ++tap) {
-    int iy = y + p.tap_dy[tap], ix = x + p.tap_dx[tap], ii = n + p.tap_img[tap];
+    int iy = y * p.a_scale + p.tap_dy[tap], ix = x * p.a_scale + p.tap_dx[tap], ii = n + p.tap_img[tap];
     if (iy < 0 || iy >= o.H_in || ix < 0 || ix >= o.w_limit) continue;
     const long long abase = (((long long)ii * o.H_in + iy) * o.W_in + ix) * o.pix_stride;
     for (int c = 0; c < p.Cin; ++c) {

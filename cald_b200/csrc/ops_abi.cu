@@ -90,8 +90,11 @@ extern "C" int cald_op_conv2d(const float* x, int n, int h, int w, int cin, cons
     f32_to_split(dr, rs, st);
   }
   Act in = a;
-  if (stride == 2) in = (k == 3) ? phase_split(ar, a, st) : subsample2(ar, a, st);
   ConvOpts o;
+  if (stride == 2) {
+    if (k == 3) in = phase_split(ar, a, st);
+    else o.in_stride2 = true;  // the conv's A tensor map skips every other pixel
+  }
   o.relu = relu != 0;
   o.stride = (k == 3) ? stride : 1;
   o.res_mode = res_mode;
