@@ -174,6 +174,30 @@ def ls_c_uncertainty(task_model, unlabeled_loader, aves=None, device=0, chunk=16
     return out
 
 
+class EngineModel:
+    """The detections-only mode of the engine behind the call shape the reference's evaluation loops use
+    (detection/engine.py:85-158 voc_evaluate, 177-256 coco_evaluate: ``model.eval(); outputs = model(images)`` with
+    ``images`` a list of CHW float tensors in [0, 1]).  Returns the reference's output dicts (frcnn_la.py:131-141 /
+    retinanet_cal.py:479-485, without 'features') as CPU torch tensors -- SURVEY.md 8(f) item 3."""
+
+    def __init__(self, task_model, device=0, **engine_kw):
+        self.engine = engine_for(task_model, _num_classes(task_model), device, **engine_kw)
+
+    def eval(self):
+        return self
+
+    def __call__(self, images):
+        import torch
+        u8 = []
+        for im in images:
+            if hasattr(im, "detach"):
+                a = im.detach().cpu().numpy()
+                u8.append(np.ascontiguousarray(np.rint(a * 255.0).astype(np.uint8).transpose(1, 2, 0)))
+            else:
+                u8.append(_to_u8(im))
+        return [{k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in d.items()} for d in self.engine.detect(u8)]
+
+
 def _num_classes(task_model):
     sd = task_model.state_dict()
     if "roi_heads.box_predictor.cls_score.weight" in sd:
@@ -182,38 +206,41 @@ def _num_classes(task_model):
 
 
 def cls_kldiv(labeled_loader, cls_corrs, budget, cycle=0):
-    """cald_train.py:234-271 (class-balance stage); host-side, O(budget * candidates * classes)."""
+    """The class-balance stage of cald_train.py:234-271, same picks, without its O(budget) recomputation.
+
+    The reference recomputes JS(softmax(mean label histogram) || softmax(class vector)) inside its while loop, but
+    the histogram update is commented out there (cald_train.py:270), so the divergences never change: they are
+    computed once here (same torch ops, float64) and the loop only masks what was already picked.
+    """
     import torch
-    from torch import nn
-    cls_inds = []
-    result = []
+    n_cls = cls_corrs[0].shape[0]
+    hist = []
     for _, targets in labeled_loader:
         for target in targets:
-            cls_corr = [0] * cls_corrs[0].shape[0]
+            row = [0] * n_cls
             for l in target['labels']:
-                cls_corr[l - 1] += 1
-            result.append(cls_corr)
-    for a in list(np.where(np.sum(cls_corrs, axis=1) == 0)[0]):
-        cls_inds.append(a)
-    while len(cls_inds) < budget:
-        kld = nn.KLDivLoss(reduction='none')
-        _cls_corrs = torch.tensor(np.array(cls_corrs))
-        _result = torch.tensor(np.mean(np.array(result), axis=0)).unsqueeze(0)
-        if uniform:
-            p = torch.nn.functional.softmax(_result + _cls_corrs, -1)
-            q = torch.nn.functional.softmax(torch.ones(_result.shape) / len(_result), -1)
-            log_mean = ((p + q) / 2).log()
-            jsdiv = torch.sum(kld(log_mean, p), dim=1) / 2 + torch.sum(kld(log_mean, q), dim=1) / 2
-            jsdiv[cls_inds] = 100
-            cls_inds.append(torch.argmin(jsdiv).item())
-        else:
-            p = torch.nn.functional.softmax(_result, -1)
-            q = torch.nn.functional.softmax(_cls_corrs, -1)
-            log_mean = ((p + q) / 2).log()
-            jsdiv = torch.sum(kld(log_mean, p), dim=1) / 2 + torch.sum(kld(log_mean, q), dim=1) / 2
-            jsdiv[cls_inds] = -1
-            cls_inds.append(torch.argmax(jsdiv).item())
-    return cls_inds
+                row[l - 1] += 1
+            hist.append(row)
+    picked = [int(a) for a in np.where(np.sum(cls_corrs, axis=1) == 0)[0]]  # all-zero class vectors go first (246-247)
+    if len(picked) >= budget:
+        return picked
+    corr = torch.tensor(np.array(cls_corrs))
+    mean_hist = torch.tensor(np.mean(np.array(hist), axis=0)).unsqueeze(0)
+    kld = torch.nn.KLDivLoss(reduction='none')
+    if uniform:   # args.uniform (cald_train.py:254-261): closest to the uniform distribution first
+        p = torch.nn.functional.softmax(mean_hist + corr, -1)
+        q = torch.nn.functional.softmax(torch.ones(mean_hist.shape) / len(mean_hist), -1)
+        fill, pick = 100, torch.argmin
+    else:         # default (262-269): most different from the labeled set's class distribution first
+        p = torch.nn.functional.softmax(mean_hist, -1)
+        q = torch.nn.functional.softmax(corr, -1)
+        fill, pick = -1, torch.argmax
+    log_mean = ((p + q) / 2).log()
+    js = torch.sum(kld(log_mean, p), dim=1) / 2 + torch.sum(kld(log_mean, q), dim=1) / 2
+    while len(picked) < budget:
+        js[picked] = fill
+        picked.append(int(pick(js).item()))
+    return picked
 
 
 def select(uncertainty, cls_corrs, subset, labeled_loader, budget_num, cycle=0, mutual=True):

@@ -61,3 +61,20 @@ def test_lt_c_rejects_retinanet():
     eng.load_state_dict(synth.planted_retinanet_weights(21, 0))
     with pytest.raises(CaldError):
         eng.score_ltc([synth.synth_image(0, 120, 160)])
+
+
+def test_engine_model_serves_the_evaluation_loop(setup):
+    """detection/engine.py's evaluators call model(list_of_float_tensors): same detections as the fixture"""
+    g, imgs, model = setup
+    from cald_b200 import EngineModel
+    det = np.load(os.path.join(GOLD, "frcnn_r50_nc21_detect.npz"))
+    m = EngineModel(model).eval()
+    from cald_b200 import synth
+    ims = [synth.synth_image(int(i), int(h), int(w)) for i, h, w in det["images"][:2]]
+    outs = m([torch.from_numpy(im).permute(2, 0, 1).float().div(255) for im in ims])
+    for k, o in enumerate(outs):
+        assert set(o) >= {"boxes", "labels", "scores"} and o["labels"].dtype == torch.int64
+        n = min(10, len(det["%d_scores" % k]), len(o["scores"]))
+        assert np.array_equal(o["labels"].numpy()[:n], det["%d_labels" % k][:n])
+        assert np.abs(o["scores"].numpy()[:n] - det["%d_scores" % k][:n]).max() < 1e-3
+        assert np.abs(o["boxes"].numpy()[:n] - det["%d_boxes" % k][:n]).max() < 5e-2
