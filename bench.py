@@ -32,6 +32,11 @@ AUGS = ['flip', 'cut_out', 'smaller_resize', 'rotation']
 METRIC = "unlabeled images scored/sec (FRCNN R50-FPN, 800x1333)"
 WORKLOAD = "FRCNN R50-FPN nc=91, synthetic 1333x800 pool, 1 ref + 4 aug (F,C,D,R) forwards per image"
 # --model retinanet = BASELINE.json configs[2] (RetinaNet R50-FPN, retinanet_cal.py), same pool shape and augmentations
+# DRAM bytes per conv launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu) averaged over the 148 igemm_tc_kernel
+# launches of one default step (batch 16: a 16-view reference pass + a 64-view augmented pass); source:
+# profiles/r01_igemm_dram_step.csv, captured with tools/final_measure.sh.  Only valid for the default FRCNN workload.
+NCU_DRAM_BYTES_PER_CONV_LAUNCH = 1617.1e6
+NCU_DRAM_BATCH = 16
 METRIC_RETINA = "unlabeled images scored/sec (RetinaNet R50-FPN, 800x1333)"
 WORKLOAD_RETINA = "RetinaNet R50-FPN nc=91, synthetic 1333x800 pool, 1 ref + 4 aug (F,C,D,R) forwards per image"
 
@@ -263,6 +268,7 @@ def main():
     ms = eng.event_elapsed_ms(0, 1)
     k1, _ = eng.counters()
     conv_ms, conv_launches, conv_flops = eng.profile_read()
+    conv_bytes = sum(r[4] for r in eng.profile_layers()) * 1e6  # algorithmic HBM bytes of the timed conv launches
     if args.layers and rank == 0:
         rows = sorted(eng.profile_layers(), key=lambda r: -r[2])
         with open(args.layers, "w") as f:
@@ -321,13 +327,18 @@ def main():
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3 + 200 * B * 8,
                 "d2h_bytes_per_step": B * (len(AUGS) + (1 + len(AUGS)) * (NUM_CLASSES - 1) + 1) * 4 + 4},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                     "frac": achieved / peak_tf if peak_tf else None,
+                     "traffic": NCU_DRAM_BYTES_PER_CONV_LAUNCH if (not retina and B == NCU_DRAM_BATCH) else None,
+                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, mean over the 148 conv "
+                                     "launches of one step; profiles/r01_igemm_dram_step.csv)",
+                     "algorithmic_bytes_per_launch": conv_bytes / conv_launches if conv_launches else None,
                      "kernel": "igemm_tc_kernel (tcgen05 implicit-GEMM conv/GEMM, all instantiations)",
                      "launches": int(conv_launches), "kernel_ms_per_step": conv_ms / args.steps,
                      "algorithmic_gflop_per_step": conv_flops / args.steps / 1e9,
                      "share_of_step": conv_ms / ms if ms else None, "peak_source": peak_src,
                      "note": "achieved = algorithmic 2*MAC of the reference convs/GEMMs / summed CUDA-event kernel "
-                             "time; bf16x3 issues 3 MMAs per algorithmic MAC"},
+                             "time; the fp32-faithful bf16x3 arithmetic issues 3 tensor-core MACs per algorithmic MAC, "
+                             "so the kernel's own ceiling is peak/3"},
     }
     if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
         v, cores = cpu_baseline(args.cpu_images, model=args.model)

@@ -1241,8 +1241,9 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
   for (int b = 0; b < B; ++b) {
     double* cls = out_cls + (size_t)b * ncls1;
     if (h_ndet[b] == 0 || A == 0) {
-      // empty reference prediction: consistency 0.0, class vector = the (all-zero) reference row (cald_train.py:118-121)
-      out_cons[b] = 0.0;
+      // empty reference prediction: consistency 0.0, class vector = the (all-zero) reference row (cald_train.py:118-121);
+      // no augmentation at all: np.mean([]) = nan (cald_train.py:225) and the class vector is the reference row
+      out_cons[b] = h_ndet[b] == 0 ? 0.0 : std::nan("");
       for (int c = 0; c < ncls1; ++c) cls[c] = (double)h_cls[(size_t)b * ncls1 + c];
       for (int a = 0; a < A; ++a) e->last_per_view.push_back(0.f);
       continue;

@@ -89,3 +89,16 @@ def test_batched_equals_single(setup):
         c, _ = api.score_images(eng, [img], ['flip', 'smaller_resize', 'rotation'])
         b.append(c[0])
     assert np.allclose(a, b, atol=1e-6)
+
+
+def test_degenerate_calls(setup):
+    """empty pool -> empty lists; no augmentation -> np.mean([]) = nan per image (cald_train.py:225) with the
+    reference view's class vector"""
+    eng, w, cfg, fo, synth = setup
+    from cald_b200 import api
+    assert api.score_images(eng, [], AUGS) == ([], [])
+    img = synth.synth_image(0, 200, 300)
+    cons, cls = api.score_images(eng, [img], [])
+    assert len(cons) == 1 and np.isnan(cons[0])
+    full, full_cls = api.score_images(eng, [img], ['flip'])
+    assert cls[0].shape == full_cls[0].shape and (cls[0] >= 0).all()
