@@ -1215,48 +1215,48 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
       check_overflow(e);
       ar.free(keys); ar.free(top); ar.free(top_count); ar.free(d_out);
     } else {
-    class_max_kernel<<<B * A, 128, ncls1 * 4, st>>>(aug.det, dc, ncls1, e->d_lut, 0, d_cls + (size_t)B * ncls1);
-    d_cons = (float*)ar.alloc((size_t)B * A * 4);
-    ConsArgs ca;
-    ca.ref = rs; ca.aug_boxes = d_augb; ca.det = aug.det; ca.det_cap = dc;
-    ca.ref_scores = ref.scores; ca.aug_scores = aug.scores; ca.cap = e->cap; ca.C = C; ca.A = A;
-    ca.bp = (float)bp; ca.out = d_cons;
-    consistency_kernel<<<dim3(A, B), 32 * CONS_WARPS, 0, st>>>(ca);
-    CALD_CUDA_CHECK(cudaGetLastError());
-    e->launches += 2;
+      class_max_kernel<<<B * A, 128, ncls1 * 4, st>>>(aug.det, dc, ncls1, e->d_lut, 0, d_cls + (size_t)B * ncls1);
+      d_cons = (float*)ar.alloc((size_t)B * A * 4);
+      ConsArgs ca;
+      ca.ref = rs; ca.aug_boxes = d_augb; ca.det = aug.det; ca.det_cap = dc;
+      ca.ref_scores = ref.scores; ca.aug_scores = aug.scores; ca.cap = e->cap; ca.C = C; ca.A = A;
+      ca.bp = (float)bp; ca.out = d_cons;
+      consistency_kernel<<<dim3(A, B), 32 * CONS_WARPS, 0, st>>>(ca);
+      CALD_CUDA_CHECK(cudaGetLastError());
+      e->launches += 2;
     }
     ar.free(d_geom);
     ar.free(d_augb);
   }
   // ---------------- results to host; final means in double as numpy does (cald_train.py:225-228)
   if (scorer == 0) {
-  std::vector<float> h_cons((size_t)B * std::max(A, 1)), h_cls((size_t)B * (1 + A) * ncls1);
-  std::vector<int> h_ndet(B);
-  if (A > 0) CALD_CUDA_CHECK(cudaMemcpyAsync(h_cons.data(), d_cons, (size_t)B * A * 4, cudaMemcpyDeviceToHost, st));
-  CALD_CUDA_CHECK(cudaMemcpyAsync(h_cls.data(), d_cls, h_cls.size() * 4, cudaMemcpyDeviceToHost, st));
-  CALD_CUDA_CHECK(cudaMemcpyAsync(h_ndet.data(), rs.n_det, B * 4, cudaMemcpyDeviceToHost, st));
-  CALD_CUDA_CHECK(cudaStreamSynchronize(st));
-  check_overflow(e);
-  e->trace("results_on_host");
-  for (int b = 0; b < B; ++b) {
-    double* cls = out_cls + (size_t)b * ncls1;
-    if (h_ndet[b] == 0 || A == 0) {
-      // empty reference prediction: consistency 0.0, class vector = the (all-zero) reference row (cald_train.py:118-121);
-      // no augmentation at all: np.mean([]) = nan (cald_train.py:225) and the class vector is the reference row
-      out_cons[b] = h_ndet[b] == 0 ? 0.0 : std::nan("");
-      for (int c = 0; c < ncls1; ++c) cls[c] = (double)h_cls[(size_t)b * ncls1 + c];
-      for (int a = 0; a < A; ++a) e->last_per_view.push_back(0.f);
-      continue;
+    std::vector<float> h_cons((size_t)B * std::max(A, 1)), h_cls((size_t)B * (1 + A) * ncls1);
+    std::vector<int> h_ndet(B);
+    if (A > 0) CALD_CUDA_CHECK(cudaMemcpyAsync(h_cons.data(), d_cons, (size_t)B * A * 4, cudaMemcpyDeviceToHost, st));
+    CALD_CUDA_CHECK(cudaMemcpyAsync(h_cls.data(), d_cls, h_cls.size() * 4, cudaMemcpyDeviceToHost, st));
+    CALD_CUDA_CHECK(cudaMemcpyAsync(h_ndet.data(), rs.n_det, B * 4, cudaMemcpyDeviceToHost, st));
+    CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+    check_overflow(e);
+    e->trace("results_on_host");
+    for (int b = 0; b < B; ++b) {
+      double* cls = out_cls + (size_t)b * ncls1;
+      if (h_ndet[b] == 0 || A == 0) {
+        // empty reference prediction: consistency 0.0, class vector = the (all-zero) reference row (cald_train.py:118-121);
+        // no augmentation at all: np.mean([]) = nan (cald_train.py:225) and the class vector is the reference row
+        out_cons[b] = h_ndet[b] == 0 ? 0.0 : std::nan("");
+        for (int c = 0; c < ncls1; ++c) cls[c] = (double)h_cls[(size_t)b * ncls1 + c];
+        for (int a = 0; a < A; ++a) e->last_per_view.push_back(0.f);
+        continue;
+      }
+      double s = 0.0;
+      for (int a = 0; a < A; ++a) { s += (double)h_cons[(size_t)b * A + a]; e->last_per_view.push_back(h_cons[(size_t)b * A + a]); }
+      out_cons[b] = s / A;
+      for (int c = 0; c < ncls1; ++c) {
+        double t = (double)h_cls[(size_t)b * ncls1 + c];
+        for (int a = 0; a < A; ++a) t += (double)h_cls[((size_t)B + (size_t)b * A + a) * ncls1 + c];
+        cls[c] = t / (1 + A);
+      }
     }
-    double s = 0.0;
-    for (int a = 0; a < A; ++a) { s += (double)h_cons[(size_t)b * A + a]; e->last_per_view.push_back(h_cons[(size_t)b * A + a]); }
-    out_cons[b] = s / A;
-    for (int c = 0; c < ncls1; ++c) {
-      double t = (double)h_cls[(size_t)b * ncls1 + c];
-      for (int a = 0; a < A; ++a) t += (double)h_cls[((size_t)B + (size_t)b * A + a) * ncls1 + c];
-      cls[c] = t / (1 + A);
-    }
-  }
   }
   if (A > 0) { free_viewset(e, aug); if (d_cons) ar.free(d_cons); }
   for (uint8_t* t : temps) ar.free(t);
