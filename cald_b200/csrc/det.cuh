@@ -370,9 +370,16 @@ __device__ __forceinline__ void bilinear_prep(float v, int size, int& lo, int& h
   l = v - (float)lo;
   h = 1.f - l;
 }
-__global__ void __launch_bounds__(256) roialign_kernel(RoiFeats F, const float4* __restrict__ props,
-                                                       const int* __restrict__ prop_count, int cap,
-                                                       bf16* __restrict__ ohi, bf16* __restrict__ olo) {
+// The 14 sample rows and 14 sample columns of a RoI (7 bins x 2 samples) are prepared ONCE per RoI by 28 threads and
+// broadcast from shared memory; before, every lane of every warp recomputed them for each of its samples (about a
+// quarter of the kernel's instructions, which is issue-bound: ncu issue-active 78 %, L1 hit rate 78 %).
+// 7 warps: each owns exactly 7 of the 49 bins.
+constexpr int ROI_THREADS = 224;
+__global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiFeats F, const float4* __restrict__ props,
+                                                               const int* __restrict__ prop_count, int cap,
+                                                               bf16* __restrict__ ohi, bf16* __restrict__ olo) {
+  __shared__ int s_lo[2][14], s_hi[2][14], s_bad[2][14];
+  __shared__ float s_l[2][14], s_h[2][14];
   const int v = blockIdx.y, r = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = F.C;  // 256
@@ -390,38 +397,52 @@ __global__ void __launch_bounds__(256) roialign_kernel(RoiFeats F, const float4*
   const float x1 = box.x * sc, y1 = box.y * sc, x2 = box.z * sc, y2 = box.w * sc;
   const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
   const float bw = rw / 7.f, bh = rh / 7.f;
+  if (threadIdx.x < 28) {
+    const int dim = threadIdx.x / 14, k = threadIdx.x - dim * 14;
+    const int pb = k >> 1, i = k & 1;
+    const float start = dim == 0 ? y1 : x1, bsz = dim == 0 ? bh : bw;
+    const float coord = start + (float)pb * bsz + ((float)i + 0.5f) * bsz / 2.f;
+    int lo, hi; float l, h; bool bad;
+    bilinear_prep(coord, dim == 0 ? H : W, lo, hi, l, h, bad);
+    s_lo[dim][k] = lo; s_hi[dim][k] = hi; s_l[dim][k] = l; s_h[dim][k] = h; s_bad[dim][k] = bad ? 1 : 0;
+  }
+  __syncthreads();
   const bf16* fhi = F.hi[lv] + (long long)v * H * W * C;
   const bf16* flo = F.lo[lv] ? F.lo[lv] + (long long)v * H * W * C : nullptr;
-  for (int bin = warp; bin < 49; bin += 8) {
+  for (int bin = warp; bin < 49; bin += ROI_THREADS / 32) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (live) {
-      const int ph = bin / 7, pw = bin % 7;
+      const int ph = bin / 7, pw = bin - ph * 7;
 #pragma unroll
       for (int iy = 0; iy < 2; ++iy) {
-        float y = y1 + (float)ph * bh + ((float)iy + 0.5f) * bh / 2.f;
-        int ylo, yhi; float ly, hy; bool ybad;
-        bilinear_prep(y, H, ylo, yhi, ly, hy, ybad);
+        const int ky = ph * 2 + iy;
+        const int ylo = s_lo[0][ky], yhi = s_hi[0][ky];
+        const float ly = s_l[0][ky], hy = s_h[0][ky];
+        const bool ybad = s_bad[0][ky] != 0;
 #pragma unroll
         for (int ix = 0; ix < 2; ++ix) {
-          float x = x1 + (float)pw * bw + ((float)ix + 0.5f) * bw / 2.f;
-          int xlo, xhi; float lx, hx; bool xbad;
-          bilinear_prep(x, W, xlo, xhi, lx, hx, xbad);
-          if (ybad || xbad) continue;
+          const int kx = pw * 2 + ix;
+          if (ybad || s_bad[1][kx] != 0) continue;
+          const int xlo = s_lo[1][kx], xhi = s_hi[1][kx];
+          const float lx = s_l[1][kx], hx = s_h[1][kx];
           const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
           const long long o1 = ((long long)ylo * W + xlo) * C + lane * 8, o2 = ((long long)ylo * W + xhi) * C + lane * 8;
           const long long o3 = ((long long)yhi * W + xlo) * C + lane * 8, o4 = ((long long)yhi * W + xhi) * C + lane * 8;
           float v1[8], v2[8], v3[8], v4[8];
           auto ld = [&](long long off, float* dst) {
-            uint4 a = *reinterpret_cast<const uint4*>(fhi + off);
-            const bf16* pa = reinterpret_cast<const bf16*>(&a);
+            const uint4 a = *reinterpret_cast<const uint4*>(fhi + off);
+            const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
             if (flo) {
-              uint4 b = *reinterpret_cast<const uint4*>(flo + off);
-              const bf16* pb = reinterpret_cast<const bf16*>(&b);
+              const uint4 b = *reinterpret_cast<const uint4*>(flo + off);
+              const uint32_t* pb2 = reinterpret_cast<const uint32_t*>(&b);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) dst[k] = join_bf16(pa[k], pb[k]);
+              for (int q = 0; q < 4; ++q) join_pack2(pa[q], pb2[q], dst[2 * q], dst[2 * q + 1]);
             } else {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) dst[k] = __bfloat162float(pa[k]);
+              for (int q = 0; q < 4; ++q) {
+                dst[2 * q] = __uint_as_float(pa[q] << 16);
+                dst[2 * q + 1] = __uint_as_float(pa[q] & 0xffff0000u);
+              }
             }
           };
           ld(o1, v1); ld(o2, v2); ld(o3, v3); ld(o4, v4);
@@ -432,15 +453,12 @@ __global__ void __launch_bounds__(256) roialign_kernel(RoiFeats F, const float4*
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] /= 4.f;
     }
-    bf16 hh[8], ll[8];
+    uint32_t ph4[4], pl4[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) split_bf16(acc[k], hh[k], ll[k]);
+    for (int q = 0; q < 4; ++q) split_pack2(acc[2 * q], acc[2 * q + 1], ph4[q], pl4[q]);
     const long long off = orow + (long long)bin * C + lane * 8;
-    *reinterpret_cast<uint4*>(ohi + off) = make_uint4(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]),
-                                                      pack_bf16x2(hh[4], hh[5]), pack_bf16x2(hh[6], hh[7]));
-    if (olo)
-      *reinterpret_cast<uint4*>(olo + off) = make_uint4(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]),
-                                                        pack_bf16x2(ll[4], ll[5]), pack_bf16x2(ll[6], ll[7]));
+    *reinterpret_cast<uint4*>(ohi + off) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
+    if (olo) *reinterpret_cast<uint4*>(olo + off) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
   }
 }
 

@@ -547,7 +547,7 @@ void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views
       F.scale[l] = (float)std::pow(2.0, std::round(std::log2((double)pf[l].h / (double)Hp)));
     }
     F.C = 256;
-    roialign_kernel<<<dim3(cap, V), 256, 0, st>>>(F, props, prop_count, cap, roi.hi, roi.lo());
+    roialign_kernel<<<dim3(cap, V), ROI_THREADS, 0, st>>>(F, props, prop_count, cap, roi.hi, roi.lo());
     CALD_CUDA_CHECK(cudaGetLastError());
     KLAUNCH(e);
   }

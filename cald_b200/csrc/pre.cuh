@@ -87,42 +87,85 @@ __global__ void view_preprocess_kernel(const ViewDesc* __restrict__ views, const
   out[(((long long)v * Hp + oy) * Wp + ox) * 3 + c] = val;
 }
 
-// Value of the normalised / resized / zero-padded detector input at integer position (c, iy, ix) of view d.
-__device__ __forceinline__ float view_input_value(const ViewDesc& d, const CutRects* cut, int c, int oy, int ox) {
-  if (oy < 0 || ox < 0 || oy >= d.rh || ox >= d.rw) return 0.f;
-  const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
-  const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
-  const float sh = (float)d.sh / (float)d.rh, sw = (float)d.sw / (float)d.rw;
-  float fy = sh * ((float)oy + 0.5f) - 0.5f;
-  if (fy < 0.f) fy = 0.f;
-  float fx = sw * ((float)ox + 0.5f) - 0.5f;
-  if (fx < 0.f) fx = 0.f;
-  int y0 = (int)fy, x0 = (int)fx;
-  int y1 = y0 + ((y0 < d.sh - 1) ? 1 : 0), x1 = x0 + ((x0 < d.sw - 1) ? 1 : 0);
-  float ly = fy - (float)y0, lx = fx - (float)x0;
-  if (ly == 0.f && lx == 0.f) return src_pixel(d, cut, c, y0, x0, mean, stdv);  // identity resize: exact copy
-  float hy = 1.f - ly, hx = 1.f - lx;
-  float p00 = src_pixel(d, cut, c, y0, x0, mean, stdv), p01 = src_pixel(d, cut, c, y0, x1, mean, stdv);
-  float p10 = src_pixel(d, cut, c, y1, x0, mean, stdv), p11 = src_pixel(d, cut, c, y1, x1, mean, stdv);
-  return hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
-}
-
 // Fused transform + space-to-depth for the stem: writes the padded phase image
 //   S[v][pr][pc][(py*2+px)*3 + c] = input(c, 2*(pr-2)+py, 2*(pc-2)+px)   (channels 12..15 = 0), split bf16,
 // with pr in [0, Ho+3), pc in [0, Wo+3).  One thread per (pr, pc): 2 x 32-byte stores.
+// The per-pixel work (resize coordinates, cutout test, flip index) is done once for the three channels, and the two
+// fp32 divisions of F.to_tensor + normalize, (p / 255 - mean) / std, come from a per-block table built with exactly
+// those operations (bit-identical results; noise views, whose values are not u8, take the arithmetic path).
 __global__ void view_stem_input_kernel(const ViewDesc* __restrict__ views, const CutRects* __restrict__ cuts, int Hs,
                                        int Ws, bf16* __restrict__ ohi, bf16* __restrict__ olo) {
+  __shared__ float s_unit[256];      // p / 255
+  __shared__ float s_norm[3][256];   // (p / 255 - mean_c) / std_c
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const float u = (float)i / 255.f;
+    s_unit[i] = u;
+    s_norm[0][i] = (u - 0.485f) / 0.229f;
+    s_norm[1][i] = (u - 0.456f) / 0.224f;
+    s_norm[2][i] = (u - 0.406f) / 0.225f;
+  }
+  __syncthreads();
   const int v = blockIdx.z, pr = blockIdx.y;
   const int pc = blockIdx.x * blockDim.x + threadIdx.x;
   if (pc >= Ws) return;
   const ViewDesc d = views[v];
   const CutRects* cut = d.n_cut_slot >= 0 ? &cuts[d.n_cut_slot] : nullptr;
+  const float sh = (float)d.sh / (float)d.rh, sw = (float)d.sw / (float)d.rw;
+  // normalised value of the three channels of source pixel (y, x)
+  auto fetch3 = [&](int y, int x, float* out) {
+    bool zero = false;
+    if (cut) {
+      for (int k = 0; k < cut->n; ++k)
+        zero |= (x >= cut->rect[k][0] && x < cut->rect[k][2] && y >= cut->rect[k][1] && y < cut->rect[k][3]);
+    }
+    const int sx = d.flip ? (d.sw - 1 - x) : x;
+    const uint8_t* px = d.src + ((long long)y * d.sw + sx) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int p = zero ? 0 : (int)px[(d.perm >> (2 * c)) & 3];
+      if (!d.noise) {
+        out[c] = s_norm[c][p];
+      } else {
+        const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+        const float stdv = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+        float val = s_unit[p];
+        const float nz = d.noise[((long long)c * d.sh + y) * d.sw + x];
+        if (d.noise_mode == 1) {
+          val = val + (nz * d.n0) / 255.0f;
+        } else {
+          if (nz < d.n0) val = d.n2;
+          if (nz > d.n1) val = d.n3;
+        }
+        out[c] = (val - mean) / stdv;
+      }
+    }
+  };
   float val[16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const int iy = 2 * (pr - 2) + (q >> 1), ix = 2 * (pc - 2) + (q & 1);
+    const int oy = 2 * (pr - 2) + (q >> 1), ox = 2 * (pc - 2) + (q & 1);
+    float* o = &val[q * 3];
+    if (oy < 0 || ox < 0 || oy >= d.rh || ox >= d.rw) {  // zero padding of the batched image
+      o[0] = o[1] = o[2] = 0.f;
+      continue;
+    }
+    // ATen area_pixel_compute_source_index, scale = in / out in float (recompute_scale_factor=True)
+    float fy = sh * ((float)oy + 0.5f) - 0.5f;
+    if (fy < 0.f) fy = 0.f;
+    float fx = sw * ((float)ox + 0.5f) - 0.5f;
+    if (fx < 0.f) fx = 0.f;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    if (ly == 0.f && lx == 0.f) {  // identity resize: exact copy
+      fetch3(y0, x0, o);
+      continue;
+    }
+    const int y1 = y0 + ((y0 < d.sh - 1) ? 1 : 0), x1 = x0 + ((x0 < d.sw - 1) ? 1 : 0);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    float p00[3], p01[3], p10[3], p11[3];
+    fetch3(y0, x0, p00); fetch3(y0, x1, p01); fetch3(y1, x0, p10); fetch3(y1, x1, p11);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) val[q * 3 + c] = view_input_value(d, cut, c, iy, ix);
+    for (int c = 0; c < 3; ++c) o[c] = hy * (hx * p00[c] + lx * p01[c]) + ly * (hx * p10[c] + lx * p11[c]);
   }
   val[12] = val[13] = val[14] = val[15] = 0.f;
   uint32_t ph[8], pl[8];
