@@ -107,17 +107,23 @@ struct cald_engine {
   uint8_t* pinned = nullptr;   // staging for pageable caller buffers (H2D from pinned memory runs at link speed)
   size_t pinned_cap = 0;
 
-  ~cald_engine() {
-    if (d_lut) cudaFree(d_lut);
-    if (pinned) cudaFreeHost(pinned);
-    for (auto& kv : pil_cache) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+  // device copies of the detector's weights (re-uploaded by every cald_load_weights: the AL cycle retrains the model)
+  void free_weights() {
     auto fw = [](ConvW& w) { free_conv_weight(w); };
     fw(stem); fw(rpn_conv); fw(rpn_out); fw(fc6); fw(fc7); fw(pred);
     fw(ret_p6); fw(ret_p7); fw(ret_cls_out); fw(ret_reg_out);
     for (int i = 0; i < 4; ++i) { fw(ret_cls_tower[i]); fw(ret_reg_tower[i]); }
-    if (d_overflow) cudaFree(d_overflow);
     for (int i = 0; i < 4; ++i) { fw(fpn_inner[i]); fw(fpn_layer[i]); }
     for (auto& l : layers) for (auto& b : l) { fw(b.c1); fw(b.c2); fw(b.c3); if (b.has_ds) fw(b.ds); }
+    layers.clear();
+    weights_ready = false;
+  }
+  ~cald_engine() {
+    if (d_lut) cudaFree(d_lut);
+    if (pinned) cudaFreeHost(pinned);
+    for (auto& kv : pil_cache) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+    free_weights();
+    if (d_overflow) cudaFree(d_overflow);
     arena.destroy();
     if (st) cudaStreamDestroy(st);
   }
@@ -1455,6 +1461,8 @@ int cald_load_weights(cald_engine* e, int n, const char* const* names, const flo
                       const int64_t* shapes) {
   API_TRY(e)
   CALD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));  // nothing may still be reading the previous weights
+  e->free_weights();
   for (int i = 0; i < n; ++i) {
     HostTensor t;
     size_t cnt = 1;

@@ -102,3 +102,22 @@ def test_degenerate_calls(setup):
     assert len(cons) == 1 and np.isnan(cons[0])
     full, full_cls = api.score_images(eng, [img], ['flip'])
     assert cls[0].shape == full_cls[0].shape and (cls[0] >= 0).all()
+
+
+def test_reloading_weights_frees_the_previous_copy(setup):
+    """get_uncertainty re-reads the state_dict every cycle (the model was retrained in between): no device leak"""
+    eng, w, cfg, fo, synth = setup
+    from cald_b200 import api
+    img = synth.synth_image(2, 200, 300)
+    random.seed(1)
+    before = api.score_images(eng, [img], ['flip'])[0][0]
+    eng.load_state_dict(w)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(4):
+        eng.load_state_dict(w)
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < (32 << 20), (free0, free1)   # one copy is ~170 MB
+    random.seed(1)
+    assert api.score_images(eng, [img], ['flip'])[0][0] == before
