@@ -65,7 +65,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
 // ---------------------------------------------------------------------------------
 // Conv / GEMM problem description shared by the tcgen05 kernel and the SIMT checker.
 // ---------------------------------------------------------------------------------
-enum { OUT_NHWC = 0, OUT_PHASE = 1 };
 enum { RES_NONE = 0, RES_SAME = 1, RES_NEAREST = 2 };
 
 struct ConvParams {
@@ -74,7 +73,7 @@ struct ConvParams {
   int H, W;            // OUTPUT spatial size (== input size for stride 1); linear: H = 1, W = M
   int Cin;             // multiple of 64
   int taps;            // 1 (1x1 / linear) or 9 (3x3)
-  int tap_dy[9], tap_dx[9], tap_img[9];  // per tap: input offset and image-index offset (phase planes)
+  int tap_dy[9], tap_dx[9], tap_img[9];  // per tap: input pixel offset (and an image-index offset, unused = 0)
   int a_lo_img;        // image-index offset of the lo plane in the A tensor map
   // ---- tiling
   int tw, th;          // spatial tile, tw * th <= 128 (rows beyond tw*th of the MMA tile are dead)
@@ -91,13 +90,11 @@ struct ConvParams {
   const bf16* res_hi;
   const bf16* res_lo;
   int res_H, res_W;    // for RES_NEAREST: source size
-  int out_mode;        // OUT_*
   bf16* out_hi;        // null when only fp32 output is wanted
   bf16* out_lo;        // null in bf16 (non-split) mode
   float* out_f32;      // optional fp32 NHWC copy (heads)
   int ldc;             // channel stride of the output row (>= Cout)
   int res_ld;
-  int out_H2, out_W2;  // OUT_PHASE: ceil(H/2), ceil(W/2)
   int kc;              // chunked accumulation: k-blocks per TMEM accumulation chunk
   int tma_store;       // 1: epilogue stages 64-channel groups in smem and stores them with TMA (NHWC bf16 outputs)
   int c_lo_img;        // image-index offset of the lo plane in the output tensor map
@@ -117,11 +114,6 @@ __host__ __device__ inline int nearest_src(int dst, int in_size, int out_size) {
 
 // Row (pixel) -> output element offset (without channel).  Returns -1 if masked.
 __device__ __forceinline__ long long out_row_offset(const ConvParams& p, int n, int y, int x) {
-  if (p.out_mode == OUT_PHASE) {
-    int ph = (y & 1) * 2 + (x & 1);
-    long long img = (long long)ph * p.n_img + n;
-    return ((img * p.out_H2 + (y >> 1)) * p.out_W2 + (x >> 1)) * (long long)p.ldc;
-  }
   return (((long long)n * p.H + y) * p.W + x) * (long long)p.ldc;
 }
 

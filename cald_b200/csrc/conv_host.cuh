@@ -9,13 +9,12 @@
 
 namespace cald {
 
-// ---- split-bf16 NHWC activation: planes [hi | lo], each [phases*n][h][w][c]
+// ---- split-bf16 NHWC activation: planes [hi | lo], each [n][h][w][c]
 struct Act {
   bf16* hi = nullptr;
   int n = 0, h = 0, w = 0, c = 0;
-  int phases = 1;
   bool split = true;
-  size_t plane_elems() const { return (size_t)phases * n * h * w * c; }
+  size_t plane_elems() const { return (size_t)n * h * w * c; }
   bf16* lo() const { return split ? hi + plane_elems() : nullptr; }
   size_t bytes() const { return plane_elems() * (split ? 2 : 1) * sizeof(bf16); }
 };
@@ -30,11 +29,9 @@ struct ConvW {
 
 struct ConvOpts {
   bool relu = false;
-  int stride = 1;               // 3x3: 1 or 2 (2 => input must be phase-split); 1x1: caller subsamples first
+  int stride = 1;               // 3x3: 1 or 2 (2: the A tensor map walks the full-resolution input with element stride 2)
   int res_mode = RES_NONE;
   const Act* res = nullptr;
-  bool out_phase = false;       // write the output phase-split (feeds a stride-2 3x3)
-  int full_h = 0, full_w = 0;   // out_phase: logical (full-resolution) output size
   float* out_f32 = nullptr;     // fp32 NHWC output instead of / in addition to split bf16
   bool no_bf16_out = false;
   // stem mode: `in` is the padded space-to-depth image [n][Ho+3][Wo+3][16]; the 7x7/s2 conv is a 4x4/s1 conv whose
@@ -217,7 +214,7 @@ struct ConvEngine {
     if (in.split != split) throw std::runtime_error("conv: activation precision mode mismatch");
     ConvParams p;
     memset(&p, 0, sizeof(p));
-    const bool spatial = (w.taps == 9) || o.out_phase || o.res_mode == RES_NEAREST || o.stem_window || o.in_stride2;
+    const bool spatial = (w.taps == 9) || o.res_mode == RES_NEAREST || o.stem_window || o.in_stride2;
     p.a_scale = o.in_stride2 ? 2 : 1;
     p.Cin = w.cin;
     p.taps = w.taps;
@@ -225,27 +222,26 @@ struct ConvEngine {
     int n_img_in;
     if (spatial) {
       p.n_img = out.n;
-      p.H = o.out_phase ? o.full_h : out.h;
-      p.W = o.out_phase ? o.full_w : out.w;
+      p.H = out.h;
+      p.W = out.w;
       n_img_in = in.n;
       if (o.stem_window) {
         for (int t = 0; t < 4; ++t) { p.tap_dy[t] = t; p.tap_dx[t] = 0; p.tap_img[t] = 0; }
       } else if (w.taps == 1) {
-        if (in.phases != 1) throw std::runtime_error("conv: 1x1 needs a plain input");
         if (o.in_stride2 && (out.h != (in.h + 1) / 2 || out.w != (in.w + 1) / 2))
           throw std::runtime_error("conv: stride-2 1x1 output shape mismatch");
         p.tap_dy[0] = p.tap_dx[0] = p.tap_img[0] = 0;
       } else if (o.stride == 2) {
-        if (in.phases != 4) throw std::runtime_error("conv: stride-2 3x3 needs a phase-split input");
+        // stride-2 3x3 straight from the plain NHWC tensor: the A tensor map walks it with element stride 2, tap (r, s)
+        // starts at input pixel (2*y0 + r - 1, 2*x0 + s - 1); out-of-range pixels are TMA zero fill == padding 1
+        p.a_scale = 2;
         for (int r = 0; r < 3; ++r)
           for (int s = 0; s < 3; ++s) {
-            int t = r * 3 + s;
-            p.tap_dy[t] = (r == 0) ? -1 : 0;
-            p.tap_dx[t] = (s == 0) ? -1 : 0;
-            p.tap_img[t] = (((r == 1) ? 0 : 1) * 2 + ((s == 1) ? 0 : 1)) * in.n;
+            p.tap_dy[r * 3 + s] = r - 1;
+            p.tap_dx[r * 3 + s] = s - 1;
+            p.tap_img[r * 3 + s] = 0;
           }
       } else {
-        if (in.phases != 1) throw std::runtime_error("conv: stride-1 3x3 needs a plain input");
         for (int r = 0; r < 3; ++r)
           for (int s = 0; s < 3; ++s) {
             p.tap_dy[r * 3 + s] = r - 1;
@@ -264,10 +260,9 @@ struct ConvEngine {
       }
       p.tiles_x = (p.W + p.tw - 1) / p.tw;
       p.tiles_y = (p.H + p.th - 1) / p.th;
-      p.a_lo_img = in.phases * in.n;
+      p.a_lo_img = in.n;
     } else {
       // linear: all pixels of all images are rows of one [M][K] matrix
-      if (in.phases != 1) throw std::runtime_error("conv: 1x1 needs a plain input");
       p.n_img = 1;
       p.H = 1;
       long long M = (long long)in.n * in.h * in.w;
@@ -293,13 +288,10 @@ struct ConvEngine {
       p.res_W = o.res->w;
       p.res_ld = o.res->c;
     }
-    p.out_mode = o.out_phase ? OUT_PHASE : OUT_NHWC;
     p.out_hi = o.no_bf16_out ? nullptr : out.hi;
     p.out_lo = o.no_bf16_out ? nullptr : out.lo();
     p.out_f32 = o.out_f32;
     p.ldc = out.c;
-    p.out_H2 = out.h;
-    p.out_W2 = out.w;
     launches++;
     // algorithmic FLOPs of the reference op (the stem's 4x4x16 window holds the 7x7x3 = 147 real taps)
     const double fl = 2.0 * (double)p.n_img * p.H * p.W * (double)w.cout * (o.stem_window ? 147.0 : (double)w.taps * w.cin);
@@ -325,14 +317,13 @@ struct ConvEngine {
       ta = make_tmap_strided(in.hi, 64, (uint64_t)in.w - 3, in.h, (uint64_t)in.n * (split ? 2 : 1), 32,
                              (uint64_t)in.w * 32, (uint64_t)in.h * in.w * 32, p.tw, p.th);
     else if (spatial)
-      ta = make_tmap(in.hi, in.c, in.w, in.h, (uint64_t)in.phases * in.n * (split ? 2 : 1), p.tw, p.th,
-                     o.in_stride2 ? 2 : 1);
+      ta = make_tmap(in.hi, in.c, in.w, in.h, (uint64_t)in.n * (split ? 2 : 1), p.tw, p.th, p.a_scale);
     else
       ta = make_tmap(in.hi, in.c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);
     tb = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, split ? 2 : 1, BN, 1);
     // epilogue output path: TMA store for plain NHWC bf16 outputs whose channel count is a multiple of 64
     CUtensorMap tc = tb;
-    p.tma_store = (!o.out_phase && !o.no_bf16_out && o.out_f32 == nullptr && (w.cout_pad % 64) == 0 &&
+    p.tma_store = (!o.no_bf16_out && o.out_f32 == nullptr && (w.cout_pad % 64) == 0 &&
                    out.c == w.cout_pad && use_tma_store) ? 1 : 0;
     if (p.tma_store) {
       if (spatial) {
@@ -347,7 +338,7 @@ struct ConvEngine {
     CUtensorMap tr = tb, ti = tb;
     p.res_kb = 0;
     if (use_res_mma && o.res_mode == RES_SAME && p.tma_store && (w.cout_pad % BN) == 0 && o.res->c == w.cout_pad &&
-        o.res->split == split && o.res->phases == 1) {
+        o.res->split == split) {
       if (spatial) {
         tr = make_tmap(o.res->hi, o.res->c, o.res->w, o.res->h, (uint64_t)o.res->n * (split ? 2 : 1), p.tw, p.th);
         p.r_lo_img = o.res->n;

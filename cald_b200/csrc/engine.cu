@@ -328,7 +328,7 @@ void dbg_store_f32(cald_engine* e, const char* name, const float* d, size_t n) {
 }
 
 Act conv(cald_engine* e, const Act& in, const ConvW& w, int n, int h, int wd, const ConvOpts& o) {
-  Act out = alloc_act(e->arena, n, h, wd, w.cout_pad, e->split, 1);
+  Act out = alloc_act(e->arena, n, h, wd, w.cout_pad, e->split);
   e->conv.run(in, w, out, o, e->st);
   KLAUNCH(e);
   return out;
@@ -346,7 +346,7 @@ void run_body(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views, co
 
   // ---- transform (normalise + resize + pad) fused with the stem's space-to-depth layout
   const int Ho = Hp / 2, Wo = Wp / 2;
-  Act sin = alloc_act(ar, V, Ho + 3, Wo + 3, 16, split, 1);
+  Act sin = alloc_act(ar, V, Ho + 3, Wo + 3, 16, split);
   {
     dim3 grid((Wo + 3 + 127) / 128, Ho + 3, V);
     view_stem_input_kernel<<<grid, 128, 0, st>>>(d_views, d_cuts, Ho + 3, Wo + 3, sin.hi, sin.lo());
@@ -390,17 +390,8 @@ void run_body(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views, co
           idt = conv(e, x, b.ds, V, ho, wo, o);
         }
       }
-      Act t1;
-      if (b.stride == 2) {
-        // conv1 at full resolution through the TMA-store epilogue, then one HBM pass re-lays it out as the four
-        // stride-2 phases the 3x3 reads (cheaper than the per-thread phase-split store path)
-        Act full = conv(e, x, b.c1, V, x.h, x.w, relu_o);
-        t1 = phase_split(ar, full, st);
-        e->launches += split ? 2 : 1;
-        free_act(ar, full);
-      } else {
-        t1 = conv(e, x, b.c1, V, x.h, x.w, relu_o);
-      }
+      // conv1 at full resolution; a stride-2 conv2 reads it through an element-strided TMA map (no phase-split copy)
+      Act t1 = conv(e, x, b.c1, V, x.h, x.w, relu_o);
       ConvOpts o2;
       o2.relu = true;
       o2.stride = b.stride;
@@ -543,7 +534,7 @@ void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views
   ar.free(keys); ar.free(sel); ar.free(sel_count); ar.free(lv_boxes); ar.free(lv_scores); ar.free(lv_count);
   ar.free(keep_idx); ar.free(keep_count);
   // ---- RoIAlign on P2..P5 -> [V*cap][49*256]
-  Act roi = alloc_act(ar, 1, 1, V * cap, 49 * 256, split, 1);
+  Act roi = alloc_act(ar, 1, 1, V * cap, 49 * 256, split);
   {
     RoiFeats F;
     for (int l = 0; l < 4; ++l) {
@@ -630,7 +621,7 @@ void ret_cell_anchors(int level, float out[RET_A][4]) {
 }
 
 Act relu_act(cald_engine* e, const Act& in) {
-  Act o = alloc_act(e->arena, in.n, in.h, in.w, in.c, in.split, 1);
+  Act o = alloc_act(e->arena, in.n, in.h, in.w, in.c, in.split);
   long long n = (long long)in.plane_elems();
   relu_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(in.hi, in.lo(), o.hi, o.lo(), n);
   CALD_CUDA_CHECK(cudaGetLastError());
@@ -668,16 +659,10 @@ void forward_pass_retina(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* 
     for (int i = 1; i < 4; ++i) free_act(ar, cfeat[i]);
     ConvOpts s2;
     s2.stride = 2;
-    Act ph = phase_split(ar, pf[2], st);
-    e->launches += split ? 2 : 1;
-    pf[3] = conv(e, ph, e->ret_p6, V, (pf[2].h + 1) / 2, (pf[2].w + 1) / 2, s2);
-    free_act(ar, ph);
+    pf[3] = conv(e, pf[2], e->ret_p6, V, (pf[2].h + 1) / 2, (pf[2].w + 1) / 2, s2);
     Act r6 = relu_act(e, pf[3]);
-    Act ph6 = phase_split(ar, r6, st);
-    e->launches += split ? 2 : 1;
+    pf[4] = conv(e, r6, e->ret_p7, V, (pf[3].h + 1) / 2, (pf[3].w + 1) / 2, s2);
     free_act(ar, r6);
-    pf[4] = conv(e, ph6, e->ret_p7, V, (pf[3].h + 1) / 2, (pf[3].w + 1) / 2, s2);
-    free_act(ar, ph6);
   }
   if (e->cfg.debug) {
     const char* nm[5] = {"p3", "p4", "p5", "p6", "p7"};

@@ -385,7 +385,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         if (!p.tma_store) {
-          // direct path: fp32 head outputs, phase-split outputs, Cout not a multiple of 64
+          // direct path: fp32 head outputs, Cout not a multiple of 64
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 64; j += 8) {

@@ -1,6 +1,6 @@
 // Elementwise / data-movement kernels around the conv engine (all HBM-bound):
-// split <-> fp32 conversion, stride-2 phase split, 2x subsample, 3x3/2 max-pool,
-// stem im2col.  16-byte vector accesses, channels innermost (NHWC).
+// split <-> fp32 conversion, 2x subsample (LastLevelMaxPool), 3x3/2 max-pool.
+// 16-byte vector accesses, channels innermost (NHWC).
 #pragma once
 #include "conv_host.cuh"
 
@@ -57,9 +57,9 @@ struct Arena {
   void reset() { blks.clear(); blks.push_back({0, cap, false}); }
 };
 
-inline Act alloc_act(Arena& a, int n, int h, int w, int c, bool split, int phases = 1) {
+inline Act alloc_act(Arena& a, int n, int h, int w, int c, bool split) {
   Act t;
-  t.n = n; t.h = h; t.w = w; t.c = c; t.split = split; t.phases = phases;
+  t.n = n; t.h = h; t.w = w; t.c = c; t.split = split;
   t.hi = (bf16*)a.alloc(t.bytes());
   return t;
 }
@@ -103,25 +103,7 @@ inline void split_to_f32(const Act& t, float* out, cudaStream_t st) {
   CALD_CUDA_CHECK(cudaGetLastError());
 }
 
-// ---------------------------------------------------------------- phase split / subsample (8 channels per thread)
-// out[(py*2+px)*n + i][y][x][c] = in[i][2y+py][2x+px][c]  (zero outside)
-__global__ void phase_split_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int n, int h, int w, int c,
-                                   int h2, int w2) {
-  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int cg = c / 8;
-  long long total = 4LL * n * h2 * w2 * cg;
-  if (gid >= total) return;
-  int g = (int)(gid % cg);
-  long long r = gid / cg;
-  int x = (int)(r % w2); r /= w2;
-  int y = (int)(r % h2); r /= h2;
-  int i = (int)(r % n);
-  int ph = (int)(r / n);
-  int sy = 2 * y + (ph >> 1), sx = 2 * x + (ph & 1);
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (sy < h && sx < w) v = *reinterpret_cast<const uint4*>(in + (((long long)i * h + sy) * w + sx) * c + g * 8);
-  *reinterpret_cast<uint4*>(out + gid * 8) = v;
-}
+// ---------------------------------------------------------------- 2x subsample (8 channels per thread)
 // out[i][y][x][c] = in[i][2y][2x][c]   (1x1 stride-2 convs, LastLevelMaxPool k=1 s=2)
 __global__ void subsample2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int n, int h, int w, int c,
                                   int h2, int w2) {
@@ -137,17 +119,8 @@ __global__ void subsample2_kernel(const bf16* __restrict__ in, bf16* __restrict_
   *reinterpret_cast<uint4*>(out + gid * 8) =
       *reinterpret_cast<const uint4*>(in + (((long long)i * h + 2 * y) * w + 2 * x) * c + g * 8);
 }
-inline Act phase_split(Arena& a, const Act& in, cudaStream_t st) {
-  Act o = alloc_act(a, in.n, (in.h + 1) / 2, (in.w + 1) / 2, in.c, in.split, 4);
-  long long total = 4LL * in.n * o.h * o.w * (in.c / 8);
-  for (int pl = 0; pl < (in.split ? 2 : 1); ++pl)
-    phase_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        in.hi + pl * in.plane_elems(), o.hi + pl * o.plane_elems(), in.n, in.h, in.w, in.c, o.h, o.w);
-  CALD_CUDA_CHECK(cudaGetLastError());
-  return o;
-}
 inline Act subsample2(Arena& a, const Act& in, cudaStream_t st) {
-  Act o = alloc_act(a, in.n, (in.h + 1) / 2, (in.w + 1) / 2, in.c, in.split, 1);
+  Act o = alloc_act(a, in.n, (in.h + 1) / 2, (in.w + 1) / 2, in.c, in.split);
   long long total = (long long)in.n * o.h * o.w * (in.c / 8);
   for (int pl = 0; pl < (in.split ? 2 : 1); ++pl)
     subsample2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
@@ -201,62 +174,10 @@ __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ ihi, const bf16* __
                                                          pack_bf16x2(ll[4], ll[5]), pack_bf16x2(ll[6], ll[7]));
 }
 inline Act maxpool3x3s2(Arena& a, const Act& in, cudaStream_t st) {
-  Act o = alloc_act(a, in.n, (in.h - 1) / 2 + 1, (in.w - 1) / 2 + 1, in.c, in.split, 1);
+  Act o = alloc_act(a, in.n, (in.h - 1) / 2 + 1, (in.w - 1) / 2 + 1, in.c, in.split);
   long long total = (long long)in.n * o.h * o.w * (in.c / 8);
   maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in.hi, in.lo(), o.hi, o.lo(), in.n, in.h, in.w,
                                                                       in.c, o.h, o.w);
-  CALD_CUDA_CHECK(cudaGetLastError());
-  return o;
-}
-
-// ---------------------------------------------------------------- stem im2col (7x7 / stride 2 / pad 3, Cin = 3)
-// Input: normalised, padded image fp32 [n][H][W][3].  Output rows = output pixels, K = 192:
-// k = r*24 + s*3 + c for s*3+c < 21, zeros elsewhere (rows r = 7 are padding up to 3 x 64).
-constexpr int STEM_K = 192;
-__global__ void stem_im2col_kernel(const float* __restrict__ img, bf16* __restrict__ ohi, bf16* __restrict__ olo,
-                                   int n, int H, int W, int ho, int wo) {
-  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)n * ho * wo * 8;
-  if (gid >= total) return;
-  int r = (int)(gid % 8);
-  long long pix = gid / 8;
-  int ox = (int)(pix % wo);
-  int oy = (int)((pix / wo) % ho);
-  int i = (int)(pix / ((long long)wo * ho));
-  bf16 hh[24], ll[24];
-  int iy = 2 * oy - 3 + r;
-  bool rowok = (r < 7) && iy >= 0 && iy < H;
-#pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    int ix = 2 * ox - 3 + s;
-    bool ok = rowok && s < 7 && ix >= 0 && ix < W;
-    const float* px = img + (((long long)i * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) * 3;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float v = ok ? px[c] : 0.f;
-      split_bf16(v, hh[s * 3 + c], ll[s * 3 + c]);
-    }
-  }
-  long long off = pix * STEM_K + r * 24;
-  uint4* dh = reinterpret_cast<uint4*>(ohi + off);
-#pragma unroll
-  for (int q = 0; q < 3; ++q)
-    dh[q] = make_uint4(pack_bf16x2(hh[q * 8 + 0], hh[q * 8 + 1]), pack_bf16x2(hh[q * 8 + 2], hh[q * 8 + 3]),
-                       pack_bf16x2(hh[q * 8 + 4], hh[q * 8 + 5]), pack_bf16x2(hh[q * 8 + 6], hh[q * 8 + 7]));
-  if (olo) {
-    uint4* dl = reinterpret_cast<uint4*>(olo + off);
-#pragma unroll
-    for (int q = 0; q < 3; ++q)
-      dl[q] = make_uint4(pack_bf16x2(ll[q * 8 + 0], ll[q * 8 + 1]), pack_bf16x2(ll[q * 8 + 2], ll[q * 8 + 3]),
-                         pack_bf16x2(ll[q * 8 + 4], ll[q * 8 + 5]), pack_bf16x2(ll[q * 8 + 6], ll[q * 8 + 7]));
-  }
-}
-// Returns the im2col matrix as an Act of shape [n][ho][wo][192].
-inline Act stem_im2col(Arena& a, const float* img, int n, int H, int W, bool split, cudaStream_t st) {
-  int ho = (H + 6 - 7) / 2 + 1, wo = (W + 6 - 7) / 2 + 1;
-  Act o = alloc_act(a, n, ho, wo, STEM_K, split, 1);
-  long long total = (long long)n * ho * wo * 8;
-  stem_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, o.hi, o.lo(), n, H, W, ho, wo);
   CALD_CUDA_CHECK(cudaGetLastError());
   return o;
 }

@@ -58,7 +58,7 @@ void free_conv_weight(ConvW& w) {
 
 extern "C" int cald_op_conv2d(const float* x, int n, int h, int w, int cin, const float* weight, const float* bias,
                               int cout, int k, int stride, int relu, const float* res, int res_mode, int res_h,
-                              int res_w, int prec, int impl, int phase_out, int block_n, int kc, float* out) {
+                              int res_w, int prec, int impl, int block_n, int kc, float* out) {
   OPS_TRY
   const bool split = (prec == 0);
   cudaStream_t st = 0;
@@ -91,24 +91,13 @@ extern "C" int cald_op_conv2d(const float* x, int n, int h, int w, int cin, cons
   }
   Act in = a;
   ConvOpts o;
-  if (stride == 2) {
-    if (k == 3) in = phase_split(ar, a, st);
-    else o.in_stride2 = true;  // the conv's A tensor map skips every other pixel
-  }
+  // both stride-2 forms read the full-resolution tensor through an element-strided A tensor map
+  if (stride == 2 && k == 1) o.in_stride2 = true;
   o.relu = relu != 0;
   o.stride = (k == 3) ? stride : 1;
   o.res_mode = res_mode;
   o.res = res_mode ? &rs : nullptr;
-  Act y;
-  if (phase_out) {
-    y = alloc_act(ar, n, (ho + 1) / 2, (wo + 1) / 2, cw.cout_pad, split, 4);
-    CALD_CUDA_CHECK(cudaMemsetAsync(y.hi, 0, y.bytes(), st));
-    o.out_phase = true;
-    o.full_h = ho;
-    o.full_w = wo;
-  } else {
-    y = alloc_act(ar, n, ho, wo, cw.cout_pad, split);
-  }
+  Act y = alloc_act(ar, n, ho, wo, cw.cout_pad, split);
   eng.run(in, cw, y, o, st);
   if (getenv("CALD_OP_TIMING")) {
     // experiment hook (tools/conv_micro.py): re-run the launch a few times bracketed by CUDA events
@@ -130,13 +119,7 @@ extern "C" int cald_op_conv2d(const float* x, int n, int h, int w, int cin, cons
     for (int yy = 0; yy < ho; ++yy)
       for (int xx = 0; xx < wo; ++xx)
         for (int c = 0; c < cout; ++c) {
-          size_t src;
-          if (phase_out) {
-            int ph = (yy & 1) * 2 + (xx & 1);
-            src = ((((size_t)ph * n + i) * y.h + (yy >> 1)) * y.w + (xx >> 1)) * cw.cout_pad + c;
-          } else {
-            src = (((size_t)i * ho + yy) * wo + xx) * cw.cout_pad + c;
-          }
+          const size_t src = (((size_t)i * ho + yy) * wo + xx) * cw.cout_pad + c;
           out[(((size_t)i * ho + yy) * wo + xx) * cout + c] = hy[src];
         }
   free_conv_weight(cw);

@@ -17,7 +17,7 @@ def _p(a):
 
 
 def conv2d(x_nhwc, weight_oihw, bias=None, stride=1, relu=False, res=None, res_mode=0, prec=0, impl=0,
-           phase_out=False, block_n=0, kc=-1):
+           block_n=0, kc=-1):
     x = np.ascontiguousarray(x_nhwc, dtype=np.float32)
     w = np.ascontiguousarray(weight_oihw, dtype=np.float32)
     b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
@@ -34,7 +34,7 @@ def conv2d(x_nhwc, weight_oihw, bias=None, stride=1, relu=False, res=None, res_m
         if res_mode == 0:
             res_mode = 1
     check_ops(lib().cald_op_conv2d(_p(x), n, h, wd, cin, _p(w), _p(b), cout, k, stride, int(relu), _p(r), res_mode,
-                                   rh, rw, prec, impl, int(phase_out), block_n, kc, _p(out)))
+                                   rh, rw, prec, impl, block_n, kc, _p(out)))
     return out
 
 

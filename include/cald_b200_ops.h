@@ -22,19 +22,19 @@ const char* cald_ops_last_error(void);
  *           ops/feature_pyramid_network.py:172-204, models/detection/rpn.py:71-78 and
  *           F.linear in models/detection/faster_rcnn.py:286-307 (a 1x1 conv on 1x1 maps).
  * x:      [n][h][w][cin]  fp32 NHWC (cin multiple of 64)
- * weight: [cout][cin][k][k] fp32 (torch layout), k in {1,3}; pad = k/2; stride in {1,2}
+ * weight: [cout][cin][k][k] fp32 (torch layout), k in {1,3}; pad = k/2; stride in {1,2} (stride 2 reads the
+ *         full-resolution input through an element-strided TMA tensor map)
  * bias:   [cout] or NULL
  * res:    optional residual added before ReLU, NHWC fp32 [n][res_h][res_w][cout];
  *         res_mode 0 none, 1 same shape, 2 nearest-upsampled to the output size
  * prec:   0 = split-bf16 x3 (fp32-faithful), 1 = single-pass bf16
  * impl:   0 = tcgen05 kernel, 1 = SIMT checker kernel
  * kc:     k-blocks per accumulation chunk in split mode (-1 = engine default, 0 = never chunk)
- * phase_out: 1 = exercise the phase-split epilogue (output is re-assembled before return)
  * out:    [n][ho][wo][cout] fp32
  */
 int cald_op_conv2d(const float* x, int n, int h, int w, int cin, const float* weight, const float* bias, int cout,
                    int k, int stride, int relu, const float* res, int res_mode, int res_h, int res_w, int prec,
-                   int impl, int phase_out, int block_n, int kc, float* out);
+                   int impl, int block_n, int kc, float* out);
 
 /* Pillow-exact augmentation images on the device (cald/cald_helper.py:47-53 resize, 135-223 rotate).
  * kind 2 = img.resize((int(w*0.8), int(h*0.8)), BILINEAR); kind 3 = img.rotate(5, expand=True).resize((w, h)) (BICUBIC).

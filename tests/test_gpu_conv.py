@@ -80,12 +80,18 @@ def test_conv_block_n_variants(block_n):
         assert np.abs(got - want).max() <= tol * np.abs(want).max()
 
 
-def test_conv_phase_split_epilogue():
+def test_conv_stride2_odd_sizes():
+    """stride-2 convs read the full-resolution tensor through an element-strided TMA map: odd extents, where the last
+    tap row / column falls into the zero padding, against torch fp32"""
     from cald_b200 import ops
-    x, wt, b, _ = _case(11, 2, 19, 25, 64, 128, 1)
-    a = ops.conv2d(x, wt, b, relu=True, prec=0, impl=0, phase_out=False)
-    p = ops.conv2d(x, wt, b, relu=True, prec=0, impl=0, phase_out=True)
-    assert np.array_equal(a, p)
+    for (n, h, w, cin, cout, k) in [(2, 19, 25, 64, 128, 3), (1, 25, 42, 128, 64, 3), (1, 33, 17, 64, 256, 1),
+                                    (1, 50, 84, 256, 256, 3)]:
+        x, wt, b, _ = _case(n + h + w, n, h, w, cin, cout, k, stride=2)
+        want = _ref(x, wt, b, 2, True)
+        for impl in (0, 1):
+            got = ops.conv2d(x, wt, b, stride=2, relu=True, prec=0, impl=impl)
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= 3e-5 * np.abs(want).max() + 1e-6, (n, h, w, cin, cout, k, impl)
 
 
 def test_conv_large_k_chunked_accumulation():
