@@ -6,6 +6,6 @@ timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|^FAIL
 python bench.py --layers gpurun_out/final_layers_frcnn.tsv > gpurun_out/final_bench_frcnn.json 2> gpurun_out/final_bench_frcnn.err; tail -1 gpurun_out/final_bench_frcnn.json | cut -c1-160
 python bench.py --model retinanet --no-cpu-baseline --layers gpurun_out/final_layers_retina.tsv > gpurun_out/final_bench_retina.json 2> gpurun_out/final_bench_retina.err; tail -1 gpurun_out/final_bench_retina.json | cut -c1-160
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workspace-gb 48"
-ncu --metrics gpu__time_duration.sum --clock-control none -s 246 -c 246 --csv --log-file gpurun_out/final_launches_step.csv $CMD > gpurun_out/final_ncu1.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 262 -c 262 --csv --log-file gpurun_out/final_launches_step.csv $CMD > gpurun_out/final_ncu1.log 2>&1
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:igemm_tc -s 148 -c 148 --csv --log-file gpurun_out/final_igemm_dram_step.csv $CMD > gpurun_out/final_ncu2.log 2>&1
 ls -la gpurun_out | grep final
