@@ -6,6 +6,7 @@
 #include <map>
 #include <string>
 #include "igemm.cuh"
+#include "igemm2.cuh"
 
 namespace cald {
 
@@ -120,6 +121,12 @@ inline void choose_tile(int H, int W, int& th, int& tw) {
 
 enum ConvImpl { CONV_TC = 0, CONV_SIMT = 1 };
 
+// launches of the CTA-pair kernel in this process (lets the parity tests assert which kernel they exercised)
+inline long long& pair_launch_counter() {
+  static long long n = 0;
+  return n;
+}
+
 struct ConvEngine {
   int num_sms = 148;
   ConvImpl impl = CONV_TC;
@@ -128,6 +135,12 @@ struct ConvEngine {
   bool use_tma_store = true;  // false: always use the direct (per-thread) store epilogue
   bool use_res_mma = true;    // false: add residuals in the epilogue registers
   bool force_pow2_tiles = false;  // true: restrict spatial tiles to power-of-two shapes
+  // CTA-pair kernel (igemm2.cuh) for the split-mode BLOCK_N = 128 launches it covers; CALD_CTA2=0/1 overrides
+  bool use_cta2 = env_flag("CALD_CTA2", false);
+  static bool env_flag(const char* name, bool dflt) {
+    const char* v = getenv(name);
+    return v && *v ? (*v != '0') : dflt;
+  }
   bf16* ident[3] = {nullptr, nullptr, nullptr};  // identity B tiles for BLOCK_N = 64 / 128 / 256
   // I[j][n][k] = (n == j*64 + k): block j routes residual channels [j*64, j*64+64) to accumulator columns
   const bf16* identity(int BN) {
@@ -200,6 +213,24 @@ struct ConvEngine {
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
     igemm_tc_kernel<BN, SP, CH><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tr, ti, p);
+    if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
+    CALD_CUDA_CHECK(cudaGetLastError());
+  }
+
+  void launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& tc,
+                  const ConvParams& p, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Igemm2Cfg::SMEM_BYTES));
+      attr_set = true;
+    }
+    const int m_tiles = p.tiles_x * p.tiles_y * p.n_img;
+    const int n_pairs = p.n_blocks * ((m_tiles + 1) / 2);
+    const int clusters = n_pairs < num_sms / 2 ? n_pairs : num_sms / 2;
+    if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
+    igemm_tc2_kernel<<<2 * clusters, IG_THREADS, Igemm2Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, tc, p);
+    pair_launch_counter()++;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
     CALD_CUDA_CHECK(cudaGetLastError());
   }
@@ -353,6 +384,8 @@ struct ConvEngine {
     const int num_kb = w.taps * (w.cin / 64) + p.res_kb;
     const bool chunked = split && kc > 0 && num_kb > kc && num_kb > chunk_above_kb && BN <= 128;
     p.kc = chunked ? kc : num_kb;
+    const bool pair = use_cta2 && split && BN == 128 && !chunked && p.res_kb == 0 && p.tma_store &&
+                      (w.cout_pad % 128) == 0 && !o.stem_window;
     if (profiling) {
       // algorithmic HBM bytes: every operand element once at its stored width (activations 4 B split / 2 B bf16)
       const double eb = split ? 4.0 : 2.0;
@@ -365,12 +398,15 @@ struct ConvEngine {
       LayerRec r;
       snprintf(r.sig, sizeof(r.sig), "%dx%dx%d k%d%s cin%d cout%d BN%d%s%s%s%s", p.n_img, p.H, p.W,
                o.stem_window ? 7 : (w.taps == 9 ? 3 : 1), o.stride == 2 ? "s2" : "", o.stem_window ? 3 : w.cin, w.cout, BN,
-               chunked ? " chunk" : "", p.res_kb ? " resmma" : (o.res_mode != RES_NONE ? " res" : ""),
+               chunked ? " chunk" : (pair ? " pair" : ""), p.res_kb ? " resmma" : (o.res_mode != RES_NONE ? " res" : ""),
                p.tma_store ? " tma" : " direct", o.relu ? " relu" : "");
       r.flops = fl; r.bytes = by;
       recs.push_back(r);
     }
-    if (split) {
+    if (pair) {
+      const CUtensorMap tbh = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, 2, 64, 1);
+      launch_tc2(ta, tb, tbh, tc, p, st);
+    } else if (split) {
       if (BN == 64) { if (chunked) launch_tc<64, true, true>(ta, tb, tc, tr, ti, p, st); else launch_tc<64, true, false>(ta, tb, tc, tr, ti, p, st); }
       else if (BN == 128) { if (chunked) launch_tc<128, true, true>(ta, tb, tc, tr, ti, p, st); else launch_tc<128, true, false>(ta, tb, tc, tr, ti, p, st); }
       else launch_tc<256, true, false>(ta, tb, tc, tr, ti, p, st);

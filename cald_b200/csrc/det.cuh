@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(1024) topk_select_kernel(TopkGroups G, unsigne
   __shared__ unsigned long long buf[TOPK_MAX];
   __shared__ int hist[256];
   __shared__ unsigned long long s_prefix, s_mask;
-  __shared__ int s_k, s_cnt;
+  __shared__ int s_k, s_cnt, s_done;
   const int g = blockIdx.x;
   const int outer = g / G.inner, inner = g % G.inner;
   const unsigned long long* keys = G.keys + (long long)outer * G.stride_outer + G.inner_off[inner];
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(1024) topk_select_kernel(TopkGroups G, unsigne
   const int k = n < G.k ? n : G.k;
   const int tid = threadIdx.x;
   for (int i = tid; i < TOPK_MAX; i += blockDim.x) buf[i] = ~0ull;
-  if (tid == 0) { s_prefix = 0; s_mask = 0; s_k = k; s_cnt = 0; }
+  if (tid == 0) { s_prefix = 0; s_mask = 0; s_k = k; s_cnt = 0; s_done = 0; }
   __syncthreads();
   if (n <= TOPK_MAX) {
     for (int i = tid; i < n; i += blockDim.x) buf[i] = keys[i];
@@ -136,10 +136,18 @@ __global__ void __launch_bounds__(1024) topk_select_kernel(TopkGroups G, unsigne
         s_k = kk - cum;
         s_prefix = prefix | ((unsigned long long)b << shift);
         s_mask = mask | (255ull << shift);
+        // After the four score bytes the selected bin holds the keys that TIE with the k-th score (normally one).
+        // If everything below them plus the whole tie group fits the sort buffer, the four index-byte passes are
+        // unnecessary: collect all of them and let the sort (score, then index) pick the first k.
+        if (pass == 3 && (k - s_k) + hist[b] <= TOPK_MAX) {
+          s_prefix |= 0xffffffffull;
+          s_done = 1;
+        }
       }
       __syncthreads();
+      if (s_done) break;
     }
-    const unsigned long long T = s_prefix;  // the k-th smallest key
+    const unsigned long long T = s_prefix;  // the k-th smallest key (or the last key of its tie group)
     for (int i = tid; i < n; i += blockDim.x) {
       unsigned long long key = keys[i];
       if (key <= T) {
@@ -378,7 +386,7 @@ constexpr int ROI_THREADS = 224;
 __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiFeats F, const float4* __restrict__ props,
                                                                const int* __restrict__ prop_count, int cap,
                                                                bf16* __restrict__ ohi, bf16* __restrict__ olo) {
-  __shared__ int s_lo[2][14], s_hi[2][14], s_bad[2][14];
+  __shared__ int s_lo[2][14], s_hi[2][14], s_bad[2][14];   // element offsets of the low / high row (dim 0) or column (dim 1)
   __shared__ float s_l[2][14], s_h[2][14];
   const int v = blockIdx.y, r = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -404,11 +412,13 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiFeats F, const
     const float coord = start + (float)pb * bsz + ((float)i + 0.5f) * bsz / 2.f;
     int lo, hi; float l, h; bool bad;
     bilinear_prep(coord, dim == 0 ? H : W, lo, hi, l, h, bad);
-    s_lo[dim][k] = lo; s_hi[dim][k] = hi; s_l[dim][k] = l; s_h[dim][k] = h; s_bad[dim][k] = bad ? 1 : 0;
+    // one feature level of one view is < 2^31 elements: 32-bit offsets (row * W * C, column * C)
+    const int pitch = dim == 0 ? W * C : C;
+    s_lo[dim][k] = lo * pitch; s_hi[dim][k] = hi * pitch; s_l[dim][k] = l; s_h[dim][k] = h; s_bad[dim][k] = bad ? 1 : 0;
   }
   __syncthreads();
-  const bf16* fhi = F.hi[lv] + (long long)v * H * W * C;
-  const bf16* flo = F.lo[lv] ? F.lo[lv] + (long long)v * H * W * C : nullptr;
+  const bf16* fhi = F.hi[lv] + (long long)v * H * W * C + lane * 8;
+  const bf16* flo = F.lo[lv] ? F.lo[lv] + (long long)v * H * W * C + lane * 8 : nullptr;
   for (int bin = warp; bin < 49; bin += ROI_THREADS / 32) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (live) {
@@ -426,10 +436,9 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiFeats F, const
           const int xlo = s_lo[1][kx], xhi = s_hi[1][kx];
           const float lx = s_l[1][kx], hx = s_h[1][kx];
           const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-          const long long o1 = ((long long)ylo * W + xlo) * C + lane * 8, o2 = ((long long)ylo * W + xhi) * C + lane * 8;
-          const long long o3 = ((long long)yhi * W + xlo) * C + lane * 8, o4 = ((long long)yhi * W + xhi) * C + lane * 8;
+          const int o1 = ylo + xlo, o2 = ylo + xhi, o3 = yhi + xlo, o4 = yhi + xhi;
           float v1[8], v2[8], v3[8], v4[8];
-          auto ld = [&](long long off, float* dst) {
+          auto ld = [&](int off, float* dst) {
             const uint4 a = *reinterpret_cast<const uint4*>(fhi + off);
             const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
             if (flo) {

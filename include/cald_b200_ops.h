@@ -36,6 +36,10 @@ int cald_op_conv2d(const float* x, int n, int h, int w, int cin, const float* we
                    int k, int stride, int relu, const float* res, int res_mode, int res_h, int res_w, int prec,
                    int impl, int block_n, int kc, float* out);
 
+/* Number of launches of the CTA-pair (tcgen05 cta_group::2) conv kernel in this process so far; the parity tests use
+ * it to assert which kernel a call exercised (CALD_CTA2=0/1 selects it, see cald_b200/csrc/conv_host.cuh). */
+long long cald_ops_pair_launches(void);
+
 /* Pillow-exact augmentation images on the device (cald/cald_helper.py:47-53 resize, 135-223 rotate).
  * kind 2 = img.resize((int(w*0.8), int(h*0.8)), BILINEAR); kind 3 = img.rotate(5, expand=True).resize((w, h)) (BICUBIC).
  * img: u8 [h][w][3].  out must hold h*w*3 bytes; the produced size is returned in out_h / out_w. */

@@ -114,3 +114,40 @@ def test_conv_large_k_chunked_accumulation():
     got = ops.conv2d(x, wt, None, prec=0, impl=0)  # engine default
     assert np.abs(got - want).max() <= 1e-5 * scale
 
+
+
+PAIR_CASES = [
+    # n, h, w, cin, cout, k, stride, res_mode, res_hw      (all map to BLOCK_N = 128, TMA-store, unchunked launches)
+    (1, 25, 42, 256, 256, 3, 1, 0, None),
+    (3, 19, 25, 128, 128, 3, 1, 0, None),       # odd tile count: the peer of the last pair idles
+    (2, 19, 25, 128, 128, 3, 2, 0, None),
+    (1, 20, 26, 256, 512, 1, 2, 0, None),
+    (1, 38, 50, 512, 256, 1, 1, 2, (19, 25)),   # FPN lateral: nearest-upsampled top-down add in the epilogue
+    (1, 1, 300, 1024, 1024, 1, 1, 0, None),     # fc7-like linear mode, 3 row tiles
+    (2, 100, 168, 256, 256, 3, 1, 0, None),     # 526 tiles: every cluster walks several pairs, all ring phases
+    (1, 7, 9, 64, 128, 1, 1, 0, None),          # one tile, one k-block
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_cta_pair_kernel_matches_fp32_and_single_cta(case, monkeypatch):
+    """The cta_group::2 kernel (igemm2.cuh) against torch fp32 and against the one-CTA kernel on the same operands."""
+    import ctypes
+    from cald_b200 import ops
+    from cald_b200._lib import lib
+    L = lib()
+    L.cald_ops_pair_launches.restype = ctypes.c_longlong
+    n, h, w, cin, cout, k, stride, res_mode, res_hw = case
+    x, wt, b, res = _case(hash(case) % 1000, n, h, w, cin, cout, k, stride, True, True, res_mode, res_hw)
+    want = _ref(x, wt, b, stride, True, res, res_mode)
+    monkeypatch.setenv("CALD_CTA2", "0")
+    before = L.cald_ops_pair_launches()
+    single = ops.conv2d(x, wt, b, stride=stride, relu=True, res=res, res_mode=res_mode, prec=0, impl=0)
+    assert L.cald_ops_pair_launches() == before
+    monkeypatch.setenv("CALD_CTA2", "1")
+    got = ops.conv2d(x, wt, b, stride=stride, relu=True, res=res, res_mode=res_mode, prec=0, impl=0)
+    assert L.cald_ops_pair_launches() == before + 1, "the launch did not take the pair kernel"
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 3e-5 * scale + 1e-6
+    # same split operands, same cross-term-separated accumulation: the two kernels agree far below the fp32 tolerance
+    assert np.abs(got - single).max() <= 2e-6 * scale + 1e-7
