@@ -136,7 +136,12 @@ struct ConvEngine {
   bool use_res_mma = true;    // false: add residuals in the epilogue registers
   bool force_pow2_tiles = false;  // true: restrict spatial tiles to power-of-two shapes
   // CTA-pair kernel (igemm2.cuh) for the split-mode BLOCK_N = 128 launches it covers; CALD_CTA2=0/1 overrides
-  bool use_cta2 = env_flag("CALD_CTA2", false);
+  bool use_cta2 = env_flag("CALD_CTA2", true);
+  int cta2_min_kb = env_int("CALD_CTA2_MIN_KB", 16);
+  static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+  }
   static bool env_flag(const char* name, bool dflt) {
     const char* v = getenv(name);
     return v && *v ? (*v != '0') : dflt;
@@ -217,11 +222,12 @@ struct ConvEngine {
     CALD_CUDA_CHECK(cudaGetLastError());
   }
 
+  template <bool CH>
   void launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& tc,
                   const ConvParams& p, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc2_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Igemm2Cfg::SMEM_BYTES));
       attr_set = true;
     }
@@ -229,7 +235,7 @@ struct ConvEngine {
     const int n_pairs = p.n_blocks * ((m_tiles + 1) / 2);
     const int clusters = n_pairs < num_sms / 2 ? n_pairs : num_sms / 2;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
-    igemm_tc2_kernel<<<2 * clusters, IG_THREADS, Igemm2Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, tc, p);
+    igemm_tc2_kernel<CH><<<2 * clusters, IG_THREADS, Igemm2Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, tc, p);
     pair_launch_counter()++;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
     CALD_CUDA_CHECK(cudaGetLastError());
@@ -384,8 +390,9 @@ struct ConvEngine {
     const int num_kb = w.taps * (w.cin / 64) + p.res_kb;
     const bool chunked = split && kc > 0 && num_kb > kc && num_kb > chunk_above_kb && BN <= 128;
     p.kc = chunked ? kc : num_kb;
-    const bool pair = use_cta2 && split && BN == 128 && !chunked && p.res_kb == 0 && p.tma_store &&
-                      (w.cout_pad % 128) == 0 && !o.stem_window;
+    // the pair kernel pays a cross-CTA handshake per tile: it wins from 16 k-blocks per tile up (measured, +8..22 % on
+    // the 3x3 and K >= 1024 layers) and loses below 8 (the short-K layers are epilogue / HBM bound)
+    const bool pair = use_cta2 && split && BN == 128 && num_kb >= cta2_min_kb && p.res_kb == 0 && !o.stem_window;
     if (profiling) {
       // algorithmic HBM bytes: every operand element once at its stored width (activations 4 B split / 2 B bf16)
       const double eb = split ? 4.0 : 2.0;
@@ -396,16 +403,16 @@ struct ConvEngine {
       if (!o.no_bf16_out) by += pix * out.c * eb;
       if (o.res_mode != RES_NONE) by += (o.res_mode == RES_NEAREST ? 0.25 : 1.0) * pix * w.cout_pad * eb;
       LayerRec r;
-      snprintf(r.sig, sizeof(r.sig), "%dx%dx%d k%d%s cin%d cout%d BN%d%s%s%s%s", p.n_img, p.H, p.W,
+      snprintf(r.sig, sizeof(r.sig), "%dx%dx%d k%d%s cin%d cout%d BN%d%s%s%s%s%s", p.n_img, p.H, p.W,
                o.stem_window ? 7 : (w.taps == 9 ? 3 : 1), o.stride == 2 ? "s2" : "", o.stem_window ? 3 : w.cin, w.cout, BN,
-               chunked ? " chunk" : (pair ? " pair" : ""), p.res_kb ? " resmma" : (o.res_mode != RES_NONE ? " res" : ""),
+               chunked ? " chunk" : "", pair ? " pair" : "", p.res_kb ? " resmma" : (o.res_mode != RES_NONE ? " res" : ""),
                p.tma_store ? " tma" : " direct", o.relu ? " relu" : "");
       r.flops = fl; r.bytes = by;
       recs.push_back(r);
     }
     if (pair) {
       const CUtensorMap tbh = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, 2, 64, 1);
-      launch_tc2(ta, tb, tbh, tc, p, st);
+      if (chunked) launch_tc2<true>(ta, tb, tbh, tc, p, st); else launch_tc2<false>(ta, tb, tbh, tc, p, st);
     } else if (split) {
       if (BN == 64) { if (chunked) launch_tc<64, true, true>(ta, tb, tc, tr, ti, p, st); else launch_tc<64, true, false>(ta, tb, tc, tr, ti, p, st); }
       else if (BN == 128) { if (chunked) launch_tc<128, true, true>(ta, tb, tc, tr, ti, p, st); else launch_tc<128, true, false>(ta, tb, tc, tr, ti, p, st); }

@@ -98,8 +98,10 @@ __device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-// Launch contract (conv_host.cuh): split mode, Cout a multiple of 128, TMA-store epilogue, no residual k-blocks, not
-// chunked; grid = 2 x clusters, every cluster strides over the (n block, pair of m tiles) list.
+// Launch contract (conv_host.cuh): split mode, BLOCK_N = 128, no residual k-blocks;
+// grid = 2 x clusters, every cluster strides over the (n block, pair of m tiles) list.  CHUNKED as in igemm.cuh: the
+// accumulator restarts every p.kc k-blocks and the epilogue warps of both CTAs sum the partial tiles in registers.
+template <bool CHUNKED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IG_THREADS, 1)
 igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmC,
@@ -216,11 +218,16 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const int kc = CHUNKED ? p.kc : num_kb;
       for (int pt = cid; pt < n_pairs; pt += n_clusters) {
-        mbar_wait_cluster(tempty_bar + 8 * acc, acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d = tmem_base + acc * Cfg::ACC_STRIDE;
+        uint32_t d = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
+          const int kin = kb % kc;  // position inside the accumulation chunk
+          if (kin == 0) {
+            mbar_wait_cluster(tempty_bar + 8 * acc, acc_phase ^ 1);
+            tcgen05_fence_after();
+            d = tmem_base + acc * Cfg::ACC_STRIDE;
+          }
           mbar_wait(full_bar + 8 * stage, phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -231,14 +238,16 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
             const uint64_t ko = (uint64_t)((k * IG_UMMA_K * 2) >> 4);
-            tcgen05_mma_bf16_pair(d, a_hi + ko, bx + ko, idesc_cat, (kb | k) != 0);
+            tcgen05_mma_bf16_pair(d, a_hi + ko, bx + ko, idesc_cat, (kin | k) != 0);
             tcgen05_mma_bf16_pair(d + BLOCK_N, a_lo + ko, by + ko, idesc_half, 1);
           }
           tcgen05_commit_pair(empty_bar + 8 * stage);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (kin == kc - 1 || kb == num_kb - 1) {
+            tcgen05_commit_pair(tfull_bar + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
         }
-        tcgen05_commit_pair(tfull_bar + 8 * acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -251,44 +260,90 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     bool store_pending = false;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int num_chunks = CHUNKED ? (num_kb + p.kc - 1) / p.kc : 1;
     for (int pt = cid; pt < n_pairs; pt += n_clusters) {
       int nb, img, y0, x0;
       const bool live = pair_coords(pt, nb, img, y0, x0);
       const int y = y0 + row / p.tw, x = x0 + row % p.tw;
       const bool valid = (row < p.th * p.tw) && (y < p.H) && (x < p.W);
-      long long rrow = 0;
+      long long orow = 0, rrow = 0;
       const bool res_on = (p.res_mode != RES_NONE) && valid && live;
       uint4 rh[8], rl[8];
+      if (valid) orow = out_row_offset(p, img, y, x);
       if (res_on) {
         rrow = res_row_offset(p, img, y, x);
-        load_res64(p, rrow, nb * BLOCK_N, rh, rl);
+        if (p.tma_store) load_res64(p, rrow, nb * BLOCK_N, rh, rl);
       }
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      tcgen05_fence_after();
+      float accv[CHUNKED ? BLOCK_N : 1];
+      if (CHUNKED) {
+        for (int ch = 0; ch < num_chunks; ++ch) {
+          mbar_wait(tfull_bar + 8 * acc, acc_phase);
+          tcgen05_fence_after();
+          const uint32_t tc = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+          for (int cc = 0; cc < (CHUNKED ? BLOCK_N : 0); cc += 32) {
+            uint32_t r[32];
+            tmem_ld32(tc + cc, r);
+            if (ch == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) accv[cc + i] = __uint_as_float(r[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) accv[cc + i] += __uint_as_float(r[i]);
+            }
+            tmem_ld32(tc + BLOCK_N + cc, r);  // the chunk's cross-term columns
+#pragma unroll
+            for (int i = 0; i < 32; ++i) accv[cc + i] += __uint_as_float(r[i]);
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * acc);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      } else {
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        tcgen05_fence_after();
+      }
       const uint32_t t0 = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
       for (int g = 0; g < BLOCK_N / 64; ++g) {
         const int c0 = nb * BLOCK_N + g * 64;
         float v[64];
-        uint32_t r[32];
-        tmem_ld32(t0 + g * 64, r);
+        if (CHUNKED) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        tmem_ld32(t0 + g * 64 + 32, r);
+          for (int i = 0; i < 64; ++i) v[i] = accv[CHUNKED ? g * 64 + i : 0];
+        } else {
+          uint32_t r[32];
+          tmem_ld32(t0 + g * 64, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
-        tmem_ld32(t0 + BLOCK_N + g * 64, r);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          tmem_ld32(t0 + g * 64 + 32, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
-        tmem_ld32(t0 + BLOCK_N + g * 64 + 32, r);
+          for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
+          tmem_ld32(t0 + BLOCK_N + g * 64, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[32 + i] += __uint_as_float(r[i]);
-        if (g == BLOCK_N / 64 - 1) {  // accumulator drained: hand the stage back to the leader's MMA thread
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * acc);
+          for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
+          tmem_ld32(t0 + BLOCK_N + g * 64 + 32, r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[32 + i] += __uint_as_float(r[i]);
+          if (g == BLOCK_N / 64 - 1) {  // accumulator drained: hand the stage back to the leader's MMA thread
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * acc);
+          }
         }
         if (!live) continue;  // uniform across the CTA
+        if (!p.tma_store) {
+          // direct path: fp32 head outputs, Cout not a multiple of 64
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 8) {
+              if (c0 + j < p.Cout) epilogue_store8(p, orow, rrow, c0 + j, &v[j]);
+            }
+          }
+          continue;
+        }
+        if (c0 >= p.Cout) continue;  // uniform across the CTA
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 64; j += 4) {
@@ -309,7 +364,7 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[q * 8 + 2 * i + 1] += b;
             }
           }
-          if (g + 1 < BLOCK_N / 64) load_res64(p, rrow, c0 + 64, rh, rl);
+          if (g + 1 < BLOCK_N / 64 && c0 + 64 < p.Cout) load_res64(p, rrow, c0 + 64, rh, rl);
         }
         if (p.relu) {
 #pragma unroll
@@ -341,7 +396,9 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         store_pending = true;
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (!CHUNKED) {
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
     }
     if (leader && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }

@@ -126,6 +126,10 @@ PAIR_CASES = [
     (1, 1, 300, 1024, 1024, 1, 1, 0, None),     # fc7-like linear mode, 3 row tiles
     (2, 100, 168, 256, 256, 3, 1, 0, None),     # 526 tiles: every cluster walks several pairs, all ring phases
     (1, 7, 9, 64, 128, 1, 1, 0, None),          # one tile, one k-block
+    (2, 25, 42, 512, 512, 3, 1, 0, None),       # 72 k-blocks: chunked accumulation across the pair
+    (1, 1, 200, 12544, 128, 1, 1, 0, None),     # fc6-like, 196 k-blocks, chunked
+    (1, 25, 42, 256, 819, 3, 1, 0, None),       # RetinaNet cls_logits: 7 n-blocks, the last one ragged, direct fp32 stores
+    (1, 10, 100, 1024, 112, 1, 1, 0, None),     # one ragged n-block (predictor-like)
 ]
 
 
@@ -145,6 +149,7 @@ def test_conv_cta_pair_kernel_matches_fp32_and_single_cta(case, monkeypatch):
     single = ops.conv2d(x, wt, b, stride=stride, relu=True, res=res, res_mode=res_mode, prec=0, impl=0)
     assert L.cald_ops_pair_launches() == before
     monkeypatch.setenv("CALD_CTA2", "1")
+    monkeypatch.setenv("CALD_CTA2_MIN_KB", "1")   # the engine default only pairs launches of >= 16 k-blocks
     got = ops.conv2d(x, wt, b, stride=stride, relu=True, res=res, res_mode=res_mode, prec=0, impl=0)
     assert L.cald_ops_pair_launches() == before + 1, "the launch did not take the pair kernel"
     scale = np.abs(want).max()
