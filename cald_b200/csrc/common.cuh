@@ -101,6 +101,9 @@ struct ConvParams {
   int res_kb;          // residual-as-MMA: extra identity k-blocks per tile (BLOCK_N / 64), else 0
   int r_lo_img;        // image-index offset of the lo plane in the residual tensor map
   int a_scale;         // 1, or 2 for a stride-2 1x1 conv: the A tensor map walks the input with element stride 2
+  int res_conv;        // 1: the extra k-blocks are a second 1x1 contraction (aux input x aux weights, e.g. the ResNet
+                       //    downsample shortcut) accumulated into the same tile, not an identity-routed residual
+  int r_scale;         // element stride of the aux input's tensor map (2 for a stride-2 shortcut), else 1
 };
 
 // ATen nearest-neighbour source index (UpSampleKernel: nearest_idx), float scale.

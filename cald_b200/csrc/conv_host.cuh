@@ -42,6 +42,13 @@ struct ConvOpts {
   // 1x1 conv with stride 2 (ResNet downsample shortcut, tv:models/resnet.py): `in` is the full-resolution tensor and
   // the TMA tensor map itself skips every other pixel (element strides 2, 2), so no subsampled copy is materialised
   bool in_stride2 = false;
+  // second 1x1 contraction accumulated into the same output tile: out = act(conv(in, w) + conv1x1(aux_in, aux_w) + bias),
+  // aux_in read with element stride aux_stride (the projection shortcut of tv:models/resnet.py Bottleneck.downsample).
+  // bias_sum = device vector of the two folded biases added together.
+  const Act* aux_in = nullptr;
+  const ConvW* aux_w = nullptr;
+  int aux_stride = 1;
+  const float* bias_sum = nullptr;
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -251,7 +258,16 @@ struct ConvEngine {
     if (in.split != split) throw std::runtime_error("conv: activation precision mode mismatch");
     ConvParams p;
     memset(&p, 0, sizeof(p));
-    const bool spatial = (w.taps == 9) || o.res_mode == RES_NEAREST || o.stem_window || o.in_stride2;
+    const bool dual = o.aux_in != nullptr;
+    if (dual) {
+      if (!o.aux_w || !o.bias_sum || o.aux_w->taps != 1 || (o.aux_w->cin % 64) != 0 || o.aux_in->c != o.aux_w->cin ||
+          o.aux_w->cout_pad != w.cout_pad || o.res_mode != RES_NONE || o.aux_in->split != split || o.aux_in->n != in.n ||
+          (o.aux_in->h + o.aux_stride - 1) / o.aux_stride != out.h || (o.aux_in->w + o.aux_stride - 1) / o.aux_stride != out.w ||
+          impl != CONV_TC)
+        throw std::runtime_error("conv: bad operands for the fused shortcut contraction");
+    }
+    const bool spatial = (w.taps == 9) || o.res_mode == RES_NEAREST || o.stem_window || o.in_stride2 ||
+                         (dual && o.aux_stride != 1);
     p.a_scale = o.in_stride2 ? 2 : 1;
     p.Cin = w.cin;
     p.taps = w.taps;
@@ -315,7 +331,8 @@ struct ConvEngine {
     p.a_bytes = p.th * p.tw * 128;
     p.n_blocks = (w.cout_pad + BN - 1) / BN;
     p.num_tiles = p.n_blocks * p.tiles_x * p.tiles_y * p.n_img;
-    p.bias = w.bias;
+    p.bias = dual ? o.bias_sum : w.bias;
+    p.r_scale = 1;
     p.relu = o.relu ? 1 : 0;
     p.res_mode = o.res_mode;
     if (o.res_mode != RES_NONE) {
@@ -331,7 +348,8 @@ struct ConvEngine {
     p.ldc = out.c;
     launches++;
     // algorithmic FLOPs of the reference op (the stem's 4x4x16 window holds the 7x7x3 = 147 real taps)
-    const double fl = 2.0 * (double)p.n_img * p.H * p.W * (double)w.cout * (o.stem_window ? 147.0 : (double)w.taps * w.cin);
+    const double fl = 2.0 * (double)p.n_img * p.H * p.W * (double)w.cout *
+                      ((o.stem_window ? 147.0 : (double)w.taps * w.cin) + (dual ? (double)o.aux_w->cin : 0.0));
     flops += fl;
     if (profiling && impl == CONV_TC) { prof_flops += fl; prof_launches++; }
 
@@ -387,6 +405,20 @@ struct ConvEngine {
       p.res_kb = BN / 64;
       p.res_mode = RES_NONE;  // the epilogue no longer sees a residual
     }
+    if (dual) {
+      const Act& ax = *o.aux_in;
+      if (spatial) {
+        tr = make_tmap(ax.hi, ax.c, ax.w, ax.h, (uint64_t)ax.n * (split ? 2 : 1), p.tw, p.th, o.aux_stride);
+        p.r_lo_img = ax.n;
+      } else {
+        tr = make_tmap(ax.hi, ax.c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);
+        p.r_lo_img = 1;
+      }
+      ti = make_tmap(o.aux_w->w, (uint64_t)o.aux_w->cin, o.aux_w->cout_pad, 1, split ? 2 : 1, BN, 1);
+      p.res_kb = o.aux_w->cin / 64;
+      p.res_conv = 1;
+      p.r_scale = o.aux_stride;
+    }
     const int num_kb = w.taps * (w.cin / 64) + p.res_kb;
     const bool chunked = split && kc > 0 && num_kb > kc && num_kb > chunk_above_kb && BN <= 128;
     p.kc = chunked ? kc : num_kb;
@@ -402,10 +434,12 @@ struct ConvEngine {
       if (o.out_f32) by += pix * out.c * 4.0;
       if (!o.no_bf16_out) by += pix * out.c * eb;
       if (o.res_mode != RES_NONE) by += (o.res_mode == RES_NEAREST ? 0.25 : 1.0) * pix * w.cout_pad * eb;
+      if (dual) by += pix * o.aux_w->cin * eb + (double)w.cout_pad * o.aux_w->cin * eb;
       LayerRec r;
       snprintf(r.sig, sizeof(r.sig), "%dx%dx%d k%d%s cin%d cout%d BN%d%s%s%s%s%s", p.n_img, p.H, p.W,
                o.stem_window ? 7 : (w.taps == 9 ? 3 : 1), o.stride == 2 ? "s2" : "", o.stem_window ? 3 : w.cin, w.cout, BN,
-               chunked ? " chunk" : "", pair ? " pair" : "", p.res_kb ? " resmma" : (o.res_mode != RES_NONE ? " res" : ""),
+               chunked ? " chunk" : "", pair ? " pair" : "",
+               dual ? (o.aux_stride == 2 ? " +ds2" : " +ds") : (p.res_kb ? " resmma" : (o.res_mode != RES_NONE ? " res" : "")),
                p.tma_store ? " tma" : " direct", o.relu ? " relu" : "");
       r.flops = fl; r.bytes = by;
       recs.push_back(r);

@@ -31,6 +31,7 @@ struct Block {
   ConvW c1, c2, c3, ds;
   bool has_ds = false;
   int stride = 1;
+  float* bias_c3ds = nullptr;  // device [cout_pad]: folded bn3 bias + folded downsample-bn bias (fused shortcut launch)
 };
 
 // fixed-capacity detections of a set of views (device)
@@ -114,7 +115,11 @@ struct cald_engine {
     fw(ret_p6); fw(ret_p7); fw(ret_cls_out); fw(ret_reg_out);
     for (int i = 0; i < 4; ++i) { fw(ret_cls_tower[i]); fw(ret_reg_tower[i]); }
     for (int i = 0; i < 4; ++i) { fw(fpn_inner[i]); fw(fpn_layer[i]); }
-    for (auto& l : layers) for (auto& b : l) { fw(b.c1); fw(b.c2); fw(b.c3); if (b.has_ds) fw(b.ds); }
+    for (auto& l : layers) for (auto& b : l) {
+      fw(b.c1); fw(b.c2); fw(b.c3);
+      if (b.has_ds) fw(b.ds);
+      if (b.bias_c3ds) cudaFree(b.bias_c3ds);
+    }
     layers.clear();
     weights_ready = false;
   }
@@ -223,6 +228,14 @@ void finalize_weights(cald_engine* e) {
       if (bi == 0) {
         blk.has_ds = true;
         blk.ds = fold_conv_bn(e, pre + ".downsample.0", pre + ".downsample.1");
+        // out = relu(bn3(conv3(y)) + bn_d(conv_d(x))): with both BNs folded the two biases simply add
+        std::vector<float> b3(blk.c3.cout_pad), bd(blk.ds.cout_pad);
+        if (b3.size() != bd.size()) throw std::runtime_error("downsample / conv3 channel mismatch");
+        CALD_CUDA_CHECK(cudaMemcpy(b3.data(), blk.c3.bias, b3.size() * 4, cudaMemcpyDeviceToHost));
+        CALD_CUDA_CHECK(cudaMemcpy(bd.data(), blk.ds.bias, bd.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < b3.size(); ++i) b3[i] += bd[i];
+        CALD_CUDA_CHECK(cudaMalloc((void**)&blk.bias_c3ds, b3.size() * 4));
+        CALD_CUDA_CHECK(cudaMemcpy(blk.bias_c3ds, b3.data(), b3.size() * 4, cudaMemcpyHostToDevice));
       }
       e->layers[li].push_back(blk);
     }
@@ -380,8 +393,13 @@ void run_body(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views, co
     for (size_t bi = 0; bi < e->layers[li].size(); ++bi) {
       const Block& b = e->layers[li][bi];
       const int ho = b.stride == 2 ? (x.h + 1) / 2 : x.h, wo = b.stride == 2 ? (x.w + 1) / 2 : x.w;
+      // The projection shortcut of a stage's first block is accumulated INSIDE the conv3 launch (second contraction
+      // over x, conv_host.cuh ConvOpts::aux_*): its 4x-wide output is never written or re-read.  layer4's two
+      // contractions (K = 512 + 1024) are tensor-bound and stay separate launches on the CTA-pair kernel.
+      static const bool fuse_env = ConvEngine::env_flag("CALD_FUSE_DS", true);
+      const bool fuse_ds = b.has_ds && fuse_env && e->conv.impl == CONV_TC && li < 3;
       Act idt;
-      if (b.has_ds) {
+      if (b.has_ds && !fuse_ds) {
         ConvOpts o;
         if (b.stride == 2) {
           o.in_stride2 = true;  // the A tensor map skips every other pixel: no subsampled copy
@@ -399,11 +417,18 @@ void run_body(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views, co
       free_act(ar, t1);
       ConvOpts o3;
       o3.relu = true;
-      o3.res_mode = RES_SAME;
-      o3.res = b.has_ds ? &idt : &x;
+      if (fuse_ds) {
+        o3.aux_in = &x;
+        o3.aux_w = &b.ds;
+        o3.aux_stride = b.stride;
+        o3.bias_sum = b.bias_c3ds;
+      } else {
+        o3.res_mode = RES_SAME;
+        o3.res = b.has_ds ? &idt : &x;
+      }
       Act y = conv(e, t2, b.c3, V, ho, wo, o3);
       free_act(ar, t2);
-      if (b.has_ds) free_act(ar, idt);
+      if (b.has_ds && !fuse_ds) free_act(ar, idt);
       const bool keep_x = (bi == 0 && li > 0);  // x is the previous stage's output (C2..C4), needed by the FPN
       if (!keep_x) free_act(ar, x);
       x = y;

@@ -197,7 +197,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int conv_kb = p.taps * k_chunks;
   // Residual add on the tensor core: the shortcut tensor is streamed through the same TMA pipeline as extra
   // k-blocks and multiplied by a 64-wide identity (R_hi*I + R_lo*I is exact), so the epilogue never waits on
-  // strided residual loads.  res_kb = BLOCK_N / 64 for such layers, else 0.
+  // strided residual loads.  res_kb = BLOCK_N / 64 for such layers, else 0.  With p.res_conv the extra k-blocks are a
+  // second 1x1 contraction instead (the projection shortcut of a stage's first bottleneck, aux_cin / 64 of them):
+  // relu(W3*y + Wd*x + b3 + bd) is ONE accumulation, so the 4x-wide shortcut tensor is never written or re-read.
   const int num_kb = conv_kb + p.res_kb;
 
   if (warp == 0) {
@@ -212,6 +214,20 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          if (kb >= conv_kb && p.res_conv) {
+            // second contraction (downsample shortcut): aux activations through tmR, aux weights through tmI
+            const int j = kb - conv_kb;
+            const int rx = x0 * p.r_scale, ry = y0 * p.r_scale, bn = nb * BLOCK_N;
+            mbar_expect_tx(fb, (SPLIT ? 2 : 1) * (p.a_bytes + Cfg::B_BYTES));
+            tma_load_4d(sa, &tmR, fb, j * 64, rx, ry, img);
+            tma_load_4d(sa + Cfg::OFF_B_HI, &tmI, fb, j * 64, bn, 0, 0);
+            if (SPLIT) {
+              tma_load_4d(sa + Cfg::OFF_A_LO, &tmR, fb, j * 64, rx, ry, img + p.r_lo_img);
+              tma_load_4d(sa + Cfg::OFF_B_LO, &tmI, fb, j * 64, bn, 0, 1);
+            }
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (kb >= conv_kb) {
             const int j = kb - conv_kb;
             const int rc = nb * BLOCK_N + j * 64;
@@ -269,7 +285,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
             const uint64_t ko = (uint64_t)((k * IG_UMMA_K * 2) >> 4);  // advance start address inside the swizzle row
-            if (kb >= conv_kb) {
+            if (kb >= conv_kb && !p.res_conv) {
               // residual k-block: D += R_lo * I + R_hi * I
               if (SPLIT) tcgen05_mma_bf16(d, a_lo + ko, b_hi + ko, idesc, (kin | k) != 0);
               tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, SPLIT ? 1u : (uint32_t)((kin | k) != 0));

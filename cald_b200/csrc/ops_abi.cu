@@ -128,3 +128,52 @@ extern "C" int cald_op_conv2d(const float* x, int n, int h, int w, int cin, cons
   ar.destroy();
   OPS_CATCH
 }
+
+extern "C" int cald_op_conv2d_dual(const float* x, int n, int h, int w, int cin, const float* weight, const float* bias,
+                                   int cout, int k, const float* x2, int h2, int w2, int cin2, const float* weight2,
+                                   const float* bias2, int stride2, int relu, float* out) {
+  OPS_TRY
+  cudaStream_t st = 0;
+  Arena ar;
+  const size_t in_e = (size_t)n * h * w * cin, in2_e = (size_t)n * h2 * w2 * cin2;
+  const int cout_pad = (cout + 7) / 8 * 8;
+  const size_t out_e = (size_t)n * h * w * cout_pad;
+  ar.init((in_e + in2_e + out_e) * 16 + ((size_t)64 << 20));
+  ConvEngine eng;
+  int dev;
+  CALD_CUDA_CHECK(cudaGetDevice(&dev));
+  CALD_CUDA_CHECK(cudaDeviceGetAttribute(&eng.num_sms, cudaDevAttrMultiProcessorCount, dev));
+  ConvW cw = upload_conv_weight(weight, bias, cout, cin, k, true, nullptr);
+  ConvW cw2 = upload_conv_weight(weight2, bias2, cout, cin2, 1, true, nullptr);
+  std::vector<float> bs(cout_pad, 0.f);
+  for (int o = 0; o < cout; ++o) bs[o] = (bias ? bias[o] : 0.f) + (bias2 ? bias2[o] : 0.f);
+  float* dbs = (float*)ar.alloc(bs.size() * 4);
+  CALD_CUDA_CHECK(cudaMemcpy(dbs, bs.data(), bs.size() * 4, cudaMemcpyHostToDevice));
+  float* dx = (float*)ar.alloc(in_e * 4);
+  CALD_CUDA_CHECK(cudaMemcpy(dx, x, in_e * 4, cudaMemcpyHostToDevice));
+  Act a = alloc_act(ar, n, h, w, cin, true);
+  f32_to_split(dx, a, st);
+  float* dx2 = (float*)ar.alloc(in2_e * 4);
+  CALD_CUDA_CHECK(cudaMemcpy(dx2, x2, in2_e * 4, cudaMemcpyHostToDevice));
+  Act a2 = alloc_act(ar, n, h2, w2, cin2, true);
+  f32_to_split(dx2, a2, st);
+  ConvOpts o;
+  o.relu = relu != 0;
+  o.aux_in = &a2;
+  o.aux_w = &cw2;
+  o.aux_stride = stride2;
+  o.bias_sum = dbs;
+  Act y = alloc_act(ar, n, h, w, cw.cout_pad, true);
+  eng.run(a, cw, y, o, st);
+  std::vector<float> hy(y.plane_elems());
+  float* dy = (float*)ar.alloc(hy.size() * 4);
+  split_to_f32(y, dy, st);
+  CALD_CUDA_CHECK(cudaMemcpyAsync(hy.data(), dy, hy.size() * 4, cudaMemcpyDeviceToHost, st));
+  CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (size_t pix = 0; pix < (size_t)n * h * w; ++pix)
+    for (int c = 0; c < cout; ++c) out[pix * cout + c] = hy[pix * cw.cout_pad + c];
+  free_conv_weight(cw);
+  free_conv_weight(cw2);
+  ar.destroy();
+  OPS_CATCH
+}

@@ -38,6 +38,23 @@ def conv2d(x_nhwc, weight_oihw, bias=None, stride=1, relu=False, res=None, res_m
     return out
 
 
+def conv2d_dual(x_nhwc, weight_oihw, bias, x2_nhwc, weight2_oi11, bias2, stride2=1, relu=True):
+    """act(conv(x, w) + b + conv1x1(x2[::s, ::s], w2) + b2) in one launch (fused projection shortcut)."""
+    x = np.ascontiguousarray(x_nhwc, dtype=np.float32)
+    w = np.ascontiguousarray(weight_oihw, dtype=np.float32)
+    x2 = np.ascontiguousarray(x2_nhwc, dtype=np.float32)
+    w2 = np.ascontiguousarray(weight2_oi11, dtype=np.float32)
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    b2 = None if bias2 is None else np.ascontiguousarray(bias2, dtype=np.float32)
+    n, h, wd, cin = x.shape
+    cout, _, k, _ = w.shape
+    _, h2, w2d, cin2 = x2.shape
+    out = np.empty((n, h, wd, cout), dtype=np.float32)
+    check_ops(lib().cald_op_conv2d_dual(_p(x), n, h, wd, cin, _p(w), _p(b), cout, k, _p(x2), h2, w2d, cin2, _p(w2),
+                                        _p(b2), stride2, int(relu), _p(out)))
+    return out
+
+
 def aug_image(kind, img_u8):
     """Device Pillow-exact augmentation image: kind 2 = smaller_resize (0.8, BILINEAR), 3 = rotation (5 deg)."""
     img = np.ascontiguousarray(img_u8, dtype=np.uint8)

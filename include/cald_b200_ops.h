@@ -36,6 +36,17 @@ int cald_op_conv2d(const float* x, int n, int h, int w, int cin, const float* we
                    int k, int stride, int relu, const float* res, int res_mode, int res_h, int res_w, int prec,
                    int impl, int block_n, int kc, float* out);
 
+/* conv2d with a second 1x1 contraction accumulated into the same output tile (one launch, one accumulator):
+ *   out = act(conv_k(x, weight) + bias + conv_1x1(x2[::stride2, ::stride2], weight2) + bias2)
+ * Replaces: the tail of torchvision resnet.py Bottleneck.forward for a stage's first block,
+ *           out = relu(bn3(conv3(out)) + downsample(x)), with both FrozenBN layers folded (tv:models/resnet.py:143-163).
+ * x:  [n][h][w][cin] fp32 NHWC, weight [cout][cin][k][k] (k in {1,3}, stride 1); x2: [n][h2][w2][cin2] with
+ * ceil(h2 / stride2) == h and ceil(w2 / stride2) == w, weight2 [cout][cin2][1][1]; split-bf16 x3 arithmetic.
+ * out: [n][h][w][cout] fp32. */
+int cald_op_conv2d_dual(const float* x, int n, int h, int w, int cin, const float* weight, const float* bias, int cout,
+                        int k, const float* x2, int h2, int w2, int cin2, const float* weight2, const float* bias2,
+                        int stride2, int relu, float* out);
+
 /* Number of launches of the CTA-pair (tcgen05 cta_group::2) conv kernel in this process so far; the parity tests use
  * it to assert which kernel a call exercised (CALD_CTA2=0/1 selects it, see cald_b200/csrc/conv_host.cuh). */
 long long cald_ops_pair_launches(void);

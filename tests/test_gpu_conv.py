@@ -156,3 +156,32 @@ def test_conv_cta_pair_kernel_matches_fp32_and_single_cta(case, monkeypatch):
     assert np.abs(got - want).max() <= 3e-5 * scale + 1e-6
     # same split operands, same cross-term-separated accumulation: the two kernels agree far below the fp32 tolerance
     assert np.abs(got - single).max() <= 2e-6 * scale + 1e-7
+
+
+DUAL_CASES = [
+    # n, h, w, cin (conv3 input), cout, h2, w2, cin2 (block input), stride2
+    (2, 19, 25, 64, 256, 19, 25, 64, 1),        # layer1.0: linear mode, 1 + 1 k-blocks
+    (1, 19, 25, 128, 512, 38, 50, 256, 2),      # layer2.0: stride-2 shortcut read through an element-strided map
+    (1, 13, 21, 256, 1024, 25, 42, 512, 2),     # layer3.0, odd source extents
+    (1, 20, 26, 128, 512, 39, 51, 256, 2),
+]
+
+
+@pytest.mark.parametrize("case", DUAL_CASES)
+def test_conv_fused_projection_shortcut(case):
+    """relu(conv3(y) + b3 + downsample(x) + bd) as ONE launch against the two torch fp32 convs added."""
+    from cald_b200 import ops
+    n, h, w, cin, cout, h2, w2, cin2, s2 = case
+    rs = np.random.RandomState(sum(case))
+    y = rs.standard_normal((n, h, w, cin)).astype(np.float32)
+    x = rs.standard_normal((n, h2, w2, cin2)).astype(np.float32)
+    w3 = (rs.standard_normal((cout, cin, 1, 1)) * np.sqrt(2.0 / cin)).astype(np.float32)
+    wd = (rs.standard_normal((cout, cin2, 1, 1)) * np.sqrt(2.0 / cin2)).astype(np.float32)
+    b3 = rs.standard_normal(cout).astype(np.float32)
+    bd = rs.standard_normal(cout).astype(np.float32)
+    a = F.conv2d(torch.from_numpy(y).permute(0, 3, 1, 2), torch.from_numpy(w3), torch.from_numpy(b3))
+    b = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(wd), torch.from_numpy(bd), stride=s2)
+    want = F.relu(a + b).permute(0, 2, 3, 1).contiguous().numpy()
+    got = ops.conv2d_dual(y, w3, b3, x, wd, bd, stride2=s2, relu=True)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 3e-5 * np.abs(want).max() + 1e-6
