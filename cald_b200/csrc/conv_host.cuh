@@ -145,6 +145,7 @@ struct ConvEngine {
   // CTA-pair kernel (igemm2.cuh) for the split-mode BLOCK_N = 128 launches it covers; CALD_CTA2=0/1 overrides
   bool use_cta2 = env_flag("CALD_CTA2", true);
   int cta2_min_kb = env_int("CALD_CTA2_MIN_KB", 16);
+  int cta2_min_kb64 = env_int("CALD_CTA2_MIN_KB64", 4);
   static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -229,20 +230,21 @@ struct ConvEngine {
     CALD_CUDA_CHECK(cudaGetLastError());
   }
 
-  template <bool CH>
+  template <int BN, bool CH>
   void launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& tc,
                   const ConvParams& p, cudaStream_t st) {
+    using Cfg = Igemm2Cfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc2_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Igemm2Cfg::SMEM_BYTES));
+      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc2_kernel<BN, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
       attr_set = true;
     }
     const int m_tiles = p.tiles_x * p.tiles_y * p.n_img;
     const int n_pairs = p.n_blocks * ((m_tiles + 1) / 2);
     const int clusters = n_pairs < num_sms / 2 ? n_pairs : num_sms / 2;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
-    igemm_tc2_kernel<CH><<<2 * clusters, IG_THREADS, Igemm2Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, tc, p);
+    igemm_tc2_kernel<BN, CH><<<2 * clusters, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, tc, p);
     pair_launch_counter()++;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
     CALD_CUDA_CHECK(cudaGetLastError());
@@ -422,9 +424,13 @@ struct ConvEngine {
     const int num_kb = w.taps * (w.cin / 64) + p.res_kb;
     const bool chunked = split && kc > 0 && num_kb > kc && num_kb > chunk_above_kb && BN <= 128;
     p.kc = chunked ? kc : num_kb;
-    // the pair kernel pays a cross-CTA handshake per tile: it wins from 16 k-blocks per tile up (measured, +8..22 % on
-    // the 3x3 and K >= 1024 layers) and loses below 8 (the short-K layers are epilogue / HBM bound)
-    const bool pair = use_cta2 && split && BN == 128 && num_kb >= cta2_min_kb && p.res_kb == 0 && !o.stem_window;
+    // the pair kernel pays a cross-CTA handshake per tile: at BLOCK_N = 128 it wins from 16 k-blocks per tile up
+    // (measured, +8..22 % on the 3x3 and K >= 1024 layers) and loses below 8 (the short-K layers are epilogue / HBM
+    // bound).  BLOCK_N = 64: only the multi-tap convs (stem, layer1 3x3), whose N <= 128 instructions are paced by the
+    // per-instruction floor of the tensor pipe - M = 256 halves the instruction count per pixel.
+    const bool pair = use_cta2 && split && p.res_kb == 0 &&
+                      ((BN == 128 && num_kb >= cta2_min_kb && !o.stem_window) ||
+                       (BN == 64 && w.taps > 1 && num_kb >= cta2_min_kb64 && !chunked));
     if (profiling) {
       // algorithmic HBM bytes: every operand element once at its stored width (activations 4 B split / 2 B bf16)
       const double eb = split ? 4.0 : 2.0;
@@ -445,8 +451,10 @@ struct ConvEngine {
       recs.push_back(r);
     }
     if (pair) {
-      const CUtensorMap tbh = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, 2, 64, 1);
-      if (chunked) launch_tc2<true>(ta, tb, tbh, tc, p, st); else launch_tc2<false>(ta, tb, tbh, tc, p, st);
+      const CUtensorMap tbh = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, 2, BN / 2, 1);
+      if (BN == 64) launch_tc2<64, false>(ta, tb, tbh, tc, p, st);
+      else if (chunked) launch_tc2<128, true>(ta, tb, tbh, tc, p, st);
+      else launch_tc2<128, false>(ta, tb, tbh, tc, p, st);
     } else if (split) {
       if (BN == 64) { if (chunked) launch_tc<64, true, true>(ta, tb, tc, tr, ti, p, st); else launch_tc<64, true, false>(ta, tb, tc, tr, ti, p, st); }
       else if (BN == 128) { if (chunked) launch_tc<128, true, true>(ta, tb, tc, tr, ti, p, st); else launch_tc<128, true, false>(ta, tb, tc, tr, ti, p, st); }

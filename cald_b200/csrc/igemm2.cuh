@@ -24,23 +24,26 @@
 
 namespace cald {
 
+template <int BN>
 struct Igemm2Cfg {
-  static constexpr int BLOCK_N = 128;
+  static constexpr int BLOCK_N = BN;                           // 128, or 64 for the Cout = 64 layers
   static constexpr int A_BYTES = IG_BLOCK_M * IG_BLOCK_K * 2;  // one plane of the CTA's own 128 pixels
-  static constexpr int BX_BYTES = 128 * IG_BLOCK_K * 2;        // this CTA's half of [B_hi | B_lo]
-  static constexpr int BY_BYTES = 64 * IG_BLOCK_K * 2;         // this CTA's half of B_hi for the A_lo product
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + BX_BYTES + BY_BYTES;  // 56 KB
+  static constexpr int BX_BYTES = BN * IG_BLOCK_K * 2;         // this CTA's half of [B_hi | B_lo]: BN rows
+  static constexpr int BY_BYTES = (BN / 2) * IG_BLOCK_K * 2;   // this CTA's half of B_hi for the A_lo product
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + BX_BYTES + BY_BYTES;  // 56 KB (BN = 128) / 44 KB (BN = 64)
   static constexpr int OUT_STAGE_BYTES = 2 * A_BYTES;
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int STAGES = 3;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - BAR_BYTES - OUT_STAGE_BYTES;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES;          // 3 / 4
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + OUT_STAGE_BYTES + 1024;
-  static constexpr int TMEM_COLS = 512;
-  static constexpr int ACC_STRIDE = 256;
+  static constexpr int TMEM_COLS = 4 * BN;                     // two accumulator stages of 2 * BN columns
+  static constexpr int ACC_STRIDE = 2 * BN;
   static constexpr int OFF_A_LO = A_BYTES;
   static constexpr int OFF_BX = 2 * A_BYTES;
   static constexpr int OFF_BY = OFF_BX + BX_BYTES;
 };
-static_assert(Igemm2Cfg::SMEM_BYTES <= 227 * 1024, "pair kernel smem");
+static_assert(Igemm2Cfg<128>::SMEM_BYTES <= 227 * 1024 && Igemm2Cfg<64>::SMEM_BYTES <= 227 * 1024, "pair kernel smem");
+static_assert(Igemm2Cfg<128>::STAGES == 3 && Igemm2Cfg<64>::STAGES == 4, "pair kernel stages");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -101,12 +104,12 @@ __device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
 // Launch contract (conv_host.cuh): split mode, BLOCK_N = 128, no residual k-blocks;
 // grid = 2 x clusters, every cluster strides over the (n block, pair of m tiles) list.  CHUNKED as in igemm.cuh: the
 // accumulator restarts every p.kc k-blocks and the epilogue warps of both CTAs sum the partial tiles in registers.
-template <bool CHUNKED>
+template <int BN_, bool CHUNKED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IG_THREADS, 1)
 igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmC,
                  const __grid_constant__ ConvParams p) {
-  using Cfg = Igemm2Cfg;
+  using Cfg = Igemm2Cfg<BN_>;
   constexpr int BLOCK_N = Cfg::BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -198,7 +201,7 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_load_4d_pair(sa, &tmA, fb, c0, ax, ay, ai);
           tma_load_4d_pair(sa + Cfg::OFF_BX, &tmB, fb, bk, bn, 0, (int)rank);          // B_hi (leader) / B_lo (peer)
           tma_load_4d_pair(sa + Cfg::OFF_A_LO, &tmA, fb, c0, ax, ay, ai + p.a_lo_img);
-          tma_load_4d_pair(sa + Cfg::OFF_BY, &tmBh, fb, bk, bn + 64 * (int)rank, 0, 0);  // this CTA's half of B_hi
+          tma_load_4d_pair(sa + Cfg::OFF_BY, &tmBh, fb, bk, bn + (BLOCK_N / 2) * (int)rank, 0, 0);  // half of B_hi
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -212,8 +215,8 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && rank == 0) {
       const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24);  // M = 256
-      const uint32_t idesc_cat = idesc_base | ((uint32_t)(256 >> 3) << 17);
-      const uint32_t idesc_half = idesc_base | ((uint32_t)(128 >> 3) << 17);
+      const uint32_t idesc_cat = idesc_base | ((uint32_t)((2 * BLOCK_N) >> 3) << 17);
+      const uint32_t idesc_half = idesc_base | ((uint32_t)(BLOCK_N >> 3) << 17);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;

@@ -130,6 +130,8 @@ PAIR_CASES = [
     (1, 1, 200, 12544, 128, 1, 1, 0, None),     # fc6-like, 196 k-blocks, chunked
     (1, 25, 42, 256, 819, 3, 1, 0, None),       # RetinaNet cls_logits: 7 n-blocks, the last one ragged, direct fp32 stores
     (1, 10, 100, 1024, 112, 1, 1, 0, None),     # one ragged n-block (predictor-like)
+    (2, 20, 28, 64, 64, 3, 1, 0, None),         # BLOCK_N = 64 pair instantiation (layer1 3x3), 9 k-blocks, 4 smem stages
+    (3, 25, 42, 128, 64, 3, 2, 0, None),        # BLOCK_N = 64, stride 2, odd tile count
 ]
 
 
@@ -150,6 +152,7 @@ def test_conv_cta_pair_kernel_matches_fp32_and_single_cta(case, monkeypatch):
     assert L.cald_ops_pair_launches() == before
     monkeypatch.setenv("CALD_CTA2", "1")
     monkeypatch.setenv("CALD_CTA2_MIN_KB", "1")   # the engine default only pairs launches of >= 16 k-blocks
+    monkeypatch.setenv("CALD_CTA2_MIN_KB64", "1")
     got = ops.conv2d(x, wt, b, stride=stride, relu=True, res=res, res_mode=res_mode, prec=0, impl=0)
     assert L.cald_ops_pair_launches() == before + 1, "the launch did not take the pair kernel"
     scale = np.abs(want).max()
