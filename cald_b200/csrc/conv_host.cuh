@@ -145,7 +145,7 @@ struct ConvEngine {
   // CTA-pair kernel (igemm2.cuh) for the split-mode BLOCK_N = 128 launches it covers; CALD_CTA2=0/1 overrides
   bool use_cta2 = env_flag("CALD_CTA2", true);
   int cta2_min_kb = env_int("CALD_CTA2_MIN_KB", 16);
-  int cta2_min_kb64 = env_int("CALD_CTA2_MIN_KB64", 4);
+  int cta2_min_kb64 = env_int("CALD_CTA2_MIN_KB64", 9);
   static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -426,11 +426,10 @@ struct ConvEngine {
     p.kc = chunked ? kc : num_kb;
     // the pair kernel pays a cross-CTA handshake per tile: at BLOCK_N = 128 it wins from 16 k-blocks per tile up
     // (measured, +8..22 % on the 3x3 and K >= 1024 layers) and loses below 8 (the short-K layers are epilogue / HBM
-    // bound).  BLOCK_N = 64: only the multi-tap convs (stem, layer1 3x3), whose N <= 128 instructions are paced by the
-    // per-instruction floor of the tensor pipe - M = 256 halves the instruction count per pixel.
-    const bool pair = use_cta2 && split && p.res_kb == 0 &&
-                      ((BN == 128 && num_kb >= cta2_min_kb && !o.stem_window) ||
-                       (BN == 64 && w.taps > 1 && num_kb >= cta2_min_kb64 && !chunked));
+    // bound).  BLOCK_N = 64: the layer1 3x3 convs gain 5 %; the stem (4 k-blocks) loses 12 % and stays on one CTA.
+    const bool pair = use_cta2 && split && p.res_kb == 0 && !o.stem_window &&
+                      ((BN == 128 && num_kb >= cta2_min_kb) ||
+                       (BN == 64 && w.taps == 9 && num_kb >= cta2_min_kb64 && !chunked));
     if (profiling) {
       // algorithmic HBM bytes: every operand element once at its stored width (activations 4 B split / 2 B bf16)
       const double eb = split ? 4.0 : 2.0;

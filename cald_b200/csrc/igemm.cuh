@@ -96,6 +96,29 @@ __device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 accumulator columns = main + cross-term columns (XSEP): both TMEM loads are in flight before the one wait, so a
+// 64-channel group costs two TMEM round trips instead of four (the epilogue of the short-K layers is latency-bound:
+// ncu stall samples sat on the first FADD after every LDTM)
+__device__ __forceinline__ void tmem_ld32_sum2(uint32_t t_main, uint32_t t_cross, float* v) {
+  uint32_t a[32], b[32];
+  tmem_ld32_nowait(t_main, a);
+  tmem_ld32_nowait(t_cross, b);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]) + __uint_as_float(b[i]);
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -379,20 +402,17 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = accv[(g * 64 + i) % NACC];
         } else {
-          uint32_t r[32];
-          tmem_ld32(t0 + g * 64, r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          tmem_ld32(t0 + g * 64 + 32, r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
           if (XSEP) {
-            tmem_ld32(t0 + BLOCK_N + g * 64, r);
+            tmem_ld32_sum2(t0 + g * 64, t0 + BLOCK_N + g * 64, v);
+            tmem_ld32_sum2(t0 + g * 64 + 32, t0 + BLOCK_N + g * 64 + 32, v + 32);
+          } else {
+            uint32_t r[32];
+            tmem_ld32(t0 + g * 64, r);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
-            tmem_ld32(t0 + BLOCK_N + g * 64 + 32, r);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            tmem_ld32(t0 + g * 64 + 32, r);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[32 + i] += __uint_as_float(r[i]);
+            for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
           }
           if (g == BLOCK_N / 64 - 1) {  // accumulator fully drained: hand the TMEM stage back to the MMA warp
             tcgen05_fence_before();

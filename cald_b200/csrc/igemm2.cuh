@@ -316,19 +316,8 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = accv[CHUNKED ? g * 64 + i : 0];
         } else {
-          uint32_t r[32];
-          tmem_ld32(t0 + g * 64, r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          tmem_ld32(t0 + g * 64 + 32, r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
-          tmem_ld32(t0 + BLOCK_N + g * 64, r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
-          tmem_ld32(t0 + BLOCK_N + g * 64 + 32, r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[32 + i] += __uint_as_float(r[i]);
+          tmem_ld32_sum2(t0 + g * 64, t0 + BLOCK_N + g * 64, v);
+          tmem_ld32_sum2(t0 + g * 64 + 32, t0 + BLOCK_N + g * 64 + 32, v + 32);
           if (g == BLOCK_N / 64 - 1) {  // accumulator drained: hand the stage back to the leader's MMA thread
             tcgen05_fence_before();
             __syncwarp();

@@ -9,9 +9,9 @@ timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|^FAIL
 python bench.py --layers gpurun_out/final_layers_frcnn.tsv > gpurun_out/final_bench_frcnn.json 2> gpurun_out/final_bench_frcnn.err; tail -1 gpurun_out/final_bench_frcnn.json | cut -c1-160
 python bench.py --model retinanet --no-cpu-baseline --layers gpurun_out/final_layers_retina.tsv > gpurun_out/final_bench_retina.json 2> gpurun_out/final_bench_retina.err; tail -1 gpurun_out/final_bench_retina.json | cut -c1-160
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workspace-gb 48"
-ncu --metrics gpu__time_duration.sum --clock-control none -s 262 -c 262 --csv --log-file gpurun_out/final_launches_step.csv $CMD > gpurun_out/final_ncu1.log 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:igemm_tc -s 148 -c 148 --csv --log-file gpurun_out/final_igemm_dram_step.csv $CMD > gpurun_out/final_ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:igemm_tc2 -s 126 -c 12 -f -o /tmp/prof_pair $CMD > gpurun_out/final_ncu3.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 256 -c 256 --csv --log-file gpurun_out/final_launches_step.csv $CMD > gpurun_out/final_ncu1.log 2>&1
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:igemm_tc -s 142 -c 142 --csv --log-file gpurun_out/final_igemm_dram_step.csv $CMD > gpurun_out/final_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:igemm_tc2 -s 142 -c 14 -f -o /tmp/prof_pair $CMD > gpurun_out/final_ncu3.log 2>&1
 ncu -i /tmp/prof_pair.ncu-rep --page raw --csv > /tmp/prof_pair_raw.csv 2>/dev/null
 python tools/ncu_condense.py /tmp/prof_pair_raw.csv > gpurun_out/final_pair_full_capture.csv
 ls -la gpurun_out | grep final

@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|^FAILED" | head
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_q.json 2>/dev/null; tail -1 gpurun_out/bench_q.json | cut -c1-170
-ncu --metrics gpu__time_duration.sum --clock-control none -s 262 -c 262 --csv --log-file gpurun_out/launches_q.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workspace-gb 48 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 256 -c 256 --csv --log-file gpurun_out/launches_q.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workspace-gb 48 > /dev/null 2>&1
 python - <<'PY'
 import csv,collections,re
 rows=list(csv.reader(open('gpurun_out/launches_q.csv')))
