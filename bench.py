@@ -32,10 +32,10 @@ AUGS = ['flip', 'cut_out', 'smaller_resize', 'rotation']
 METRIC = "unlabeled images scored/sec (FRCNN R50-FPN, 800x1333)"
 WORKLOAD = "FRCNN R50-FPN nc=91, synthetic 1333x800 pool, 1 ref + 4 aug (F,C,D,R) forwards per image"
 # --model retinanet = BASELINE.json configs[2] (RetinaNet R50-FPN, retinanet_cal.py), same pool shape and augmentations
-# DRAM bytes per conv launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu) averaged over the 148 igemm_tc_kernel /
+# DRAM bytes per conv launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu) averaged over the 142 igemm_tc_kernel /
 # igemm_tc2_kernel launches of one default step (batch 16: a 16-view reference pass + a 64-view augmented pass); source:
 # profiles/r01_igemm_dram_step.csv, captured with tools/final_measure.sh.  Only valid for the default FRCNN workload.
-NCU_DRAM_BYTES_PER_CONV_LAUNCH = 1619.3e6
+NCU_DRAM_BYTES_PER_CONV_LAUNCH = 1556.2e6
 NCU_DRAM_BATCH = 16
 METRIC_RETINA = "unlabeled images scored/sec (RetinaNet R50-FPN, 800x1333)"
 WORKLOAD_RETINA = "RetinaNet R50-FPN nc=91, synthetic 1333x800 pool, 1 ref + 4 aug (F,C,D,R) forwards per image"
@@ -329,7 +329,7 @@ def main():
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None,
                      "traffic": NCU_DRAM_BYTES_PER_CONV_LAUNCH if (not retina and B == NCU_DRAM_BATCH) else None,
-                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, mean over the 148 conv "
+                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, mean over the 142 conv "
                                      "launches of one step; profiles/r01_igemm_dram_step.csv)",
                      "algorithmic_bytes_per_launch": conv_bytes / conv_launches if conv_launches else None,
                      "kernel": "igemm_tc_kernel + igemm_tc2_kernel (tcgen05 implicit-GEMM conv/GEMM: one-CTA and CTA-pair cta_group::2 instantiations)",

@@ -1,5 +1,6 @@
 // Host side of the implicit-GEMM engine: tensor-map construction, tile choice, launch.
 #pragma once
+#include <atomic>
 #include <cstring>
 #include <vector>
 #include <cstdlib>
@@ -129,8 +130,8 @@ inline void choose_tile(int H, int W, int& th, int& tw) {
 enum ConvImpl { CONV_TC = 0, CONV_SIMT = 1 };
 
 // launches of the CTA-pair kernel in this process (lets the parity tests assert which kernel they exercised)
-inline long long& pair_launch_counter() {
-  static long long n = 0;
+inline std::atomic<long long>& pair_launch_counter() {
+  static std::atomic<long long> n{0};  // independent engine handles may launch from different host threads
   return n;
 }
 

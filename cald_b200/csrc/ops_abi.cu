@@ -7,7 +7,7 @@ using namespace cald;
 static thread_local std::string g_ops_err;
 extern "C" const char* cald_ops_last_error(void) { return g_ops_err.c_str(); }
 
-extern "C" long long cald_ops_pair_launches(void) { return pair_launch_counter(); }
+extern "C" long long cald_ops_pair_launches(void) { return pair_launch_counter().load(); }
 
 #define OPS_TRY try {
 #define OPS_CATCH                                   \
