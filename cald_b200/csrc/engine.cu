@@ -569,7 +569,9 @@ void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views
       F.scale[l] = (float)std::pow(2.0, std::round(std::log2((double)pf[l].h / (double)Hp)));
     }
     F.C = 256;
-    roialign_kernel<<<dim3(cap, V), ROI_THREADS, 0, st>>>(F, props, prop_count, cap, roi.hi, roi.lo());
+    static const bool roi_fma = ConvEngine::env_flag("CALD_ROI_FMA", true);
+    if (roi_fma) roialign_kernel<true><<<dim3(cap, V), ROI_THREADS, 0, st>>>(F, props, prop_count, cap, roi.hi, roi.lo());
+    else roialign_kernel<false><<<dim3(cap, V), ROI_THREADS, 0, st>>>(F, props, prop_count, cap, roi.hi, roi.lo());
     CALD_CUDA_CHECK(cudaGetLastError());
     KLAUNCH(e);
   }

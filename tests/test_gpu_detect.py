@@ -53,6 +53,33 @@ def test_dense_stages_match_oracle(setup):
         assert np.abs(got[..., 3:15].reshape(-1, 4) - dl.numpy()).max() < 1e-3
 
 
+def test_roialign_matches_oracle_on_engine_inputs(setup):
+    """MultiScaleRoIAlign stage (a14) in isolation: the oracle's RoIAlign (tv:ops/roi_align.py restated) fed with the
+    ENGINE's own pyramid and proposals must reproduce the engine's pooled features.  The pyramid values are split-bf16
+    numbers (exact in fp32), so the only differences are the order of the fp32 operations and the 2^-17 rounding of
+    the pooled output to split bf16."""
+    eng, w, cfg, fo, synth = setup
+    img = synth.synth_image(8, 200, 300)
+    st = {}
+    fo.forward(torch.from_numpy(img).permute(2, 0, 1).float().div(255), w, cfg, st)
+    eng.detect([img])
+    n = int(eng.debug_fetch("proposal_count")[0])
+    props = eng.debug_fetch("proposals").reshape(-1, 4)
+    cap = props.shape[0]
+    assert 0 < n <= cap
+    feats = []
+    for i, name in enumerate(("p2", "p3", "p4", "p5")):
+        c, h, wd = st["p"][i].shape[1:]
+        feats.append(torch.from_numpy(eng.debug_fetch(name).reshape(h, wd, c)).permute(2, 0, 1)[None].contiguous())
+    want = fo.multiscale_roi_align(feats, torch.from_numpy(props[:n].copy())).numpy()      # n x 256 x 7 x 7
+    got = eng.debug_fetch("pooled").reshape(cap, 7, 7, 256)[:n].transpose(0, 3, 1, 2)
+    scale = np.abs(want).max()
+    assert scale > 0
+    assert np.abs(got - want).max() <= 2e-5 * scale, np.abs(got - want).max() / scale
+    # rows beyond the proposal count are zero
+    assert not eng.debug_fetch("pooled").reshape(cap, -1)[n:].any()
+
+
 def test_proposals_match_oracle(setup):
     eng, w, cfg, fo, synth = setup
     img = synth.synth_image(6, 200, 300)
