@@ -443,10 +443,11 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiFeats F, const
           const int o1 = ylo + xlo, o2 = ylo + xhi, o3 = yhi + xlo, o4 = yhi + xhi;
           float v1[8], v2[8], v3[8], v4[8];
           auto ld = [&](int off, float* dst) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(fhi + off));
+            // plain (coherent-path) loads: the non-coherent LDG.CONSTANT form measured 45 % slower here (5.37 vs 3.70 ms)
+            const uint4 a = *reinterpret_cast<const uint4*>(fhi + off);
             const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
             if (flo) {
-              const uint4 b = __ldg(reinterpret_cast<const uint4*>(flo + off));
+              const uint4 b = *reinterpret_cast<const uint4*>(flo + off);
               const uint32_t* pb2 = reinterpret_cast<const uint32_t*>(&b);
 #pragma unroll
               for (int q = 0; q < 4; ++q) join_pack2(pa[q], pb2[q], dst[2 * q], dst[2 * q + 1]);
