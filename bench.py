@@ -148,6 +148,25 @@ def cpu_baseline(n_images, threads=None, model="frcnn"):
     return n_images / dt, torch.get_num_threads()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to stdout
+    when NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the whole run and the
+    result line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(obj) + "\n").encode())
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
     if rank != 0:
@@ -167,7 +186,7 @@ def run_reference(args, rank):
     v = args.steps / dt
     cores = torch.get_num_threads()
     sample = "%d images (1 per step), oracle port of cald_train.get_uncertainty on torch CPU fp32" % args.steps
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC_RETINA if args.model == "retinanet" else METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -193,6 +212,7 @@ def main():
     ap.add_argument("--layers", default=None, help="write the per-layer conv timing table (TSV) to this path")
     args = ap.parse_args()
 
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -344,7 +364,7 @@ def main():
         v, cores = cpu_baseline(args.cpu_images, model=args.model)
         out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                                "sample": "%d image(s) of the same workload, oracle port (torch CPU fp32)" % args.cpu_images}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
