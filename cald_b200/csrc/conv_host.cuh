@@ -145,6 +145,7 @@ struct ConvEngine {
   bool force_pow2_tiles = false;  // true: restrict spatial tiles to power-of-two shapes
   // CTA-pair kernel (igemm2.cuh) for the split-mode BLOCK_N = 128 launches it covers; CALD_CTA2=0/1 overrides
   bool use_cta2 = env_flag("CALD_CTA2", true);
+  int resmma_max_kb = env_int("CALD_RESMMA_MAX_KB", 1 << 20);
   int cta2_min_kb = env_int("CALD_CTA2_MIN_KB", 16);
   int cta2_min_kb64 = env_int("CALD_CTA2_MIN_KB64", 9);
   static int env_int(const char* name, int dflt) {
@@ -395,8 +396,12 @@ struct ConvEngine {
     // residual on the tensor core (see igemm.cuh): same-shape shortcut, channel count a multiple of BLOCK_N
     CUtensorMap tr = tb, ti = tb;
     p.res_kb = 0;
+    // A residual k-block costs as many MMA instructions as a conv k-block; for launches paced by the tensor pipe
+    // (256 -> 1024: 2 of 6 k-blocks) adding the shortcut in the epilogue registers instead may win.  resmma_max_kb
+    // (CALD_RESMMA_MAX_KB) limits the MMA form to contractions of at most that many conv k-blocks; unmeasured so far,
+    // hence unlimited by default.
     if (use_res_mma && o.res_mode == RES_SAME && p.tma_store && (w.cout_pad % BN) == 0 && o.res->c == w.cout_pad &&
-        o.res->split == split) {
+        o.res->split == split && w.taps * (w.cin / 64) <= resmma_max_kb) {
       if (spatial) {
         tr = make_tmap(o.res->hi, o.res->c, o.res->w, o.res->h, (uint64_t)o.res->n * (split ? 2 : 1), p.tw, p.th);
         p.r_lo_img = o.res->n;

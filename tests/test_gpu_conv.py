@@ -5,6 +5,8 @@ reference's CPU run executes: tv resnet.py / feature_pyramid_network.py / rpn.py
 Tolerances: split-bf16 x3 mode carries ~16 mantissa bits per operand -> relative
 error ~2e-5 of the output scale; single-pass bf16 ~1e-2.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -52,6 +54,7 @@ CASES = [
     (2, 19, 25, 128, 128, 3, 2, 0, None),
     (1, 20, 26, 256, 512, 1, 2, 0, None),
     (1, 38, 50, 512, 256, 1, 1, 2, (19, 25)),
+    (2, 19, 25, 256, 1024, 1, 1, 1, None),      # layer3 expand conv: 4 conv + 2 residual k-blocks, 8 n-blocks
     (1, 13, 21, 256, 16, 1, 1, 0, None),
     (1, 10, 100, 1024, 112, 1, 1, 0, None),
 ]
@@ -188,3 +191,22 @@ def test_conv_fused_projection_shortcut(case):
     got = ops.conv2d_dual(y, w3, b3, x, wd, bd, stride2=s2, relu=True)
     assert got.shape == want.shape
     assert np.abs(got - want).max() <= 3e-5 * np.abs(want).max() + 1e-6
+
+
+@pytest.mark.skipif(os.environ.get("CALD_TEST_EXPERIMENTAL") != "1",
+                    reason="CALD_RESMMA_MAX_KB is an experiment switch that has not run on a B200 yet "
+                           "(the round's GPU budget was spent); set CALD_TEST_EXPERIMENTAL=1 to run it")
+def test_conv_shortcut_in_epilogue_registers(monkeypatch):
+    """CALD_RESMMA_MAX_KB limits the residual-as-MMA form to short contractions; above it the same-shape shortcut is
+    added in the epilogue registers.  Both forms against torch fp32 and against each other."""
+    from cald_b200 import ops
+    case = (2, 19, 25, 256, 1024, 1, 1, 1, None)
+    n, h, w, cin, cout, k, stride, res_mode, res_hw = case
+    x, wt, b, res = _case(11, n, h, w, cin, cout, k, stride, True, True, res_mode, res_hw)
+    want = _ref(x, wt, b, stride, True, res, res_mode)
+    outs = {}
+    for lim in ("1000000", "2"):
+        monkeypatch.setenv("CALD_RESMMA_MAX_KB", lim)
+        outs[lim] = ops.conv2d(x, wt, b, relu=True, res=res, res_mode=1, prec=0, impl=0)
+        assert np.abs(outs[lim] - want).max() <= 3e-5 * np.abs(want).max() + 1e-6, lim
+    assert np.abs(outs["2"] - outs["1000000"]).max() <= 4e-6 * np.abs(want).max()
