@@ -93,3 +93,14 @@ def test_shard_partition_covers_pool_in_order():
             assert sorted(flat.tolist()) == list(range(n))
             merged = shard.merge_shards([np.asarray(p, float) * 2 for p in parts], n, world)
             assert np.array_equal(merged, np.arange(n) * 2.0)
+
+
+def test_bench_prints_exactly_one_json_line_on_stdout():
+    """bench.py's contract is ONE JSON line on stdout; anything a library prints to file descriptor 1 during the run
+    (NCCL's version banner under torchrun) must end up on stderr instead."""
+    code = ("import os, sys, json; sys.path.insert(0, %r); import bench; bench.claim_stdout(); "
+            "print('library noise'); os.write(1, b'raw fd-1 noise\\n'); bench.emit({'metric': 'm', 'value': 1.5})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"metric": "m", "value": 1.5}\n'
+    assert "library noise" in r.stderr and "raw fd-1 noise" in r.stderr
