@@ -50,6 +50,10 @@ struct ConvOpts {
   const ConvW* aux_w = nullptr;
   int aux_stride = 1;
   const float* bias_sum = nullptr;
+  // fused 1x1 head (experiment): see igemm2.cuh HEAD.  head_w = device fp32 [16][w.cout_pad], head_part = device fp32
+  // [n_blocks][pixels][16]; requires relu, no residual, no stored output (no_bf16_out) and the pair kernel.
+  const float* head_w = nullptr;
+  float* head_part = nullptr;
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -232,13 +236,13 @@ struct ConvEngine {
     CALD_CUDA_CHECK(cudaGetLastError());
   }
 
-  template <int BN, bool CH>
+  template <int BN, bool CH, bool HEAD = false>
   void launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& tc,
                   const ConvParams& p, cudaStream_t st) {
     using Cfg = Igemm2Cfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc2_kernel<BN, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc2_kernel<BN, CH, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
       attr_set = true;
     }
@@ -246,7 +250,7 @@ struct ConvEngine {
     const int n_pairs = p.n_blocks * ((m_tiles + 1) / 2);
     const int clusters = n_pairs < num_sms / 2 ? n_pairs : num_sms / 2;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
-    igemm_tc2_kernel<BN, CH><<<2 * clusters, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, tc, p);
+    igemm_tc2_kernel<BN, CH, HEAD><<<2 * clusters, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, tc, p);
     pair_launch_counter()++;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
     CALD_CUDA_CHECK(cudaGetLastError());
@@ -433,9 +437,20 @@ struct ConvEngine {
     // the pair kernel pays a cross-CTA handshake per tile: at BLOCK_N = 128 it wins from 16 k-blocks per tile up
     // (measured, +8..22 % on the 3x3 and K >= 1024 layers) and loses below 8 (the short-K layers are epilogue / HBM
     // bound).  BLOCK_N = 64: the layer1 3x3 convs gain 5 %; the stem (4 k-blocks) loses 12 % and stays on one CTA.
-    const bool pair = use_cta2 && split && p.res_kb == 0 && !o.stem_window &&
-                      ((BN == 128 && num_kb >= cta2_min_kb) ||
-                       (BN == 64 && w.taps == 9 && num_kb >= cta2_min_kb64 && !chunked));
+    bool pair = use_cta2 && split && p.res_kb == 0 && !o.stem_window &&
+                ((BN == 128 && num_kb >= cta2_min_kb) ||
+                 (BN == 64 && w.taps == 9 && num_kb >= cta2_min_kb64 && !chunked));
+    const bool head = o.head_w != nullptr;
+    if (head) {
+      if (!o.head_part || !use_cta2 || !split || BN != 128 || chunked || p.res_kb != 0 || o.res_mode != RES_NONE ||
+          !o.relu || !o.no_bf16_out || o.out_f32 || !spatial || (w.cout_pad % 128) != 0)
+        throw std::runtime_error("conv: bad operands for the fused head");
+      pair = true;
+      p.head_w = o.head_w;
+      p.head_part = o.head_part;
+      p.head_ld = w.cout_pad;
+      p.head_rows = (long long)p.n_img * p.H * p.W;
+    }
     if (profiling) {
       // algorithmic HBM bytes: every operand element once at its stored width (activations 4 B split / 2 B bf16)
       const double eb = split ? 4.0 : 2.0;
@@ -446,18 +461,20 @@ struct ConvEngine {
       if (!o.no_bf16_out) by += pix * out.c * eb;
       if (o.res_mode != RES_NONE) by += (o.res_mode == RES_NEAREST ? 0.25 : 1.0) * pix * w.cout_pad * eb;
       if (dual) by += pix * o.aux_w->cin * eb + (double)w.cout_pad * o.aux_w->cin * eb;
+      if (head) by += pix * 16 * 4.0 * p.n_blocks;
       LayerRec r;
       snprintf(r.sig, sizeof(r.sig), "%dx%dx%d k%d%s cin%d cout%d BN%d%s%s%s%s%s", p.n_img, p.H, p.W,
                o.stem_window ? 7 : (w.taps == 9 ? 3 : 1), o.stride == 2 ? "s2" : "", o.stem_window ? 3 : w.cin, w.cout, BN,
                chunked ? " chunk" : "", pair ? " pair" : "",
                dual ? (o.aux_stride == 2 ? " +ds2" : " +ds") : (p.res_kb ? " resmma" : (o.res_mode != RES_NONE ? " res" : "")),
-               p.tma_store ? " tma" : " direct", o.relu ? " relu" : "");
+               head ? " head" : (p.tma_store ? " tma" : " direct"), o.relu ? " relu" : "");
       r.flops = fl; r.bytes = by;
       recs.push_back(r);
     }
     if (pair) {
       const CUtensorMap tbh = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, 2, BN / 2, 1);
-      if (BN == 64) launch_tc2<64, false>(ta, tb, tbh, tc, p, st);
+      if (head) launch_tc2<128, false, true>(ta, tb, tbh, tc, p, st);
+      else if (BN == 64) launch_tc2<64, false>(ta, tb, tbh, tc, p, st);
       else if (chunked) launch_tc2<128, true>(ta, tb, tbh, tc, p, st);
       else launch_tc2<128, false>(ta, tb, tbh, tc, p, st);
     } else if (split) {

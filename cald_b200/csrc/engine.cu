@@ -60,6 +60,10 @@ struct cald_engine {
 
   std::map<std::string, HostTensor> staged;
   bool weights_ready = false;
+  // experiment (CALD_FUSE_RPN=1, read when the engine is created): RPN 1x1 heads folded into the 3x3 RPN conv's epilogue
+  bool fuse_rpn = ConvEngine::env_flag("CALD_FUSE_RPN", false);
+  float* rpn_head_w = nullptr;  // device fp32 [16][256]: rows 0..2 objectness, 3..14 box deltas, row 15 zero
+  float* rpn_head_b = nullptr;  // device fp32 [16]
   ConvW stem;
   std::vector<std::vector<Block>> layers;
   ConvW fpn_inner[4], fpn_layer[4], rpn_conv, rpn_out, fc6, fc7, pred;
@@ -121,6 +125,9 @@ struct cald_engine {
       if (b.bias_c3ds) cudaFree(b.bias_c3ds);
     }
     layers.clear();
+    if (rpn_head_w) cudaFree(rpn_head_w);
+    if (rpn_head_b) cudaFree(rpn_head_b);
+    rpn_head_w = rpn_head_b = nullptr;
     weights_ready = false;
   }
   ~cald_engine() {
@@ -276,6 +283,13 @@ void finalize_weights(cald_engine* e) {
     for (int i = 0; i < 3; ++i) b[i] = bc.v[i];
     for (int i = 0; i < 12; ++i) b[3 + i] = bb.v[i];
     e->rpn_out = upload_conv_weight(w.data(), b.data(), 15, 256, 1, e->split, nullptr);
+    std::vector<float> w16(16 * 256, 0.f), b16(16, 0.f);
+    memcpy(w16.data(), w.data(), 15 * 256 * 4);
+    memcpy(b16.data(), b.data(), 15 * 4);
+    CALD_CUDA_CHECK(cudaMalloc((void**)&e->rpn_head_w, w16.size() * 4));
+    CALD_CUDA_CHECK(cudaMemcpy(e->rpn_head_w, w16.data(), w16.size() * 4, cudaMemcpyHostToDevice));
+    CALD_CUDA_CHECK(cudaMalloc((void**)&e->rpn_head_b, b16.size() * 4));
+    CALD_CUDA_CHECK(cudaMemcpy(e->rpn_head_b, b16.data(), b16.size() * 4, cudaMemcpyHostToDevice));
   }
   {
     // fc6: torch flattens [256][7][7] as c*49 + ph*7 + pw; RoIAlign writes (ph*7+pw)*256 + c
@@ -489,16 +503,36 @@ void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views
   static const float sizes[5] = {32.f, 64.f, 128.f, 256.f, 512.f};
   int off = 0;
   for (int l = 0; l < 5; ++l) {
-    Act t = conv(e, pf[l], e->rpn_conv, V, pf[l].h, pf[l].w, relu_o);
     rpn_raw[l] = (float*)ar.alloc((size_t)V * pf[l].h * pf[l].w * 16 * 4);
-    Act dummy;
-    dummy.n = V; dummy.h = pf[l].h; dummy.w = pf[l].w; dummy.c = 16; dummy.split = split; dummy.hi = nullptr;
-    ConvOpts o;
-    o.out_f32 = rpn_raw[l];
-    o.no_bf16_out = true;
-    e->conv.run(t, e->rpn_out, dummy, o, st);
-    KLAUNCH(e);
-    free_act(ar, t);
+    if (e->fuse_rpn && split && e->conv.use_cta2 && e->conv.impl == CONV_TC) {
+      // experiment: relu(conv3x3) never reaches HBM; its epilogue emits the two per-n-block partial head rows
+      const long long pix = (long long)V * pf[l].h * pf[l].w;
+      float* part = (float*)ar.alloc((size_t)pix * 16 * 4 * 2);
+      Act none;
+      none.n = V; none.h = pf[l].h; none.w = pf[l].w; none.c = e->rpn_conv.cout_pad; none.split = split; none.hi = nullptr;
+      ConvOpts o;
+      o.relu = true;
+      o.no_bf16_out = true;
+      o.head_w = e->rpn_head_w;
+      o.head_part = part;
+      e->conv.run(pf[l], e->rpn_conv, none, o, st);
+      KLAUNCH(e);
+      rpn_head_sum_kernel<<<(unsigned)((pix * 4 + 255) / 256), 256, 0, st>>>(
+          (const float4*)part, pix * 4, (const float4*)e->rpn_head_b, (float4*)rpn_raw[l]);
+      CALD_CUDA_CHECK(cudaGetLastError());
+      KLAUNCH(e);
+      ar.free(part);
+    } else {
+      Act t = conv(e, pf[l], e->rpn_conv, V, pf[l].h, pf[l].w, relu_o);
+      Act dummy;
+      dummy.n = V; dummy.h = pf[l].h; dummy.w = pf[l].w; dummy.c = 16; dummy.split = split; dummy.hi = nullptr;
+      ConvOpts o;
+      o.out_f32 = rpn_raw[l];
+      o.no_bf16_out = true;
+      e->conv.run(t, e->rpn_out, dummy, o, st);
+      KLAUNCH(e);
+      free_act(ar, t);
+    }
     RpnLevel& lv = L.lv[l];
     lv.out = rpn_raw[l];
     lv.h = pf[l].h; lv.w = pf[l].w;

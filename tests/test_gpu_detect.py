@@ -127,3 +127,33 @@ def test_simt_and_tcgen05_paths_agree(setup):
     assert np.abs(pa - pb).max() / np.abs(pb).max() < 1e-4
     k = min(len(a["scores"]), len(b["scores"]), 10)
     assert np.abs(a["scores"][:k] - b["scores"][:k]).max() < 1e-3
+
+
+@pytest.mark.skipif(__import__("os").environ.get("CALD_TEST_EXPERIMENTAL") != "1",
+                    reason="CALD_FUSE_RPN is an experiment switch that has not run on a B200 yet; "
+                           "set CALD_TEST_EXPERIMENTAL=1 to run it")
+def test_fused_rpn_head_matches_separate_launches(setup, monkeypatch):
+    """CALD_FUSE_RPN=1 folds the RPN 1x1 heads into the 3x3 RPN conv's epilogue (fp32 FFMA on the un-rounded activations).
+    Objectness logits / box deltas must agree with the two-launch form and with the oracle; detections must agree."""
+    eng, w, cfg, fo, synth = setup
+    from cald_b200.engine import Engine
+    img = synth.synth_image(5, 200, 300)
+    st = {}
+    fo.forward(torch.from_numpy(img).permute(2, 0, 1).float().div(255), w, cfg, st)
+    monkeypatch.setenv("CALD_FUSE_RPN", "1")
+    e2 = Engine(depth=50, num_classes=21, min_size=320, max_size=512, debug=True, max_views_per_pass=4)
+    e2.load_state_dict(w)
+    a = eng.detect([img])[0]
+    b = e2.detect([img])[0]
+    for l in range(5):
+        lg, dl = st["rpn"][l]
+        h, wd = st["p"][l].shape[-2:]
+        sep = eng.debug_fetch("rpn%d" % l).reshape(h, wd, 16)
+        fus = e2.debug_fetch("rpn%d" % l).reshape(h, wd, 16)
+        assert np.abs(fus[..., :15] - sep[..., :15]).max() < 2e-3
+        assert np.abs(fus[..., :3].reshape(-1) - lg.numpy()).max() < 2e-3
+        assert np.abs(fus[..., 3:15].reshape(-1, 4) - dl.numpy()).max() < 1e-3
+    k = min(len(a["scores"]), len(b["scores"]), 10)
+    assert abs(len(a["scores"]) - len(b["scores"])) <= 1
+    assert np.array_equal(a["labels"][:k], b["labels"][:k])
+    assert np.abs(a["scores"][:k] - b["scores"][:k]).max() < 1e-3
