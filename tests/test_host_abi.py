@@ -47,6 +47,10 @@ def test_create_fails_loudly_without_gpu(built):
 def test_sass_contains_blackwell_tensor_and_tma_instructions(built):
     out = subprocess.run(["cuobjdump", "-sass", built], capture_output=True, text=True).stdout
     assert "UTCHMMA" in out and "UTMALDG" in out and "LDTM" in out
+    # CTA-pair conv kernel (igemm2.cuh): cta_group::2 MMA, multicast commit, pair TMA loads, cluster barrier
+    for mnemonic in ("UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST", "UTMALDG.4D.2CTA", "UCGABAR_ARV"):
+        assert mnemonic in out, mnemonic
+    assert "HMMA.16816" not in out  # no legacy mma.sync tensor path anywhere in the library
 
 
 def test_weight_key_aliases():
