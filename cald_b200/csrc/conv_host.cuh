@@ -1,6 +1,7 @@
 // Host side of the implicit-GEMM engine: tensor-map construction, tile choice, launch.
 #pragma once
 #include <atomic>
+#include <mutex>
 #include <cstring>
 #include <vector>
 #include <cstdlib>
@@ -223,12 +224,11 @@ struct ConvEngine {
   void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
                  const CUtensorMap& ti, const ConvParams& p, cudaStream_t st) {
     using Cfg = IgemmCfg<BN, SP>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::once_flag attr_once;  // independent engine handles may launch from different host threads
+    std::call_once(attr_once, [] {
       CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<BN, SP, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
-      attr_set = true;
-    }
+    });
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
     igemm_tc_kernel<BN, SP, CH><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tr, ti, p);
@@ -240,12 +240,11 @@ struct ConvEngine {
   void launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& tc,
                   const ConvParams& p, cudaStream_t st) {
     using Cfg = Igemm2Cfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::once_flag attr_once;
+    std::call_once(attr_once, [] {
       CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc2_kernel<BN, CH, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
-      attr_set = true;
-    }
+    });
     const int m_tiles = p.tiles_x * p.tiles_y * p.n_img;
     const int n_pairs = p.n_blocks * ((m_tiles + 1) / 2);
     const int clusters = n_pairs < num_sms / 2 ? n_pairs : num_sms / 2;
