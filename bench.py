@@ -348,6 +348,7 @@ def main():
                 "d2h_bytes_per_step": B * (len(AUGS) + (1 + len(AUGS)) * (NUM_CLASSES - 1) + 1) * 4 + 4},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None,
+                     "frac_of_bf16x3_ceiling": 3.0 * achieved / peak_tf if peak_tf else None,
                      "traffic": NCU_DRAM_BYTES_PER_CONV_LAUNCH if (not retina and B == NCU_DRAM_BATCH) else None,
                      "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, mean over the 142 conv "
                                      "launches of one step; profiles/r01_igemm_dram_step.csv)",
