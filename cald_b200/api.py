@@ -48,9 +48,23 @@ def _model_config(task_model, num_cls):
     return depth, min_size, max_size, sd, arch_id
 
 
+def _weights_fingerprint(sd):
+    """Cheap identity of a state_dict's CONTENT: torch bumps ``tensor._version`` on every in-place update (optimizer
+    steps, load_state_dict), so (storage address, version) of every tensor changes whenever the weights do.  Anything
+    that is not a torch tensor (numpy weights in the tests) has no version counter: None = always reload."""
+    fp = []
+    for k, v in sd.items():
+        if not hasattr(v, "_version") or not hasattr(v, "data_ptr"):
+            return None
+        fp.append((k, v.data_ptr(), v._version, tuple(v.shape)))
+    return hash(tuple(fp))
+
+
 def engine_for(task_model, num_cls, device=0, **kw):
-    """Build (or reuse) the engine for this model object; weights are re-read on every call of
-    get_uncertainty because the AL cycle retrains the model in between (cald_train.py:409-411)."""
+    """The engine for this detector configuration (one per configuration and GPU, built on first use) holding THIS
+    model's current weights.  The AL cycle retrains the model between scoring calls (cald_train.py:409-411) and one
+    configuration may serve several model objects, so the weights are re-read whenever the state_dict's fingerprint
+    differs from what the engine holds -- never silently stale, not re-uploaded when nothing changed."""
     depth, mn, mx, sd, arch_id = _model_config(task_model, num_cls)
     key = (arch_id, depth, num_cls, mn, mx, device, tuple(sorted(kw.items())))
     eng = _engine_cache.get(key)
@@ -58,8 +72,18 @@ def engine_for(task_model, num_cls, device=0, **kw):
         eng = _eng.Engine(depth=depth, num_classes=num_cls, min_size=mn, max_size=mx, device=device,
                           arch_id=arch_id, **kw)
         _engine_cache[key] = eng
-    eng.load_state_dict(sd)
+    fp = _weights_fingerprint(sd)
+    if fp is None or getattr(eng, "_weights_fp", None) != fp:
+        eng.load_state_dict(sd)
+        eng._weights_fp = fp
     return eng
+
+
+def close_engines():
+    """Destroy every cached engine (each holds a device arena of up to 64 GB and a weight replica)."""
+    for eng in _engine_cache.values():
+        eng.close()
+    _engine_cache.clear()
 
 
 def _to_u8(image):
@@ -70,51 +94,104 @@ def _to_u8(image):
     return np.ascontiguousarray(a)
 
 
-def _draw_noise(images, views):
-    """torch CPU-generator draws in the order the reference makes them (cald_helper.py:74, 80): per image, per
-    noise view: torch.randn(image.size()) for GaussianNoise, torch.rand(image.size()) for SaltPepperNoise."""
+def _draw_noise_one(im, views):
+    """torch CPU-generator draws for ONE image in the order the reference makes them (cald_helper.py:74, 80): per noise
+    view torch.randn(image.size()) for GaussianNoise, torch.rand(image.size()) for SaltPepperNoise."""
     import torch
+    size = (3, im.shape[0], im.shape[1])
     planes = []
-    for im in images:
-        size = (3, im.shape[0], im.shape[1])
-        for kind, _ in views:
-            if kind == _eng.AUG_GAUSS:
-                planes.append(torch.randn(size).numpy())
-            elif kind == _eng.AUG_SALTPEPPER:
-                planes.append(torch.rand(size).numpy())
+    for kind, _ in views:
+        if kind == _eng.AUG_GAUSS:
+            planes.append(torch.randn(size).numpy())
+        elif kind == _eng.AUG_SALTPEPPER:
+            planes.append(torch.rand(size).numpy())
     return planes
 
 
-def score_images(eng, images, augs, chunk=64):
+def score_images(eng, images, augs, chunk=None):
     """Score u8 images with an existing engine.  Consumes python's global ``random`` stream exactly as
-    cald_helper.cutout would (4 uniforms per try, data-dependent number of tries) and torch's global CPU
-    generator exactly as GaussianNoise / SaltPepperNoise would."""
+    cald_helper.cutout / ColorSwap would (4 uniforms per cutout try, data-dependent number of tries; one randint per
+    swap view) and torch's global CPU generator exactly as GaussianNoise / SaltPepperNoise would.
+
+    The reference draws NOTHING for an image whose reference prediction is empty (it ``continue``s at
+    cald_train.py:118-121, before any augmentation is built).  Cutout draws are data dependent anyway and are resolved
+    on the device; the swap / noise draws are made optimistically here, before the forward pass, and when a chunk turns
+    out to contain an empty image both generators are rewound to where they stood before that image's draws and the
+    rest of the chunk is scored again -- so the streams always end where the reference leaves them."""
+    import torch
     views = _aug_kinds(augs)
     n_cut = sum(1 for k, _ in views if k == _eng.AUG_CUTOUT)
     n_swap = sum(1 for k, _ in views if k == _eng.AUG_COLOR_SWAP)
     has_noise = any(k in _eng.NOISE_KINDS for k, _ in views)
-    if n_swap and n_cut:
-        # ColorSwap's random.randint precedes the same image's cutout draws in python's RNG stream and the number of
-        # cutout draws is data dependent: keep the stream exact by scoring one image per call
+    if chunk is None:
+        chunk = 4 * eng.images_per_chunk(len(views))  # several engine passes per call: the upload pipeline overlaps them
+    if (n_swap or has_noise) and n_cut:
+        # swap / noise draws of an image precede the same image's data-dependent cutout draws in the reference's
+        # streams: keep both exact by scoring one image per call
         chunk = 1
+    speculative = bool(n_swap or has_noise) and len(views) > 0
     cons_all, cls_all = [], []
-    for pos in range(0, len(images), chunk):
+    pos = 0
+    while pos < len(images):
         batch = images[pos:pos + chunk]
-        # cald_helper.ColorSwap: perms[random.randint(0, len(perms) - 1)], one draw per (image, swap view)
-        swaps = [random.randint(0, 5) for _ in range(n_swap * len(batch))] if n_swap else None
+        marks, swaps, noise = [], [], []
+        for im in batch:
+            if speculative:
+                marks.append((random.getstate() if n_swap else None, torch.get_rng_state() if has_noise else None))
+            # cald_helper.ColorSwap: perms[random.randint(0, len(perms) - 1)], one draw per swap view
+            swaps += [random.randint(0, 5) for _ in range(n_swap)]
+            if has_noise:
+                noise += _draw_noise_one(im, views)
         u = None
         if n_cut:
             state = random.getstate()
             u = np.array([random.random() for _ in range(200 * n_cut * len(batch))], dtype=np.float64)
-        noise = _draw_noise(batch, views) if has_noise else None
-        cons, cls, used = eng.score(batch, views, bp, u, noise, swaps)
+        cons, cls, used = eng.score(batch, views, bp, u, noise if has_noise else None, swaps if n_swap else None)
         if n_cut:
             random.setstate(state)
             for _ in range(used):
                 random.random()
-        cons_all.extend(float(c) for c in cons)
-        cls_all.extend(np.array(r, dtype=np.float64) for r in cls)
+        good = len(batch)
+        if speculative:
+            ref_counts = eng.last_ref_counts(len(batch))
+            for i in range(len(batch)):
+                if ref_counts[i] == 0:
+                    py_state, torch_state = marks[i]
+                    if py_state is not None:
+                        random.setstate(py_state)
+                    if torch_state is not None:
+                        torch.set_rng_state(torch_state)
+                    good = i + 1  # the empty image's own result (0.0, zeros) does not depend on the draws
+                    break
+        cons_all.extend(float(c) for c in cons[:good])
+        cls_all.extend(np.array(r, dtype=np.float64) for r in cls[:good])
+        pos += good
     return cons_all, cls_all
+
+
+def _prefetched(iterable, depth):
+    """Iterate ``iterable`` in a background thread, ``depth`` items ahead (the C call releases the GIL, so the
+    DataLoader's collation / PIL decode of the next images overlaps the current scoring pass)."""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=max(1, depth))
+    end = object()
+
+    def work():
+        try:
+            for item in iterable:
+                q.put(item)
+            q.put(end)
+        except BaseException as ex:  # re-raised in the consumer
+            q.put(ex)
+    threading.Thread(target=work, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is end:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
 
 
 def get_uncertainty(task_model, unlabeled_loader, augs, num_cls, device=0, **engine_kw):
@@ -123,36 +200,58 @@ def get_uncertainty(task_model, unlabeled_loader, augs, num_cls, device=0, **eng
     unlabeled_loader yields ``(tuple_of_PIL_images, tuple_of_targets)`` with batch size 1
     (cald_train.py:370-371).  Returns ``(consistency_all, cls_all)``: list of float and list
     of float64 arrays of shape (num_cls - 1,), in loader order.
+
+    The loader is consumed as a stream, like the reference consumes it (cald_train.py:101): a group of a few engine
+    passes' worth of images is held in host memory at a time, never the pool, and the next group is pulled from the
+    loader while the current one is on the GPU.
     """
     eng = engine_for(task_model, num_cls, device, **engine_kw)
-    images = []
-    for imgs, _ in unlabeled_loader:
+    group = 4 * eng.images_per_chunk(max(1, len(_eng.expand_augs(augs))))
+    cons_all, cls_all, pending = [], [], []
+
+    def flush():
+        c, v = score_images(eng, pending, augs)
+        cons_all.extend(c)
+        cls_all.extend(v)
+        del pending[:]
+    for imgs, _ in _prefetched(unlabeled_loader, 2 * group):
         for image in imgs:
-            images.append(_to_u8(image))
-    return score_images(eng, images, augs)
+            pending.append(_to_u8(image))
+        if len(pending) >= group:
+            flush()
+    if pending:
+        flush()
+    return cons_all, cls_all
 
 
-def _loader_images(unlabeled_loader):
-    """Images of a reference-style loader (tuple_of_images, tuple_of_targets) as u8 HWC arrays.  The baseline scripts
-    feed ToTensor()'d float tensors (lt_c_train.py:109-111); those came from u8 pixels, so x * 255 is exact."""
-    out = []
-    for imgs, _ in unlabeled_loader:
+def _image_u8(image):
+    """One loader image as a u8 HWC array.  The baseline scripts feed ToTensor()'d float tensors
+    (lt_c_train.py:109-111); those came from u8 pixels, so x * 255 is exact."""
+    if hasattr(image, "detach"):  # torch CHW float in [0, 1]
+        a = image.detach().cpu().numpy()
+        return np.ascontiguousarray(np.rint(a * 255.0).astype(np.uint8).transpose(1, 2, 0))
+    return _to_u8(image)
+
+
+def _loader_groups(unlabeled_loader, group):
+    """Stream a reference-style loader (tuple_of_images, tuple_of_targets) as lists of ``group`` u8 images."""
+    pending = []
+    for imgs, _ in _prefetched(unlabeled_loader, 2 * group):
         for image in imgs:
-            if hasattr(image, "detach"):  # torch CHW float in [0, 1]
-                a = image.detach().cpu().numpy()
-                out.append(np.ascontiguousarray(np.rint(a * 255.0).astype(np.uint8).transpose(1, 2, 0)))
-            else:
-                out.append(_to_u8(image))
-    return out
+            pending.append(_image_u8(image))
+        if len(pending) >= group:
+            yield pending
+            pending = []
+    if pending:
+        yield pending
 
 
 def lt_c_uncertainty(task_model, unlabeled_loader, device=0, chunk=64, **engine_kw):
     """Drop-in for lt_c_train.get_uncertainty (lt_c_train.py:105-121): list of float, loader order."""
     eng = engine_for(task_model, _num_classes(task_model), device, **engine_kw)
-    images = _loader_images(unlabeled_loader)
     out = []
-    for pos in range(0, len(images), chunk):
-        out.extend(float(v) for v in eng.score_ltc(images[pos:pos + chunk]))
+    for batch in _loader_groups(unlabeled_loader, chunk):
+        out.extend(float(v) for v in eng.score_ltc(batch))
     return out
 
 
@@ -161,16 +260,27 @@ def ls_c_uncertainty(task_model, unlabeled_loader, aves=None, device=0, chunk=16
     torch.randn planes per image from torch's global CPU generator in the reference's order."""
     import torch
     eng = engine_for(task_model, _num_classes(task_model), device, **engine_kw)
-    images = _loader_images(unlabeled_loader)
     out = []
-    for pos in range(0, len(images), chunk):
-        batch = images[pos:pos + chunk]
-        noise = []
-        for im in batch:
-            # NOTE: the reference draws nothing for an image without reference detections (ls_c_train.py:118-120);
-            # the engine cannot know that before the forward, so the torch stream differs after such an image.
-            noise += [torch.randn((3, im.shape[0], im.shape[1])).numpy() for _ in range(6)]
-        out.extend(float(v) for v in eng.score_lsc(batch, noise))
+    for batch in _loader_groups(unlabeled_loader, chunk):
+        pos = 0
+        while pos < len(batch):
+            part = batch[pos:]
+            marks, noise = [], []
+            for im in part:
+                marks.append(torch.get_rng_state())
+                noise += [torch.randn((3, im.shape[0], im.shape[1])).numpy() for _ in range(6)]
+            vals = eng.score_lsc(part, noise)
+            good = len(part)
+            # the reference draws nothing for an image without reference detections (ls_c_train.py:118-120, before
+            # the noise loop): rewind the generator to before the first such image's draws and score the rest again
+            ref_counts = eng.last_ref_counts(len(part))
+            for i in range(len(part)):
+                if ref_counts[i] == 0:
+                    torch.set_rng_state(marks[i])
+                    good = i + 1
+                    break
+            out.extend(float(v) for v in vals[:good])
+            pos += good
     return out
 
 
@@ -181,6 +291,7 @@ class EngineModel:
     retinanet_cal.py:479-485, without 'features') as CPU torch tensors -- SURVEY.md 8(f) item 3."""
 
     def __init__(self, task_model, device=0, **engine_kw):
+        self.task_model, self.device, self.engine_kw = task_model, device, engine_kw
         self.engine = engine_for(task_model, _num_classes(task_model), device, **engine_kw)
 
     def eval(self):
@@ -188,13 +299,10 @@ class EngineModel:
 
     def __call__(self, images):
         import torch
-        u8 = []
-        for im in images:
-            if hasattr(im, "detach"):
-                a = im.detach().cpu().numpy()
-                u8.append(np.ascontiguousarray(np.rint(a * 255.0).astype(np.uint8).transpose(1, 2, 0)))
-            else:
-                u8.append(_to_u8(im))
+        # engines are shared per configuration and the model is retrained between evaluations: engine_for re-reads
+        # the weights whenever they differ from what the engine holds (fingerprint of the state_dict)
+        self.engine = engine_for(self.task_model, _num_classes(self.task_model), self.device, **self.engine_kw)
+        u8 = [_image_u8(im) for im in images]
         return [{k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in d.items()} for d in self.engine.detect(u8)]
 
 

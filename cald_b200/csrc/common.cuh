@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -21,45 +22,114 @@
 
 namespace cald {
 
-typedef __nv_bfloat16 bf16;
-
 // ---------------------------------------------------------------------------------
-// Split-bf16 activation format.  A real value v is stored as hi = bf16(v) and
-// lo = bf16(v - hi) in two planes; hi + lo carries 16 mantissa bits.  The tensor-core
-// path multiplies A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with fp32 accumulation in TMEM,
-// which is what keeps the detector's discrete stages (top-k / NMS / arg-max) on the
-// same side of their thresholds as the reference's fp32 CPU run.
+// Split 16-bit activation / weight format.  A real value v is stored as two 16-bit planes
+//   hi = rn16(v),  lo = rn16((v - hi) * LO_SCALE)            =>  v ~= hi + lo * LO_INV
+// and the tensor-core path multiplies A_hi*B_hi + (A_hi*B_lo + A_lo*B_hi) * LO_INV with fp32
+// accumulation in TMEM (the cross terms have their own accumulator columns, igemm.cuh XSEP),
+// which is what keeps the detector's discrete stages (top-k / NMS / arg-max) on the same side
+// of their thresholds as the reference's fp32 CPU run.
+//
+// Two element types, chosen at compile time (CALD_SPLIT_FP16):
+//   1 (default)  IEEE half planes, LO_SCALE = 2^11: 11 + 11 significand bits -- the operands carry 22-23 bits,
+//                i.e. fp32's own precision, at the same tcgen05 kind::f16 rate and the same 4 B / element.  The lo
+//                plane is pre-scaled so that it stays in half's normal range; conversions saturate at +-65504.
+//   0            bfloat16 planes, LO_SCALE = 1: 8 + 8 bits (round 1's format; kept for A/B measurements).
 // ---------------------------------------------------------------------------------
-__host__ __device__ inline void split_bf16(float v, bf16& hi, bf16& lo) {
-#ifdef __CUDA_ARCH__
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+#ifndef CALD_SPLIT_FP16
+#define CALD_SPLIT_FP16 1
+#endif
+#if CALD_SPLIT_FP16
+typedef __half pl16;
+#define CALD_LO_SCALE 2048.0f
+#define CALD_LO_INV (1.0f / 2048.0f)
 #else
-  hi = __float2bfloat16(v);
-  lo = __float2bfloat16(v - __bfloat162float(hi));
+typedef __nv_bfloat16 pl16;
+#define CALD_LO_SCALE 1.0f
+#define CALD_LO_INV 1.0f
+#endif
+// tcgen05 instruction-descriptor operand format field (a_format bits [7,10), b_format bits [10,13)): 0 = F16, 1 = BF16
+constexpr uint32_t PL16_MMA_FMT = CALD_SPLIT_FP16 ? 0u : 1u;
+
+__host__ __device__ inline float pl16_to_float(pl16 v) {
+#if CALD_SPLIT_FP16
+  return __half2float(v);
+#else
+  return pl16_to_float(v);
+#endif
+}
+__host__ __device__ inline pl16 float_to_pl16(float v) {
+#if CALD_SPLIT_FP16
+  // saturate instead of producing inf (an inf operand would turn a whole accumulator row into NaN)
+  v = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
+  return __float2half_rn(v);
+#else
+#ifdef __CUDA_ARCH__
+  return __float2bfloat16_rn(v);
+#else
+  return float_to_pl16(v);
+#endif
 #endif
 }
 
-__device__ __forceinline__ float join_bf16(bf16 hi, bf16 lo) {
-  return __bfloat162float(hi) + __bfloat162float(lo);
+__host__ __device__ inline void split_pl(float v, pl16& hi, pl16& lo) {
+  hi = float_to_pl16(v);
+  lo = float_to_pl16((v - pl16_to_float(hi)) * CALD_LO_SCALE);
 }
 
-// Two floats -> packed (hi plane, lo plane) bf16x2 words with 6 instructions (cvt.rn.bf16x2.f32 packs a pair).
-__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+__device__ __forceinline__ float join_pl(pl16 hi, pl16 lo) {
+  return fmaf(pl16_to_float(lo), CALD_LO_INV, pl16_to_float(hi));  // the scale is a power of two: exact product
+}
+
+#if CALD_SPLIT_FP16
+// two floats -> packed half2 word (first argument in the low half), saturating
+__device__ __forceinline__ uint32_t cvt_pack2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+  a = f.x; b = f.y;
+}
+#else
+__device__ __forceinline__ uint32_t cvt_pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
-  __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
-  lo = *reinterpret_cast<uint32_t*>(&l);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
-// packed bf16x2 (hi, lo planes) -> two floats
+__device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
+  a = __uint_as_float(w << 16);
+  b = __uint_as_float(w & 0xffff0000u);
+}
+#endif
+
+// Two floats -> packed (hi plane, lo plane) words
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_pack2(a, b);
+  float ha, hb;
+  unpack2(hi, ha, hb);
+#if CALD_SPLIT_FP16
+  lo = cvt_pack2((a - ha) * CALD_LO_SCALE, (b - hb) * CALD_LO_SCALE);
+#else
+  lo = cvt_pack2(a - ha, b - hb);
+#endif
+}
+// packed (hi, lo plane) words -> two floats
 __device__ __forceinline__ void join_pack2(uint32_t hi, uint32_t lo, float& a, float& b) {
-  a = __uint_as_float(hi << 16) + __uint_as_float(lo << 16);
-  b = __uint_as_float(hi & 0xffff0000u) + __uint_as_float(lo & 0xffff0000u);
+  float ha, hb, la, lb;
+  unpack2(hi, ha, hb);
+  unpack2(lo, la, lb);
+#if CALD_SPLIT_FP16
+  a = fmaf(la, CALD_LO_INV, ha);
+  b = fmaf(lb, CALD_LO_INV, hb);
+#else
+  a = ha + la;
+  b = hb + lb;
+#endif
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+__device__ __forceinline__ uint32_t pack_pl16x2(pl16 a, pl16 b) {
+  return (uint32_t)(*reinterpret_cast<unsigned short*>(&a)) | ((uint32_t)(*reinterpret_cast<unsigned short*>(&b)) << 16);
 }
 
 // ---------------------------------------------------------------------------------
@@ -87,16 +157,16 @@ struct ConvParams {
   const float* bias;   // [Cout] or null
   int relu;
   int res_mode;        // RES_*
-  const bf16* res_hi;
-  const bf16* res_lo;
+  const pl16* res_hi;
+  const pl16* res_lo;
   int res_H, res_W;    // for RES_NEAREST: source size
-  bf16* out_hi;        // null when only fp32 output is wanted
-  bf16* out_lo;        // null in bf16 (non-split) mode
+  pl16* out_hi;        // null when only fp32 output is wanted
+  pl16* out_lo;        // null in pl16 (non-split) mode
   float* out_f32;      // optional fp32 NHWC copy (heads)
   int ldc;             // channel stride of the output row (>= Cout)
   int res_ld;
   int kc;              // chunked accumulation: k-blocks per TMEM accumulation chunk
-  int tma_store;       // 1: epilogue stages 64-channel groups in smem and stores them with TMA (NHWC bf16 outputs)
+  int tma_store;       // 1: epilogue stages 64-channel groups in smem and stores them with TMA (NHWC pl16 outputs)
   int c_lo_img;        // image-index offset of the lo plane in the output tensor map
   int res_kb;          // residual-as-MMA: extra identity k-blocks per tile (BLOCK_N / 64), else 0
   int r_lo_img;        // image-index offset of the lo plane in the residual tensor map
@@ -110,6 +180,11 @@ struct ConvParams {
   float* head_part;
   int head_ld;
   long long head_rows;
+  // Round-toward-zero compensation.  tcgen05.mma adds into the fp32 TMEM accumulator with truncation, which shrinks
+  // the result by a relative beta per accumulate on average (measured); coherent over ~50
+  // layers that is the engine's largest deviation from an fp32 CPU run.  acc_gain = 1 + beta * (MMA instructions
+  // accumulated into one main accumulator) is applied to the main accumulator when the epilogue reads it.
+  float acc_gain;
 };
 
 // ATen nearest-neighbour source index (UpSampleKernel: nearest_idx), float scale.
@@ -146,15 +221,15 @@ __device__ __forceinline__ void epilogue_store8(const ConvParams& p, long long o
   }
   if (p.res_mode != RES_NONE) {
     uint4 rh = *reinterpret_cast<const uint4*>(p.res_hi + rrow + c);
-    const bf16* h = reinterpret_cast<const bf16*>(&rh);
+    const pl16* h = reinterpret_cast<const pl16*>(&rh);
     if (p.res_lo) {
       uint4 rl = *reinterpret_cast<const uint4*>(p.res_lo + rrow + c);
-      const bf16* l = reinterpret_cast<const bf16*>(&rl);
+      const pl16* l = reinterpret_cast<const pl16*>(&rl);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += join_bf16(h[i], l[i]);
+      for (int i = 0; i < 8; ++i) v[i] += join_pl(h[i], l[i]);
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += __bfloat162float(h[i]);
+      for (int i = 0; i < 8; ++i) v[i] += pl16_to_float(h[i]);
     }
   }
   if (p.relu) {
@@ -167,15 +242,15 @@ __device__ __forceinline__ void epilogue_store8(const ConvParams& p, long long o
     o[1] = make_float4(v[4], v[5], v[6], v[7]);
   }
   if (p.out_hi) {
-    bf16 h[8], l[8];
+    pl16 h[8], l[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
-    uint4 ph = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]),
-                          pack_bf16x2(h[6], h[7]));
+    for (int i = 0; i < 8; ++i) split_pl(v[i], h[i], l[i]);
+    uint4 ph = make_uint4(pack_pl16x2(h[0], h[1]), pack_pl16x2(h[2], h[3]), pack_pl16x2(h[4], h[5]),
+                          pack_pl16x2(h[6], h[7]));
     *reinterpret_cast<uint4*>(p.out_hi + orow + c) = ph;
     if (p.out_lo) {
-      uint4 pl = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]),
-                            pack_bf16x2(l[6], l[7]));
+      uint4 pl = make_uint4(pack_pl16x2(l[0], l[1]), pack_pl16x2(l[2], l[3]), pack_pl16x2(l[4], l[5]),
+                            pack_pl16x2(l[6], l[7]));
       *reinterpret_cast<uint4*>(p.out_lo + orow + c) = pl;
     }
   }

@@ -10,21 +10,25 @@
 #include "igemm.cuh"
 #include "igemm2.cuh"
 
+#ifndef CALD_RZ_BETA_DEFAULT
+#define CALD_RZ_BETA_DEFAULT 0.0
+#endif
+
 namespace cald {
 
-// ---- split-bf16 NHWC activation: planes [hi | lo], each [n][h][w][c]
+// ---- split-pl16 NHWC activation: planes [hi | lo], each [n][h][w][c]
 struct Act {
-  bf16* hi = nullptr;
+  pl16* hi = nullptr;
   int n = 0, h = 0, w = 0, c = 0;
   bool split = true;
   size_t plane_elems() const { return (size_t)n * h * w * c; }
-  bf16* lo() const { return split ? hi + plane_elems() : nullptr; }
-  size_t bytes() const { return plane_elems() * (split ? 2 : 1) * sizeof(bf16); }
+  pl16* lo() const { return split ? hi + plane_elems() : nullptr; }
+  size_t bytes() const { return plane_elems() * (split ? 2 : 1) * sizeof(pl16); }
 };
 
-// ---- conv / linear weights on device: [2][cout_pad][taps*cin] bf16 (BN already folded) + fp32 bias
+// ---- conv / linear weights on device: [2][cout_pad][taps*cin] pl16 (BN already folded) + fp32 bias
 struct ConvW {
-  bf16* w = nullptr;
+  pl16* w = nullptr;
   float* bias = nullptr;
   int cout = 0, cout_pad = 0, cin = 0, taps = 1;
   size_t plane_elems() const { return (size_t)cout_pad * taps * cin; }
@@ -35,7 +39,7 @@ struct ConvOpts {
   int stride = 1;               // 3x3: 1 or 2 (2: the A tensor map walks the full-resolution input with element stride 2)
   int res_mode = RES_NONE;
   const Act* res = nullptr;
-  float* out_f32 = nullptr;     // fp32 NHWC output instead of / in addition to split bf16
+  float* out_f32 = nullptr;     // fp32 NHWC output instead of / in addition to split pl16
   bool no_bf16_out = false;
   // stem mode: `in` is the padded space-to-depth image [n][Ho+3][Wo+3][16]; the 7x7/s2 conv is a 4x4/s1 conv whose
   // k-block `dy` is the 64-element window (4 pixels x 16 ch) starting at pixel (oy + dy, ox): an overlapping-stride
@@ -73,7 +77,7 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-// 4-D bf16 tensor map, innermost box = 64 elements (128 B) with 128B swizzle.
+// 4-D pl16 tensor map, innermost box = 64 elements (128 B) with 128B swizzle.
 inline CUtensorMap make_tmap(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint32_t b1,
                              uint32_t b2, uint32_t estride = 1) {
   CUtensorMap tm;
@@ -143,7 +147,7 @@ inline std::atomic<long long>& pair_launch_counter() {
 struct ConvEngine {
   int num_sms = 148;
   ConvImpl impl = CONV_TC;
-  bool split = true;       // false: single-pass bf16 (hi plane only)
+  bool split = true;       // false: single-pass pl16 (hi plane only)
   int force_block_n = 0;   // 0 = auto
   bool use_tma_store = true;  // false: always use the direct (per-thread) store epilogue
   bool use_res_mma = true;    // false: add residuals in the epilogue registers
@@ -153,6 +157,13 @@ struct ConvEngine {
   int resmma_max_kb = env_int("CALD_RESMMA_MAX_KB", 1 << 20);
   int cta2_min_kb = env_int("CALD_CTA2_MIN_KB", 16);
   int cta2_min_kb64 = env_int("CALD_CTA2_MIN_KB64", 9);
+  // relative shrink of the fp32 TMEM accumulator per truncating tcgen05.mma accumulate (ConvParams::acc_gain);
+  // CALD_RZ_BETA overrides the measured default
+  double rz_beta = env_double("CALD_RZ_BETA", CALD_RZ_BETA_DEFAULT);
+  static double env_double(const char* name, double dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atof(v) : dflt;
+  }
   static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -161,23 +172,24 @@ struct ConvEngine {
     const char* v = getenv(name);
     return v && *v ? (*v != '0') : dflt;
   }
-  bf16* ident[3] = {nullptr, nullptr, nullptr};  // identity B tiles for BLOCK_N = 64 / 128 / 256
+  pl16* ident[3] = {nullptr, nullptr, nullptr};  // identity B tiles for BLOCK_N = 64 / 128 / 256
   // I[j][n][k] = (n == j*64 + k): block j routes residual channels [j*64, j*64+64) to accumulator columns
-  const bf16* identity(int BN) {
+  const pl16* identity(int BN) {
     int slot = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
     if (!ident[slot]) {
-      std::vector<bf16> h((size_t)(BN / 64) * BN * 64);
+      std::vector<pl16> h((size_t)(BN / 64) * BN * 64);
       for (int j = 0; j < BN / 64; ++j)
         for (int n = 0; n < BN; ++n)
-          for (int k = 0; k < 64; ++k) h[((size_t)j * BN + n) * 64 + k] = __float2bfloat16(n == j * 64 + k ? 1.f : 0.f);
-      CALD_CUDA_CHECK(cudaMalloc((void**)&ident[slot], h.size() * sizeof(bf16)));
-      CALD_CUDA_CHECK(cudaMemcpy(ident[slot], h.data(), h.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+          for (int k = 0; k < 64; ++k) h[((size_t)j * BN + n) * 64 + k] = float_to_pl16(n == j * 64 + k ? 1.f : 0.f);
+      CALD_CUDA_CHECK(cudaMalloc((void**)&ident[slot], h.size() * sizeof(pl16)));
+      CALD_CUDA_CHECK(cudaMemcpy(ident[slot], h.data(), h.size() * sizeof(pl16), cudaMemcpyHostToDevice));
     }
     return ident[slot];
   }
-  int kc = 8;              // split mode: k-blocks (of 64) per accumulation chunk; 0 = never chunk
-  int chunk_above_kb = 40; // chunk only contractions longer than this many k-blocks (K > 2560): up to there the
-                           // cross-term-separated accumulator (igemm.cuh XSEP) is as accurate and faster
+  int kc = env_int("CALD_KC", 8);  // split mode: k-blocks (of 64) per accumulation chunk; 0 = never chunk
+  // chunk only contractions longer than this many k-blocks (K > 2560): up to there the cross-term-separated
+  // accumulator (igemm.cuh XSEP) with the truncation compensation (acc_gain) is as accurate and faster
+  int chunk_above_kb = env_int("CALD_CHUNK_ABOVE_KB", 40);
   long long launches = 0;  // kernels launched (bench's gpu_launches)
   double flops = 0;        // algorithmic 2*MAC of the launches
   // optional per-launch timing with CUDA events on the launching stream (bench.py roofline)
@@ -383,7 +395,7 @@ struct ConvEngine {
     else
       ta = make_tmap(in.hi, in.c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);
     tb = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, split ? 2 : 1, BN, 1);
-    // epilogue output path: TMA store for plain NHWC bf16 outputs whose channel count is a multiple of 64
+    // epilogue output path: TMA store for plain NHWC pl16 outputs whose channel count is a multiple of 64
     CUtensorMap tc = tb;
     p.tma_store = (!o.no_bf16_out && o.out_f32 == nullptr && (w.cout_pad % 64) == 0 &&
                    out.c == w.cout_pad && use_tma_store) ? 1 : 0;
@@ -433,6 +445,15 @@ struct ConvEngine {
     const int num_kb = w.taps * (w.cin / 64) + p.res_kb;
     const bool chunked = split && kc > 0 && num_kb > kc && num_kb > chunk_above_kb && BN <= 128;
     p.kc = chunked ? kc : num_kb;
+    if (CALD_SPLIT_FP16 && split && BN > 128)
+      throw std::runtime_error("conv: the scaled-lo half format needs the cross-term accumulator (BLOCK_N <= 128)");
+    {
+      // accumulates that can truncate the main accumulator of one output: 4 MMA k-steps per 64-wide k-block; an
+      // identity-routed residual block adds one non-zero term per column
+      const int real_kb = w.taps * (w.cin / 64) + (p.res_conv ? p.res_kb : 0);
+      const int adds = chunked ? kc * 4 : real_kb * 4 + ((p.res_kb && !p.res_conv) ? 1 : 0);
+      p.acc_gain = (float)(1.0 + rz_beta * (double)adds);
+    }
     // the pair kernel pays a cross-CTA handshake per tile: at BLOCK_N = 128 it wins from 16 k-blocks per tile up
     // (measured, +8..22 % on the 3x3 and K >= 1024 layers) and loses below 8 (the short-K layers are epilogue / HBM
     // bound).  BLOCK_N = 64: the layer1 3x3 convs gain 5 %; the stem (4 k-blocks) loses 12 % and stays on one CTA.
@@ -451,7 +472,7 @@ struct ConvEngine {
       p.head_rows = (long long)p.n_img * p.H * p.W;
     }
     if (profiling) {
-      // algorithmic HBM bytes: every operand element once at its stored width (activations 4 B split / 2 B bf16)
+      // algorithmic HBM bytes: every operand element once at its stored width (activations 4 B split / 2 B pl16)
       const double eb = split ? 4.0 : 2.0;
       const double pix = (double)p.n_img * p.H * p.W;
       double by = pix * (o.stem_window ? 16.0 : (double)w.cin) * eb * (o.stride == 2 ? 1.0 : 1.0) +

@@ -361,11 +361,11 @@ __global__ void __launch_bounds__(1024) rpn_merge_kernel(const float4* __restric
 }
 
 // ---------------------------------------------------------------- multi-scale RoIAlign (7x7, sampling 2, aligned=False)
-// Features: 4 pyramid levels, split-bf16 NHWC [V][h][w][C].  Output rows [V*cap][49][C] split bf16 (the K-major A
+// Features: 4 pyramid levels, split-pl16 NHWC [V][h][w][C].  Output rows [V*cap][49][C] split pl16 (the K-major A
 // operand of fc6, weight columns permuted to (ph, pw, c) at load time).  One CTA per RoI, one warp per bin, 8 ch/lane.
 struct RoiFeats {
-  const bf16* hi[4];
-  const bf16* lo[4];
+  const pl16* hi[4];
+  const pl16* lo[4];
   int h[4], w[4];
   float scale[4];
   int C;
@@ -384,12 +384,12 @@ __device__ __forceinline__ void bilinear_prep(float v, int size, int& lo, int& h
 // 7 warps: each owns exactly 7 of the 49 bins.
 // FUSED: the four weighted taps of a sample are accumulated with FFMA (4 instructions per value instead of the 4 FMUL +
 // 4 FADD of the unfused ATen expression; the kernel is instruction-bound).  The difference to the unfused form is a few
-// 2^-24 relative, two orders below the 2^-17 rounding of the split-bf16 features the taps are read from.
+// 2^-24 relative, two orders below the 2^-17 rounding of the split-pl16 features the taps are read from.
 constexpr int ROI_THREADS = 224;
 template <bool FUSED>
 __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiFeats F, const float4* __restrict__ props,
                                                                const int* __restrict__ prop_count, int cap,
-                                                               bf16* __restrict__ ohi, bf16* __restrict__ olo) {
+                                                               pl16* __restrict__ ohi, pl16* __restrict__ olo) {
   __shared__ int s_lo[2][14], s_hi[2][14], s_bad[2][14];   // element offsets of the low / high row (dim 0) or column (dim 1)
   __shared__ float s_l[2][14], s_h[2][14];
   const int v = blockIdx.y, r = blockIdx.x;
@@ -421,8 +421,8 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiFeats F, const
     s_lo[dim][k] = lo * pitch; s_hi[dim][k] = hi * pitch; s_l[dim][k] = l; s_h[dim][k] = h; s_bad[dim][k] = bad ? 1 : 0;
   }
   __syncthreads();
-  const bf16* fhi = F.hi[lv] + (long long)v * H * W * C + lane * 8;
-  const bf16* flo = F.lo[lv] ? F.lo[lv] + (long long)v * H * W * C + lane * 8 : nullptr;
+  const pl16* fhi = F.hi[lv] + (long long)v * H * W * C + lane * 8;
+  const pl16* flo = F.lo[lv] ? F.lo[lv] + (long long)v * H * W * C + lane * 8 : nullptr;
   for (int bin = warp; bin < 49; bin += ROI_THREADS / 32) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (live) {
@@ -453,10 +453,7 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiFeats F, const
               for (int q = 0; q < 4; ++q) join_pack2(pa[q], pb2[q], dst[2 * q], dst[2 * q + 1]);
             } else {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                dst[2 * q] = __uint_as_float(pa[q] << 16);
-                dst[2 * q + 1] = __uint_as_float(pa[q] & 0xffff0000u);
-              }
+              for (int q = 0; q < 4; ++q) unpack2(pa[q], dst[2 * q], dst[2 * q + 1]);
             }
           };
           ld(o1, v1); ld(o2, v2); ld(o3, v3); ld(o4, v4);

@@ -6,6 +6,7 @@
 #include <memory>
 #include <chrono>
 #include <cstdlib>
+#include <functional>
 #include "layers.cuh"
 #include "det.cuh"
 #include "pre.cuh"
@@ -80,7 +81,15 @@ struct cald_engine {
   std::map<long long, std::pair<int*, int*>> pil_cache;  // (in,out,filter) -> device bounds, kk
   std::map<long long, int> pil_ksize;
   std::vector<float> last_per_view;
+  std::vector<int> last_ref_counts;  // detections of every image's reference view in the last scoring call
   int last_A = 0;
+  // debug = 1: detections of every view of the last scoring call, ragged, (image, [reference, aug 0, aug 1, ...]) order
+  struct DbgViews {
+    std::vector<int> counts;
+    std::vector<float> boxes, scores, prob_max;
+    std::vector<int> labels;
+    void clear() { counts.clear(); boxes.clear(); scores.clear(); prob_max.clear(); labels.clear(); }
+  } dbg_views;
   cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // CALD_TRACE=1: host timestamp + CUDA event at named points of a scoring call, printed at the end of the call
   struct TracePt { const char* name; double host_us; cudaEvent_t ev; };
@@ -109,8 +118,15 @@ struct cald_engine {
     fprintf(stderr, "\n");
     trace_pts.clear();
   }
-  uint8_t* pinned = nullptr;   // staging for pageable caller buffers (H2D from pinned memory runs at link speed)
-  size_t pinned_cap = 0;
+  // Image upload pipeline: chunk i+1's u8 images travel host -> device on `copy_st` while chunk i computes on `st`.
+  // Pageable caller buffers are first gathered into one of two page-locked staging buffers (one CPU memcpy, then a
+  // single link-speed DMA instead of n driver-staged pageable copies).
+  cudaStream_t copy_st = nullptr;
+  uint8_t* pinned[2] = {nullptr, nullptr};
+  size_t pinned_cap[2] = {0, 0};
+  cudaEvent_t pinned_free[2] = {nullptr, nullptr};  // the DMA out of staging buffer k has completed
+  cudaEvent_t upload_done[2] = {nullptr, nullptr};  // device slab k holds its chunk
+  int views_per_pass = 8;      // resolved cfg.max_views_per_pass (0 = sized from the arena, cald_create)
 
   // device copies of the detector's weights (re-uploaded by every cald_load_weights: the AL cycle retrains the model)
   void free_weights() {
@@ -132,7 +148,12 @@ struct cald_engine {
   }
   ~cald_engine() {
     if (d_lut) cudaFree(d_lut);
-    if (pinned) cudaFreeHost(pinned);
+    for (int k = 0; k < 2; ++k) {
+      if (pinned[k]) cudaFreeHost(pinned[k]);
+      if (pinned_free[k]) cudaEventDestroy(pinned_free[k]);
+      if (upload_done[k]) cudaEventDestroy(upload_done[k]);
+    }
+    if (copy_st) cudaStreamDestroy(copy_st);
     for (auto& kv : pil_cache) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
     free_weights();
     if (d_overflow) cudaFree(d_overflow);
@@ -787,10 +808,9 @@ void forward_pass_retina(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* 
     kept.anchor = (int*)ar.alloc((size_t)V * K * pc * 4);
     kept.count = (int*)ar.alloc((size_t)V * K * 4);
     CALD_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)V * K * 4, st));
-    ret_candidates_kernel<<<dim3(e->conv.num_sms * 8, V), 256, 0, st>>>(L, e->cfg.box_score_thresh, keys, counts,
-                                                                        e->d_overflow);
-    ret_class_nms_kernel<<<dim3(K, V), 1024, RET_NMS_SMEM, st>>>(L, keys, counts, d_image_hw, 1e-2f,
-                                                                 (double)e->cfg.box_nms_thresh, pc, kept);
+    ret_candidates_kernel<<<dim3(e->conv.num_sms * 8, V), 256, 0, st>>>(L, e->cfg.box_score_thresh, keys, counts);
+    ret_class_nms_kernel<<<dim3(K, V), 1024, RET_NMS_SMEM, st>>>(L, keys, counts, d_image_hw, e->cfg.box_score_thresh,
+                                                                 1e-2f, (double)e->cfg.box_nms_thresh, pc, kept);
     ret_gather_kernel<<<V, 1024, (K + 1) * 4, st>>>(L, kept, pc, d_ratio, e->det_cap, vs.det, vs.scores, e->d_overflow);
     CALD_CUDA_CHECK(cudaGetLastError());
     e->launches += 3;
@@ -831,7 +851,8 @@ struct HostView {
   int cut_slot;
   const float* noise = nullptr;  // device planes [3][sh][sw]
   int noise_mode = 0;
-  float n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+  float n0 = 0, n1 = 0;
+  const int* mm = nullptr;       // device [2]: min / max of the source image (salt / pepper values)
   int perm = PERM_IDENTITY;
 };
 
@@ -842,6 +863,7 @@ void resized_hw(const cald_config& c, int h, int w, int& rh, int& rw) {
   rw = (int)std::floor((double)w * s);
 }
 inline int pad32(int v) { return (int)(std::ceil((double)v / 32.0) * 32.0); }
+constexpr double ARENA_BYTES_PER_PIXEL = 420.0;
 
 // Run the detector over `views` (any mix of sizes): group by padded shape, forward each group, results in view order.
 void detect_views(cald_engine* e, const std::vector<HostView>& views, const CutRects* d_cuts, ViewSet& out) {
@@ -853,8 +875,7 @@ void detect_views(cald_engine* e, const std::vector<HostView>& views, const CutR
     int rh, rw;
     resized_hw(e->cfg, views[i].sh, views[i].sw, rh, rw);
     vd[i] = ViewDesc{views[i].src, views[i].sh, views[i].sw, rh, rw, views[i].flip, views[i].cut_slot,
-                     views[i].noise, views[i].noise_mode, views[i].n0, views[i].n1, views[i].n2, views[i].n3,
-                     views[i].perm};
+                     views[i].noise, views[i].noise_mode, views[i].n0, views[i].n1, views[i].mm, views[i].perm};
     hw[i * 2] = rh; hw[i * 2 + 1] = rw;
     if (e->retina) {  // tv:transform.py:306-311: fp32 tensors divided in fp32
       ratio[i * 2] = (float)views[i].sh / (float)rh;
@@ -873,7 +894,7 @@ void detect_views(cald_engine* e, const std::vector<HostView>& views, const CutR
   });
   Arena& ar = e->arena;
   cudaStream_t st = e->st;
-  const int maxv = e->cfg.max_views_per_pass > 0 ? e->cfg.max_views_per_pass : 8;
+  const int maxv = e->views_per_pass;
   int pos = 0;
   while (pos < V) {
     int end = pos + 1;
@@ -1013,6 +1034,15 @@ uint8_t* pil_resize_device(cald_engine* e, const uint8_t* src, int h, int w, int
     long long key = ((long long)in << 34) | ((long long)out << 4) | filter;
     auto it = e->pil_cache.find(key);
     if (it == e->pil_cache.end()) {
+      // a real pool has thousands of distinct image sizes: keep at most PIL_CACHE_MAX coefficient tables.  Tables
+      // may still be read by enqueued kernels, so the cache is only flushed after the stream has drained.
+      constexpr size_t PIL_CACHE_MAX = 256;
+      if (e->pil_cache.size() >= PIL_CACHE_MAX) {
+        CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (auto& kv : e->pil_cache) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+        e->pil_cache.clear();
+        e->pil_ksize.clear();
+      }
       PilCoeffs pc = pil_precompute(in, out, filter);
       int *b, *k;
       CALD_CUDA_CHECK(cudaMalloc((void**)&b, pc.bounds.size() * 4));
@@ -1069,7 +1099,12 @@ void rotate_box_geom(int w, int h, double angle_deg, int rot_w, int rot_h, AugGe
 }
 
 // min / max of a device u8 image as to_tensor values (salt / pepper of cald_helper.py:81-82)
-__global__ void u8_minmax_kernel(const uint8_t* __restrict__ img, long long n, int* __restrict__ out /*[2] min,max*/) {
+// grid = (blocks, B): one launch for the whole chunk; out[b] = {min, max}, pre-set to {255, 0}
+__global__ void u8_minmax_kernel(const ViewDesc* __restrict__ imgs, int* __restrict__ out_all) {
+  const ViewDesc d = imgs[blockIdx.y];
+  const uint8_t* img = d.src;
+  const long long n = (long long)d.sh * d.sw * 3;
+  int* out = out_all + blockIdx.y * 2;
   int lo = 255, hi = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int v = img[i];
@@ -1087,7 +1122,8 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
                  const std::vector<cald_aug>& augs, double bp, const double* d_u, int n_u, int* d_cursor,
                  const float* const* d_noise /* [B][n_noise] device planes */,
                  const int* swap_perms /* [B][n_swap] host, or null */, double* out_cons, double* out_cls,
-                 int scorer = 0 /* 0: CALD consistency, 1: LS+C stability (ls_c_train.py:108-155) */) {
+                 int scorer = 0 /* 0: CALD consistency, 1: LS+C stability (ls_c_train.py:108-155) */,
+                 const std::function<void()>& before_wait = nullptr /* runs once everything is enqueued */) {
   Arena& ar = e->arena;
   cudaStream_t st = e->st;
   const int A = (int)augs.size();
@@ -1134,22 +1170,27 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
     KLAUNCH(e);
     ar.free(d_cn);
   }
-  // salt / pepper values need each image's min / max
-  std::vector<int> h_mm(B * 2, 0);
+  // salt / pepper values need each image's min / max: one launch for the chunk, the values stay on the device
+  // (the stem-input kernel reads them through ViewDesc::mm), so there is no host round trip
   bool has_sp = false;
   for (const cald_aug& a : augs) has_sp |= (a.kind == CALD_AUG_SALTPEPPER);
+  int* d_mm = nullptr;
   if (has_sp) {
-    int* d_mm = (int*)ar.alloc(B * 8);
+    d_mm = (int*)ar.alloc(B * 8);
     std::vector<int> init(B * 2);
-    for (int b = 0; b < B; ++b) { init[b * 2] = 255; init[b * 2 + 1] = 0; }
-    CALD_CUDA_CHECK(cudaMemcpyAsync(d_mm, init.data(), B * 8, cudaMemcpyHostToDevice, st));
+    std::vector<ViewDesc> srcs(B);
     for (int b = 0; b < B; ++b) {
-      u8_minmax_kernel<<<64, 256, 0, st>>>(d_images[b], (long long)hs[b] * ws[b] * 3, d_mm + b * 2);
-      KLAUNCH(e);
+      init[b * 2] = 255; init[b * 2 + 1] = 0;
+      memset(&srcs[b], 0, sizeof(ViewDesc));
+      srcs[b].src = d_images[b]; srcs[b].sh = hs[b]; srcs[b].sw = ws[b];
     }
-    CALD_CUDA_CHECK(cudaMemcpyAsync(h_mm.data(), d_mm, B * 8, cudaMemcpyDeviceToHost, st));
-    CALD_CUDA_CHECK(cudaStreamSynchronize(st));
-    ar.free(d_mm);
+    ViewDesc* d_srcs = (ViewDesc*)ar.alloc(B * sizeof(ViewDesc));
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d_mm, init.data(), B * 8, cudaMemcpyHostToDevice, st));
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d_srcs, srcs.data(), B * sizeof(ViewDesc), cudaMemcpyHostToDevice, st));
+    u8_minmax_kernel<<<dim3(64, B), 256, 0, st>>>(d_srcs, d_mm);
+    CALD_CUDA_CHECK(cudaGetLastError());
+    KLAUNCH(e);
+    ar.free(d_srcs);  // stream-ordered reuse
   }
   // ---------------- augmented views
   std::vector<HostView> av((size_t)B * A);
@@ -1200,8 +1241,7 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
             hv.noise_mode = 2;
             hv.n0 = (float)(prm / 2.0);
             hv.n1 = (float)(1.0 - prm / 2.0);
-            hv.n2 = (float)h_mm[b * 2 + 1] / 255.0f;  // salt = max(image)
-            hv.n3 = (float)h_mm[b * 2] / 255.0f;      // pepper = min(image)
+            hv.mm = d_mm + b * 2;
           }
           break;
         }
@@ -1263,7 +1303,11 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
       CALD_CUDA_CHECK(cudaGetLastError());
       e->launches += 3;
       CALD_CUDA_CHECK(cudaMemcpyAsync(out_cons, d_out, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+      std::vector<int> h_rc(B);
+      CALD_CUDA_CHECK(cudaMemcpyAsync(h_rc.data(), ref.det.count, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+      if (before_wait) before_wait();
       CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+      e->last_ref_counts.insert(e->last_ref_counts.end(), h_rc.begin(), h_rc.end());
       check_overflow(e);
       ar.free(keys); ar.free(top); ar.free(top_count); ar.free(d_out);
     } else {
@@ -1287,9 +1331,11 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
     if (A > 0) CALD_CUDA_CHECK(cudaMemcpyAsync(h_cons.data(), d_cons, (size_t)B * A * 4, cudaMemcpyDeviceToHost, st));
     CALD_CUDA_CHECK(cudaMemcpyAsync(h_cls.data(), d_cls, h_cls.size() * 4, cudaMemcpyDeviceToHost, st));
     CALD_CUDA_CHECK(cudaMemcpyAsync(h_ndet.data(), rs.n_det, B * 4, cudaMemcpyDeviceToHost, st));
+    if (before_wait) before_wait();
     CALD_CUDA_CHECK(cudaStreamSynchronize(st));
     check_overflow(e);
     e->trace("results_on_host");
+    e->last_ref_counts.insert(e->last_ref_counts.end(), h_ndet.begin(), h_ndet.end());
     for (int b = 0; b < B; ++b) {
       double* cls = out_cls + (size_t)b * ncls1;
       if (h_ndet[b] == 0 || A == 0) {
@@ -1310,71 +1356,126 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
       }
     }
   }
+  if (e->cfg.debug && scorer == 0) {
+    auto fetch = [&](const ViewSet& vs, int V, std::vector<int>& cnt, std::vector<float>& bx, std::vector<float>& sc,
+                     std::vector<float>& pm, std::vector<int>& lb) {
+      cnt.resize(V); bx.resize((size_t)V * dc * 4); sc.resize((size_t)V * dc); pm.resize((size_t)V * dc); lb.resize((size_t)V * dc);
+      CALD_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), vs.det.count, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
+      CALD_CUDA_CHECK(cudaMemcpyAsync(bx.data(), vs.det.boxes, bx.size() * 4, cudaMemcpyDeviceToHost, st));
+      CALD_CUDA_CHECK(cudaMemcpyAsync(sc.data(), vs.det.scores, sc.size() * 4, cudaMemcpyDeviceToHost, st));
+      CALD_CUDA_CHECK(cudaMemcpyAsync(pm.data(), vs.det.prob_max, pm.size() * 4, cudaMemcpyDeviceToHost, st));
+      CALD_CUDA_CHECK(cudaMemcpyAsync(lb.data(), vs.det.labels, lb.size() * 4, cudaMemcpyDeviceToHost, st));
+      CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+    };
+    std::vector<int> rc, ac, rl, al;
+    std::vector<float> rb, rsc, rpm, ab, asc, apm;
+    fetch(ref, B, rc, rb, rsc, rpm, rl);
+    if (A > 0) fetch(aug, B * A, ac, ab, asc, apm, al);
+    auto push = [&](int v, const std::vector<int>& cnt, const std::vector<float>& bx, const std::vector<float>& sc,
+                    const std::vector<float>& pm, const std::vector<int>& lb) {
+      const int n = cnt[v];
+      e->dbg_views.counts.push_back(n);
+      e->dbg_views.boxes.insert(e->dbg_views.boxes.end(), bx.begin() + (size_t)v * dc * 4, bx.begin() + ((size_t)v * dc + n) * 4);
+      e->dbg_views.scores.insert(e->dbg_views.scores.end(), sc.begin() + (size_t)v * dc, sc.begin() + (size_t)v * dc + n);
+      e->dbg_views.prob_max.insert(e->dbg_views.prob_max.end(), pm.begin() + (size_t)v * dc, pm.begin() + (size_t)v * dc + n);
+      e->dbg_views.labels.insert(e->dbg_views.labels.end(), lb.begin() + (size_t)v * dc, lb.begin() + (size_t)v * dc + n);
+    };
+    for (int b = 0; b < B; ++b) {
+      push(b, rc, rb, rsc, rpm, rl);
+      for (int a = 0; a < A; ++a) push(b * A + a, ac, ab, asc, apm, al);
+    }
+  }
   if (A > 0) { free_viewset(e, aug); if (d_cons) ar.free(d_cons); }
   for (uint8_t* t : temps) ar.free(t);
+  if (d_mm) ar.free(d_mm);
   ar.free(d_img_hw); ar.free(d_cuts); ar.free(d_cls);
   ar.free(rs.n); ar.free(rs.n_det); ar.free(rs.boxes); ar.free(rs.prob_max); ar.free(rs.prop_idx);
   free_viewset(e, ref);
 }
 
-// upload host images into one device slab; returns device pointers
+// ------------------------------------------------------------------------------------------------------------
+// Image upload pipeline.  A call's images are scored in chunks; chunk i+1 is copied host -> device on the engine's copy
+// stream into the other of two fixed device slabs while chunk i computes, so the H2D time disappears behind the
+// forward passes.  Caller buffers that are page-locked are DMA'd in place; pageable ones are gathered into a
+// page-locked staging buffer first (one CPU memcpy, then a single link-speed DMA).
+// ------------------------------------------------------------------------------------------------------------
 struct DeviceImages {
-  uint8_t* slab = nullptr;
   std::vector<const uint8_t*> ptr;
 };
-DeviceImages upload_images(cald_engine* e, int n, const uint8_t* const* images, const int* hs, const int* ws) {
-  DeviceImages d;
-  size_t total = 0;
-  std::vector<size_t> off(n);
-  for (int i = 0; i < n; ++i) { off[i] = total; total += ((size_t)hs[i] * ws[i] * 3 + 255) & ~(size_t)255; }
-  d.slab = (uint8_t*)e->arena.alloc(total);
-  d.ptr.resize(n);
-  // caller buffers that are not page-locked are gathered into the engine's pinned slab first: one CPU memcpy, then
-  // a single link-speed DMA instead of n driver-staged pageable copies
-  static const bool trace = getenv("CALD_TRACE_UPLOAD") != nullptr;
-  auto now = [] { return std::chrono::steady_clock::now(); };
-  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-    return std::chrono::duration<double, std::micro>(b - a).count();
-  };
-  auto t0 = now();
+struct UploadPipe {
+  cald_engine* e;
+  int n_images, per_chunk;
+  const uint8_t* const* imgs;
+  const int* hs;
+  const int* ws;
+  uint8_t* slab[2] = {nullptr, nullptr};
+  size_t slab_bytes = 0;
   bool all_pinned = true;
-  for (int i = 0; i < n && all_pinned; ++i) {
-    cudaPointerAttributes at;
-    cudaError_t ce = cudaPointerGetAttributes(&at, images[i]);
-    if (ce != cudaSuccess) { cudaGetLastError(); all_pinned = false; break; }
-    all_pinned = (at.type == cudaMemoryTypeHost);
-    if (trace && !all_pinned) fprintf(stderr, "[upload] image %d: cudaPointerGetAttributes type %d\n", i, (int)at.type);
-  }
-  auto t1 = now();
-  if (all_pinned) {
-    for (int i = 0; i < n; ++i)
-      CALD_CUDA_CHECK(cudaMemcpyAsync(d.slab + off[i], images[i], (size_t)hs[i] * ws[i] * 3, cudaMemcpyHostToDevice, e->st));
-    if (trace) {
-      auto t2 = now();
-      CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
-      fprintf(stderr, "[upload] pinned: attr %.0f us, %d copies enqueued in %.0f us, complete after %.0f us\n", us(t0, t1), n,
-              us(t1, t2), us(t1, now()));
+  int started = 0;  // chunks whose copy has been enqueued
+
+  static size_t padded(int h, int w) { return ((size_t)h * w * 3 + 255) & ~(size_t)255; }
+  int n_chunks() const { return (n_images + per_chunk - 1) / per_chunk; }
+
+  // Both slabs are taken from the arena before anything else of the call and live until its end: arena blocks freed
+  // and re-used during the call are only ordered on the compute stream, never against the copy stream.
+  UploadPipe(cald_engine* eng, int n, const uint8_t* const* images, const int* heights, const int* widths, int chunk)
+      : e(eng), n_images(n), per_chunk(std::max(1, chunk)), imgs(images), hs(heights), ws(widths) {
+    for (int c = 0; c < n_chunks(); ++c) {
+      size_t b = 0;
+      for (int i = c * per_chunk; i < std::min(n, (c + 1) * per_chunk); ++i) b += padded(hs[i], ws[i]);
+      slab_bytes = std::max(slab_bytes, b);
     }
-  } else {
-    if (e->pinned_cap < total) {
-      CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
-      if (e->pinned) cudaFreeHost(e->pinned);
-      CALD_CUDA_CHECK(cudaMallocHost((void**)&e->pinned, total));
-      e->pinned_cap = total;
+    for (int i = 0; i < n && all_pinned; ++i) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, imgs[i]) != cudaSuccess) { cudaGetLastError(); all_pinned = false; break; }
+      all_pinned = (at.type == cudaMemoryTypeHost);
+    }
+    if (n > 0) {
+      slab[0] = (uint8_t*)e->arena.alloc(slab_bytes);
+      if (n_chunks() > 1) slab[1] = (uint8_t*)e->arena.alloc(slab_bytes);
+    }
+  }
+  // enqueue the copy of chunk c (no-op if already started or out of range)
+  void start(int c) {
+    if (c != started || c >= n_chunks()) return;
+    const int k = c & 1, i0 = c * per_chunk, i1 = std::min(n_images, i0 + per_chunk);
+    if (all_pinned) {
+      size_t off = 0;
+      for (int i = i0; i < i1; ++i) {
+        CALD_CUDA_CHECK(cudaMemcpyAsync(slab[k] + off, imgs[i], (size_t)hs[i] * ws[i] * 3, cudaMemcpyHostToDevice, e->copy_st));
+        off += padded(hs[i], ws[i]);
+      }
     } else {
-      CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));  // the previous upload must have left the slab
+      if (e->pinned_cap[k] < slab_bytes) {
+        CALD_CUDA_CHECK(cudaEventSynchronize(e->pinned_free[k]));
+        if (e->pinned[k]) cudaFreeHost(e->pinned[k]);
+        e->pinned[k] = nullptr;
+        CALD_CUDA_CHECK(cudaMallocHost((void**)&e->pinned[k], slab_bytes));
+        e->pinned_cap[k] = slab_bytes;
+      }
+      CALD_CUDA_CHECK(cudaEventSynchronize(e->pinned_free[k]));  // the previous DMA out of this staging buffer
+      size_t off = 0;
+      for (int i = i0; i < i1; ++i) {
+        memcpy(e->pinned[k] + off, imgs[i], (size_t)hs[i] * ws[i] * 3);
+        off += padded(hs[i], ws[i]);
+      }
+      CALD_CUDA_CHECK(cudaMemcpyAsync(slab[k], e->pinned[k], off, cudaMemcpyHostToDevice, e->copy_st));
+      CALD_CUDA_CHECK(cudaEventRecord(e->pinned_free[k], e->copy_st));
     }
-    auto t2 = now();
-    for (int i = 0; i < n; ++i) memcpy(e->pinned + off[i], images[i], (size_t)hs[i] * ws[i] * 3);
-    auto t3 = now();
-    CALD_CUDA_CHECK(cudaMemcpyAsync(d.slab, e->pinned, total, cudaMemcpyHostToDevice, e->st));
-    if (trace)
-      fprintf(stderr, "[upload] staged: attr %.0f us, sync %.0f us, memcpy %.0f us, enqueue %.0f us\n", us(t0, t1), us(t1, t2),
-              us(t2, t3), us(t3, now()));
+    CALD_CUDA_CHECK(cudaEventRecord(e->upload_done[k], e->copy_st));
+    started = c + 1;
   }
-  for (int i = 0; i < n; ++i) d.ptr[i] = d.slab + off[i];
-  return d;
-}
+  // device pointers of chunk c; the compute stream waits for its copy
+  DeviceImages get(int c) {
+    start(c);
+    const int k = c & 1, i0 = c * per_chunk, i1 = std::min(n_images, i0 + per_chunk);
+    CALD_CUDA_CHECK(cudaStreamWaitEvent(e->st, e->upload_done[k], 0));
+    DeviceImages d;
+    size_t off = 0;
+    for (int i = i0; i < i1; ++i) { d.ptr.push_back(slab[k] + off); off += padded(hs[i], ws[i]); }
+    return d;
+  }
+};
 
 // RetinaNet capacities are fixed; a pool image that exceeds them must fail the call, not be scored differently
 void check_overflow(cald_engine* e) {
@@ -1384,8 +1485,8 @@ void check_overflow(cald_engine* e) {
   CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
   if (flag) {
     CALD_CUDA_CHECK(cudaMemsetAsync(e->d_overflow, 0, 4, e->st));
-    throw std::runtime_error(flag == 1 ? "RetinaNet: more than 4096 candidates above the score threshold in one class"
-                                       : "RetinaNet: more detections in one image than retina_max_detections");
+    throw std::runtime_error("RetinaNet: more detections in one image than retina_max_detections (the default, "
+                             "300 * num_classes, cannot overflow)");
   }
 }
 
@@ -1416,7 +1517,8 @@ int cald_config_default(cald_config* cfg, int arch, int depth, int num_classes, 
   cfg->rpn_pre_nms_top_n = 1000; cfg->rpn_post_nms_top_n = 1000; cfg->rpn_nms_thresh = 0.7f;
   cfg->box_score_thresh = 0.05f; cfg->box_nms_thresh = 0.5f; cfg->box_detections_per_img = 100;
   if (arch == CALD_ARCH_RETINANET) cfg->box_detections_per_img = 300;  /* per class, retinanet_cal.py:333,463 */
-  cfg->retina_max_detections = 16384;
+  /* the reference keeps up to 300 detections per class (retinanet_cal.py:333, 463): 300 * K rows can never overflow */
+  cfg->retina_max_detections = std::min(32768, 300 * num_classes);
   cfg->device = 0; cfg->precision = CALD_PREC_BF16X3; cfg->conv_impl = CALD_CONV_TCGEN05;
   cfg->max_views_per_pass = 0; cfg->workspace_bytes = 0; cfg->debug = 0;
   return 0;
@@ -1471,6 +1573,23 @@ int cald_create(const cald_config* cfg, cald_engine** out) {
       ws = std::min<size_t>(fr / 2, (size_t)64 << 30);
     }
     e->arena.init(ws);
+    CALD_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_st, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CALD_CUDA_CHECK(cudaEventCreateWithFlags(&e->pinned_free[k], cudaEventDisableTiming));
+      CALD_CUDA_CHECK(cudaEventCreateWithFlags(&e->upload_done[k], cudaEventDisableTiming));
+    }
+    if (cfg->max_views_per_pass > 0) {
+      e->views_per_pass = cfg->max_views_per_pass;
+    } else {
+      // auto: as many views as the arena holds at the detector's largest padded input, up to 64 (= 16 images with
+      // four augmentations; larger passes measured no faster).  Peak arena use per view is ~ARENA_BYTES_PER_PIXEL of
+      // the padded input (measured with cald_arena_peak: activations of the widest point of the pass + RoI features
+      // + per-view result buffers); two chunk-sized image slabs come on top.
+      const double per_view = (double)pad32(cfg->min_size) * (double)pad32(cfg->max_size) * ARENA_BYTES_PER_PIXEL +
+                              (retina ? (double)e->det_cap * (cfg->num_classes + 16) * 4.0 : 8.0e6);
+      const double fit = 0.85 * (double)ws / per_view;
+      e->views_per_pass = (int)std::max(4.0, std::min(64.0, std::floor(fit)));
+    }
     CALD_CUDA_CHECK(cudaFuncSetAttribute(nms_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM));
     CALD_CUDA_CHECK(cudaFuncSetAttribute(det_class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          NMS_SMEM + TOPK_MAX * 12));
@@ -1528,6 +1647,8 @@ static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, 
   check_ready(e);
   e->arena.reset();
   e->last_per_view.clear();
+  e->last_ref_counts.clear();
+  e->dbg_views.clear();
   e->last_A = n_augs;
   std::vector<cald_aug> augs(aug_list, aug_list + n_augs);
   int n_noise = 0, n_swap = 0;
@@ -1545,10 +1666,15 @@ static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, 
   } else {
     n_uniforms = 0;
   }
-  const int maxv = e->cfg.max_views_per_pass > 0 ? e->cfg.max_views_per_pass : 8;
+  const int maxv = e->views_per_pass;
   const int Bmax = std::max(1, maxv / std::max(1, n_augs));
   e->trace("call_start");
-  for (int pos = 0; pos < n_images; pos += Bmax) {
+  std::unique_ptr<UploadPipe> pipe;
+  if (!on_device) pipe.reset(new UploadPipe(e, n_images, imgs, heights, widths, Bmax));
+  // no copy may still be reading the caller's buffers when the call returns, on the error path either
+  struct CopyFence { cudaStream_t s; ~CopyFence() { cudaStreamSynchronize(s); } } copy_fence{e->copy_st};
+  int chunk = 0;
+  for (int pos = 0; pos < n_images; pos += Bmax, ++chunk) {
     const int B = std::min(Bmax, n_images - pos);
     DeviceImages di;
     const uint8_t* const* dptr;
@@ -1558,22 +1684,27 @@ static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, 
       dptr = imgs + pos;
       for (int i = 0; i < B * n_noise; ++i) nz.push_back(noise[(size_t)pos * n_noise + i]);
     } else {
-      di = upload_images(e, B, imgs + pos, heights + pos, widths + pos);
+      di = pipe->get(chunk);
       dptr = di.ptr.data();
       for (int b = 0; b < B; ++b)
         for (int j = 0; j < n_noise; ++j) {
+          const float* src = noise[(size_t)(pos + b) * n_noise + j];
+          if (!src) { nz.push_back(nullptr); continue; }  // image without reference detections: never read
           size_t bytes = (size_t)heights[pos + b] * widths[pos + b] * 3 * 4;
           float* d = (float*)e->arena.alloc(bytes);
-          CALD_CUDA_CHECK(cudaMemcpyAsync(d, noise[(size_t)(pos + b) * n_noise + j], bytes, cudaMemcpyHostToDevice, e->st));
+          CALD_CUDA_CHECK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, e->st));
           nz.push_back(d);
           nz_owned.push_back(d);
         }
     }
+    // the next chunk's images start travelling once this chunk's work is enqueued, before its results are awaited
+    UploadPipe* pp = pipe.get();
+    const int next = chunk + 1;
+    std::function<void()> prefetch = [pp, next]() { if (pp) pp->start(next); };
     score_chunk(e, B, dptr, heights + pos, widths + pos, augs, bp, d_u, n_uniforms, d_cursor,
                 n_noise ? nz.data() : nullptr, swap_perms ? swap_perms + (size_t)pos * n_swap : nullptr,
-                out_consistency + pos, out_cls ? out_cls + (size_t)pos * (e->C - 1) : nullptr, scorer);
+                out_consistency + pos, out_cls ? out_cls + (size_t)pos * (e->C - 1) : nullptr, scorer, prefetch);
     for (float* d : nz_owned) e->arena.free(d);
-    if (di.slab) e->arena.free(di.slab);
   }
   int consumed = 0;
   CALD_CUDA_CHECK(cudaMemcpyAsync(&consumed, d_cursor, 4, cudaMemcpyDeviceToHost, e->st));
@@ -1614,10 +1745,13 @@ int cald_score_ltc(cald_engine* e, int n_images, const uint8_t* const* images, c
   if (e->retina) throw std::runtime_error("LT/C needs the proposals of a Faster R-CNN ('props', frcnn_la.py:131-141)");
   e->arena.reset();
   const int dc = e->det_cap;
-  const int maxv = e->cfg.max_views_per_pass > 0 ? e->cfg.max_views_per_pass : 8;
-  for (int pos = 0; pos < n_images; pos += maxv) {
+  const int maxv = e->views_per_pass;
+  UploadPipe pipe(e, n_images, images, heights, widths, maxv);
+  struct CopyFence { cudaStream_t s; ~CopyFence() { cudaStreamSynchronize(s); } } copy_fence{e->copy_st};
+  int chunk = 0;
+  for (int pos = 0; pos < n_images; pos += maxv, ++chunk) {
     const int B = std::min(maxv, n_images - pos);
-    DeviceImages di = upload_images(e, B, images + pos, heights + pos, widths + pos);
+    DeviceImages di = pipe.get(chunk);
     std::vector<HostView> hv(B);
     for (int b = 0; b < B; ++b) hv[b] = HostView{di.ptr[b], heights[pos + b], widths[pos + b], 0, -1};
     ViewSet vs = alloc_viewset(e, B);
@@ -1628,11 +1762,11 @@ int cald_score_ltc(cald_engine* e, int n_images, const uint8_t* const* images, c
     KLAUNCH(e);
     std::vector<float> h(B);
     CALD_CUDA_CHECK(cudaMemcpyAsync(h.data(), d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, e->st));
+    pipe.start(chunk + 1);
     CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
     for (int b = 0; b < B; ++b) out_uncertainty[pos + b] = (double)h[b];
     e->arena.free(d_out);
     free_viewset(e, vs);
-    e->arena.free(di.slab);
   }
   API_CATCH(e)
 }
@@ -1644,10 +1778,13 @@ int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, cons
   check_ready(e);
   e->arena.reset();
   const int dc = e->det_cap, C = e->C;
-  const int maxv = e->cfg.max_views_per_pass > 0 ? e->cfg.max_views_per_pass : 8;
-  for (int pos = 0; pos < n_images; pos += maxv) {
+  const int maxv = e->views_per_pass;
+  UploadPipe pipe(e, n_images, images, heights, widths, maxv);
+  struct CopyFence { cudaStream_t s; ~CopyFence() { cudaStreamSynchronize(s); } } copy_fence{e->copy_st};
+  int chunk = 0;
+  for (int pos = 0; pos < n_images; pos += maxv, ++chunk) {
     const int B = std::min(maxv, n_images - pos);
-    DeviceImages di = upload_images(e, B, images + pos, heights + pos, widths + pos);
+    DeviceImages di = pipe.get(chunk);
     std::vector<HostView> hv(B);
     for (int b = 0; b < B; ++b) hv[b] = HostView{di.ptr[b], heights[pos + b], widths[pos + b], 0, -1};
     ViewSet vs = alloc_viewset(e, B);
@@ -1666,6 +1803,7 @@ int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, cons
       h_scores_all.resize((size_t)B * e->cap * C);
       CALD_CUDA_CHECK(cudaMemcpyAsync(h_scores_all.data(), vs.scores, h_scores_all.size() * 4, cudaMemcpyDeviceToHost, st));
     }
+    pipe.start(chunk + 1);
     CALD_CUDA_CHECK(cudaStreamSynchronize(st));
     check_overflow(e);
     for (int b = 0; b < B; ++b) {
@@ -1680,9 +1818,16 @@ int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, cons
       }
     }
     free_viewset(e, vs);
-    e->arena.free(di.slab);
   }
   API_CATCH(e)
+}
+
+int cald_last_ref_counts(cald_engine* e, int* out, int capacity) {
+  if (!e || !out) return -1;
+  int n = (int)e->last_ref_counts.size();
+  if (n > capacity) n = capacity;
+  memcpy(out, e->last_ref_counts.data(), (size_t)n * 4);
+  return n;
 }
 
 int cald_last_per_view(cald_engine* e, float* out, int capacity) {
@@ -1692,6 +1837,24 @@ int cald_last_per_view(cald_engine* e, float* out, int capacity) {
   memcpy(out, e->last_per_view.data(), (size_t)n * 4);
   return n;
 }
+
+long long cald_debug_views(cald_engine* e, int* counts, int counts_capacity, float* boxes, float* scores, int* labels,
+                           float* prob_max, long long rows_capacity) {
+  if (!e) return -1;
+  const cald_engine::DbgViews& d = e->dbg_views;
+  const long long rows = (long long)d.scores.size();
+  if (counts) memcpy(counts, d.counts.data(), (size_t)std::min<long long>(counts_capacity, (long long)d.counts.size()) * 4);
+  const size_t n = (size_t)std::min(rows, rows_capacity);
+  if (boxes) memcpy(boxes, d.boxes.data(), n * 16);
+  if (scores) memcpy(scores, d.scores.data(), n * 4);
+  if (labels) memcpy(labels, d.labels.data(), n * 4);
+  if (prob_max) memcpy(prob_max, d.prob_max.data(), n * 4);
+  return rows;
+}
+
+long long cald_arena_peak(cald_engine* e) { return e ? (long long)e->arena.peak : -1; }
+
+int cald_views_per_pass(cald_engine* e) { return e ? e->views_per_pass : -1; }
 
 long long cald_debug_fetch(cald_engine* e, const char* name, float* buf, long long capacity) {
   if (!e) return -1;

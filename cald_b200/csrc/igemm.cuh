@@ -4,14 +4,14 @@
 // detectors the CALD scoring path runs (a11 ResNet body, a12 FPN,
 // a13 RPN head, a15 box head, a18 RetinaNet heads):
 //   warp 0   : TMA producer  (cp.async.bulk.tensor 4-D boxes -> 128B-swizzled smem)
-//   warp 1   : MMA issuer    (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM)
-//   warps 2-5: epilogue      (tcgen05.ld -> bias / residual / ReLU -> split-bf16 NHWC)
+//   warp 1   : MMA issuer    (tcgen05.mma kind::f16, pl16 x pl16 -> fp32 in TMEM)
+//   warps 2-5: epilogue      (tcgen05.ld -> bias / residual / ReLU -> split-pl16 NHWC)
 // A tile = 128 output pixels (th x tw patch of one image, or 128 rows in linear
 // mode) x 64 input channels; the 3x3 taps are realised as shifted TMA boxes with
 // hardware zero fill at the borders, so no im2col buffer ever exists in HBM.
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 //
-// Split-bf16 ("bf16x3") arithmetic: A = A_hi + A_lo, B = B_hi + B_lo, product = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi.
+// Split-pl16 ("bf16x3") arithmetic: A = A_hi + A_lo, B = B_hi + B_lo, product = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi.
 // Launches with BLOCK_N <= 128 keep the small cross terms in their OWN accumulator columns (XSEP): one N = 2*BLOCK_N MMA
 // multiplies A_hi by the concatenation [B_hi | B_lo] (B_lo sits right behind B_hi in the stage), a second N = BLOCK_N
 // MMA adds A_lo*B_hi into the cross columns, and the epilogue sums the two halves in fp32.  That is two wide
@@ -23,7 +23,7 @@
 namespace cald {
 
 constexpr int IG_BLOCK_M = 128;
-constexpr int IG_BLOCK_K = 64;   // bf16 elements = one 128-byte swizzle row
+constexpr int IG_BLOCK_K = 64;   // pl16 elements = one 128-byte swizzle row
 constexpr int IG_UMMA_K = 16;
 constexpr int IG_THREADS = 192;  // 6 warps
 
@@ -111,13 +111,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // 32 accumulator columns = main + cross-term columns (XSEP): both TMEM loads are in flight before the one wait, so a
 // 64-channel group costs two TMEM round trips instead of four (the epilogue of the short-K layers is latency-bound:
 // ncu stall samples sat on the first FADD after every LDTM)
-__device__ __forceinline__ void tmem_ld32_sum2(uint32_t t_main, uint32_t t_cross, float* v) {
+// The cross-term accumulator holds LO_SCALE * (A_hi*B_lo + A_lo*B_hi) (common.cuh); `gain` is the round-toward-zero
+// compensation of the main accumulator (ConvParams::acc_gain).
+__device__ __forceinline__ void tmem_ld32_sum2(uint32_t t_main, uint32_t t_cross, float gain, float* v) {
   uint32_t a[32], b[32];
   tmem_ld32_nowait(t_main, a);
   tmem_ld32_nowait(t_cross, b);
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]) + __uint_as_float(b[i]);
+  for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(b[i]), CALD_LO_INV, __uint_as_float(a[i]) * gain);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -279,11 +281,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+      const uint32_t idesc = (1u << 4) | (PL16_MMA_FMT << 7) | (PL16_MMA_FMT << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                              ((uint32_t)(IG_BLOCK_M >> 4) << 24);
       // XSEP: the same instruction shape with N = 2 * BLOCK_N over [B_hi | B_lo]
-      const uint32_t idesc_cat = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BLOCK_N) >> 3) << 17) |
-                                 ((uint32_t)(IG_BLOCK_M >> 4) << 24);
+      const uint32_t idesc_cat = (1u << 4) | (PL16_MMA_FMT << 7) | (PL16_MMA_FMT << 10) |
+                                 ((uint32_t)((2 * BLOCK_N) >> 3) << 17) | ((uint32_t)(IG_BLOCK_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -309,9 +311,14 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
             const uint64_t ko = (uint64_t)((k * IG_UMMA_K * 2) >> 4);  // advance start address inside the swizzle row
             if (kb >= conv_kb && !p.res_conv) {
-              // residual k-block: D += R_lo * I + R_hi * I
-              if (SPLIT) tcgen05_mma_bf16(d, a_lo + ko, b_hi + ko, idesc, (kin | k) != 0);
-              tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, SPLIT ? 1u : (uint32_t)((kin | k) != 0));
+              // residual k-block: main += R_hi * I, cross += R_lo * I (the lo plane carries LO_SCALE like the cross terms)
+              if (XSEP) {
+                tcgen05_mma_bf16(d + BLOCK_N, a_lo + ko, b_hi + ko, idesc, 1);
+                tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, 1);
+              } else {
+                if (SPLIT) tcgen05_mma_bf16(d, a_lo + ko, b_hi + ko, idesc, (kin | k) != 0);
+                tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, SPLIT ? 1u : (uint32_t)((kin | k) != 0));
+              }
             } else if (XSEP) {
               // columns [0, BLOCK_N) += A_hi*B_hi, columns [BLOCK_N, 2*BLOCK_N) += A_hi*B_lo + A_lo*B_hi
               tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc_cat, (kin | k) != 0);
@@ -372,15 +379,15 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tmem_ld32(t0 + cc, r);
             if (ch == 0) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) accv[cc + i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 32; ++i) accv[cc + i] = __uint_as_float(r[i]) * p.acc_gain;
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) accv[cc + i] += __uint_as_float(r[i]);
+              for (int i = 0; i < 32; ++i) accv[cc + i] = fmaf(__uint_as_float(r[i]), p.acc_gain, accv[cc + i]);
             }
             if (XSEP) {  // the chunk's cross-term columns
               tmem_ld32(t0 + BLOCK_N + cc, r);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) accv[cc + i] += __uint_as_float(r[i]);
+              for (int i = 0; i < 32; ++i) accv[cc + i] = fmaf(__uint_as_float(r[i]), CALD_LO_INV, accv[cc + i]);
             }
           }
           tcgen05_fence_before();
@@ -403,16 +410,16 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int i = 0; i < 64; ++i) v[i] = accv[(g * 64 + i) % NACC];
         } else {
           if (XSEP) {
-            tmem_ld32_sum2(t0 + g * 64, t0 + BLOCK_N + g * 64, v);
-            tmem_ld32_sum2(t0 + g * 64 + 32, t0 + BLOCK_N + g * 64 + 32, v + 32);
+            tmem_ld32_sum2(t0 + g * 64, t0 + BLOCK_N + g * 64, p.acc_gain, v);
+            tmem_ld32_sum2(t0 + g * 64 + 32, t0 + BLOCK_N + g * 64 + 32, p.acc_gain, v + 32);
           } else {
             uint32_t r[32];
             tmem_ld32(t0 + g * 64, r);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.acc_gain;
             tmem_ld32(t0 + g * 64 + 32, r);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
+            for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]) * p.acc_gain;
           }
           if (g == BLOCK_N / 64 - 1) {  // accumulator fully drained: hand the TMEM stage back to the MMA warp
             tcgen05_fence_before();
@@ -450,8 +457,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (SPLIT) {
                 join_pack2(h[i], l[i], a, b);
               } else {
-                a = __uint_as_float(h[i] << 16);
-                b = __uint_as_float(h[i] & 0xffff0000u);
+                unpack2(h[i], a, b);
               }
               v[q * 8 + 2 * i] += a;
               v[q * 8 + 2 * i + 1] += b;
@@ -469,7 +475,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        // ---- split to bf16 planes and write this row's 8 x 16-byte chunks at their 128B-swizzled positions
+        // ---- split to pl16 planes and write this row's 8 x 16-byte chunks at their 128B-swizzled positions
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           uint32_t ph[4], pl[4];
@@ -516,9 +522,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // engine's CALD_CONV=simt debugging path.  One thread = one pixel x 8 output channels.
 // --------------------------------------------------------------------------------
 struct SimtOperands {
-  const bf16* a_hi; const bf16* a_lo;   // [img'][H_in][W_in][Cin]
-  const bf16* b_hi; const bf16* b_lo;   // [Cout_pad][taps*Cin]
-  int H_in, W_in, n_img_in;             // input plane geometry (a_lo == null -> bf16 mode)
+  const pl16* a_hi; const pl16* a_lo;   // [img'][H_in][W_in][Cin]
+  const pl16* b_hi; const pl16* b_lo;   // [Cout_pad][taps*Cin]
+  int H_in, W_in, n_img_in;             // input plane geometry (a_lo == null -> pl16 mode)
   int pix_stride;                       // elements between consecutive pixels (Cin, or 16 for the stem window)
   int w_limit;                          // number of valid window start columns (W_in, or W_in - 3 for the stem)
 };
@@ -540,13 +546,13 @@ __global__ void conv_simt_kernel(ConvParams p, SimtOperands o) {
     if (iy < 0 || iy >= o.H_in || ix < 0 || ix >= o.w_limit) continue;
     const long long abase = (((long long)ii * o.H_in + iy) * o.W_in + ix) * o.pix_stride;
     for (int c = 0; c < p.Cin; ++c) {
-      float a = __bfloat162float(o.a_hi[abase + c]);
-      if (o.a_lo) a += __bfloat162float(o.a_lo[abase + c]);
+      float a = pl16_to_float(o.a_hi[abase + c]);
+      if (o.a_lo) a = join_pl(o.a_hi[abase + c], o.a_lo[abase + c]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const long long bi = (long long)(cg * 8 + j) * ktot + tap * p.Cin + c;
-        float b = __bfloat162float(o.b_hi[bi]);
-        if (o.b_lo) b += __bfloat162float(o.b_lo[bi]);
+        float b = pl16_to_float(o.b_hi[bi]);
+        if (o.b_lo) b = join_pl(o.b_hi[bi], o.b_lo[bi]);
         acc[j] = fmaf(a, b, acc[j]);
       }
     }

@@ -1,4 +1,4 @@
-// CTA-pair (cta_group::2) variant of the implicit-GEMM conv kernel for the tensor-bound split-bf16 layers.
+// CTA-pair (cta_group::2) variant of the implicit-GEMM conv kernel for the tensor-bound split-pl16 layers.
 //
 // Two CTAs of one cluster (= the two SMs of a TPC) compute two 128-pixel tiles against the same 128 output
 // channels as ONE M = 256 tcgen05.mma.  In pair mode each CTA feeds its own 128 rows of A and only HALF of the B
@@ -217,7 +217,7 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24);  // M = 256
+      const uint32_t idesc_base = (1u << 4) | (PL16_MMA_FMT << 7) | (PL16_MMA_FMT << 10) | ((uint32_t)(256 >> 4) << 24);  // M = 256
       const uint32_t idesc_cat = idesc_base | ((uint32_t)((2 * BLOCK_N) >> 3) << 17);
       const uint32_t idesc_half = idesc_base | ((uint32_t)(BLOCK_N >> 3) << 17);
       int stage = 0;
@@ -297,14 +297,14 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld32(tc + cc, r);
             if (ch == 0) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) accv[cc + i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 32; ++i) accv[cc + i] = __uint_as_float(r[i]) * p.acc_gain;
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) accv[cc + i] += __uint_as_float(r[i]);
+              for (int i = 0; i < 32; ++i) accv[cc + i] = fmaf(__uint_as_float(r[i]), p.acc_gain, accv[cc + i]);
             }
-            tmem_ld32(tc + BLOCK_N + cc, r);  // the chunk's cross-term columns
+            tmem_ld32(tc + BLOCK_N + cc, r);  // the chunk's cross-term columns (scaled by LO_SCALE, common.cuh)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) accv[cc + i] += __uint_as_float(r[i]);
+            for (int i = 0; i < 32; ++i) accv[cc + i] = fmaf(__uint_as_float(r[i]), CALD_LO_INV, accv[cc + i]);
           }
           tcgen05_fence_before();
           __syncwarp();
@@ -324,8 +324,8 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = accv[CHUNKED ? g * 64 + i : 0];
         } else {
-          tmem_ld32_sum2(t0 + g * 64, t0 + BLOCK_N + g * 64, v);
-          tmem_ld32_sum2(t0 + g * 64 + 32, t0 + BLOCK_N + g * 64 + 32, v + 32);
+          tmem_ld32_sum2(t0 + g * 64, t0 + BLOCK_N + g * 64, p.acc_gain, v);
+          tmem_ld32_sum2(t0 + g * 64 + 32, t0 + BLOCK_N + g * 64 + 32, p.acc_gain, v + 32);
           if (g == BLOCK_N / 64 - 1) {  // accumulator drained: hand the stage back to the leader's MMA thread
             tcgen05_fence_before();
             __syncwarp();

@@ -60,37 +60,37 @@ struct Arena {
 inline Act alloc_act(Arena& a, int n, int h, int w, int c, bool split) {
   Act t;
   t.n = n; t.h = h; t.w = w; t.c = c; t.split = split;
-  t.hi = (bf16*)a.alloc(t.bytes());
+  t.hi = (pl16*)a.alloc(t.bytes());
   return t;
 }
 inline void free_act(Arena& a, Act& t) { a.free(t.hi); t.hi = nullptr; }
 
 // ---------------------------------------------------------------- conversions
-__global__ void f32_to_split_kernel(const float* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo,
+__global__ void f32_to_split_kernel(const float* __restrict__ in, pl16* __restrict__ hi, pl16* __restrict__ lo,
                                     long long n) {
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   if (i + 3 < n) {
     float4 v = *reinterpret_cast<const float4*>(in + i);
-    bf16 h[4], l[4];
-    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
-    split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
-    *reinterpret_cast<uint2*>(hi + i) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-    if (lo) *reinterpret_cast<uint2*>(lo + i) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+    pl16 h[4], l[4];
+    split_pl(v.x, h[0], l[0]); split_pl(v.y, h[1], l[1]);
+    split_pl(v.z, h[2], l[2]); split_pl(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi + i) = make_uint2(pack_pl16x2(h[0], h[1]), pack_pl16x2(h[2], h[3]));
+    if (lo) *reinterpret_cast<uint2*>(lo + i) = make_uint2(pack_pl16x2(l[0], l[1]), pack_pl16x2(l[2], l[3]));
   } else {
     for (; i < n; ++i) {
-      bf16 h, l;
-      split_bf16(in[i], h, l);
+      pl16 h, l;
+      split_pl(in[i], h, l);
       hi[i] = h;
       if (lo) lo[i] = l;
     }
   }
 }
-__global__ void split_to_f32_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, float* __restrict__ out,
+__global__ void split_to_f32_kernel(const pl16* __restrict__ hi, const pl16* __restrict__ lo, float* __restrict__ out,
                                     long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = lo ? join_bf16(hi[i], lo[i]) : __bfloat162float(hi[i]);
+  out[i] = lo ? join_pl(hi[i], lo[i]) : pl16_to_float(hi[i]);
 }
 inline void f32_to_split(const float* in, Act& t, cudaStream_t st) {
   long long n = (long long)t.plane_elems();
@@ -105,7 +105,7 @@ inline void split_to_f32(const Act& t, float* out, cudaStream_t st) {
 
 // ---------------------------------------------------------------- 2x subsample (8 channels per thread)
 // out[i][y][x][c] = in[i][2y][2x][c]   (1x1 stride-2 convs, LastLevelMaxPool k=1 s=2)
-__global__ void subsample2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int n, int h, int w, int c,
+__global__ void subsample2_kernel(const pl16* __restrict__ in, pl16* __restrict__ out, int n, int h, int w, int c,
                                   int h2, int w2) {
   long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = c / 8;
@@ -140,8 +140,8 @@ __global__ void rpn_head_sum_kernel(const float4* __restrict__ part, long long q
 }
 
 // ---------------------------------------------------------------- 3x3 / stride 2 / pad 1 max-pool (tv resnet.py maxpool)
-__global__ void maxpool3x3s2_kernel(const bf16* __restrict__ ihi, const bf16* __restrict__ ilo, bf16* __restrict__ ohi,
-                                    bf16* __restrict__ olo, int n, int h, int w, int c, int ho, int wo) {
+__global__ void maxpool3x3s2_kernel(const pl16* __restrict__ ihi, const pl16* __restrict__ ilo, pl16* __restrict__ ohi,
+                                    pl16* __restrict__ olo, int n, int h, int w, int c, int ho, int wo) {
   long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = c / 8;
   long long total = (long long)n * ho * wo * cg;
@@ -162,26 +162,26 @@ __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ ihi, const bf16* __
       if (sx < 0 || sx >= w) continue;
       long long off = (((long long)i * h + sy) * w + sx) * c + g * 8;
       uint4 vh = *reinterpret_cast<const uint4*>(ihi + off);
-      const bf16* ph = reinterpret_cast<const bf16*>(&vh);
+      const pl16* ph = reinterpret_cast<const pl16*>(&vh);
       if (ilo) {
         uint4 vl = *reinterpret_cast<const uint4*>(ilo + off);
-        const bf16* pl = reinterpret_cast<const bf16*>(&vl);
+        const pl16* pl = reinterpret_cast<const pl16*>(&vl);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], join_bf16(ph[k], pl[k]));
+        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], join_pl(ph[k], pl[k]));
       } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], __bfloat162float(ph[k]));
+        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], pl16_to_float(ph[k]));
       }
     }
   }
-  bf16 hh[8], ll[8];
+  pl16 hh[8], ll[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) split_bf16(m[k], hh[k], ll[k]);
-  *reinterpret_cast<uint4*>(ohi + gid * 8) = make_uint4(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]),
-                                                       pack_bf16x2(hh[4], hh[5]), pack_bf16x2(hh[6], hh[7]));
+  for (int k = 0; k < 8; ++k) split_pl(m[k], hh[k], ll[k]);
+  *reinterpret_cast<uint4*>(ohi + gid * 8) = make_uint4(pack_pl16x2(hh[0], hh[1]), pack_pl16x2(hh[2], hh[3]),
+                                                       pack_pl16x2(hh[4], hh[5]), pack_pl16x2(hh[6], hh[7]));
   if (olo)
-    *reinterpret_cast<uint4*>(olo + gid * 8) = make_uint4(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]),
-                                                         pack_bf16x2(ll[4], ll[5]), pack_bf16x2(ll[6], ll[7]));
+    *reinterpret_cast<uint4*>(olo + gid * 8) = make_uint4(pack_pl16x2(ll[0], ll[1]), pack_pl16x2(ll[2], ll[3]),
+                                                         pack_pl16x2(ll[4], ll[5]), pack_pl16x2(ll[6], ll[7]));
 }
 inline Act maxpool3x3s2(Arena& a, const Act& in, cudaStream_t st) {
   Act o = alloc_act(a, in.n, (in.h - 1) / 2 + 1, (in.w - 1) / 2 + 1, in.c, in.split);

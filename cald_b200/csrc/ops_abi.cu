@@ -20,7 +20,7 @@ extern "C" long long cald_ops_pair_launches(void) { return pair_launch_counter()
   return 0;
 
 namespace cald {
-// Upload torch-layout weights [cout][cin][k][k] as [2][cout_pad][(r,s,cin)] split bf16 (+ fp32 bias).
+// Upload torch-layout weights [cout][cin][k][k] as [2][cout_pad][(r,s,cin)] split pl16 (+ fp32 bias).
 ConvW upload_conv_weight(const float* w, const float* bias, int cout, int cin, int k, bool split,
                          const float* scale /*per-cout or null*/) {
   ConvW cw;
@@ -29,8 +29,8 @@ ConvW upload_conv_weight(const float* w, const float* bias, int cout, int cin, i
   cw.cin = cin;
   cw.taps = k * k;
   size_t pe = cw.plane_elems();
-  std::vector<bf16> h(pe * (split ? 2 : 1));
-  for (auto& v : h) v = __float2bfloat16(0.f);
+  std::vector<pl16> h(pe * (split ? 2 : 1));
+  for (auto& v : h) v = float_to_pl16(0.f);
   for (int o = 0; o < cout; ++o)
     for (int c = 0; c < cin; ++c)
       for (int r = 0; r < k; ++r)
@@ -38,13 +38,13 @@ ConvW upload_conv_weight(const float* w, const float* bias, int cout, int cin, i
           float v = w[(((size_t)o * cin + c) * k + r) * k + s];
           if (scale) v *= scale[o];
           size_t idx = (size_t)o * cw.taps * cin + (size_t)(r * k + s) * cin + c;
-          bf16 hi, lo;
-          split_bf16(v, hi, lo);
+          pl16 hi, lo;
+          split_pl(v, hi, lo);
           h[idx] = hi;
           if (split) h[pe + idx] = lo;
         }
-  CALD_CUDA_CHECK(cudaMalloc((void**)&cw.w, h.size() * sizeof(bf16)));
-  CALD_CUDA_CHECK(cudaMemcpy(cw.w, h.data(), h.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  CALD_CUDA_CHECK(cudaMalloc((void**)&cw.w, h.size() * sizeof(pl16)));
+  CALD_CUDA_CHECK(cudaMemcpy(cw.w, h.data(), h.size() * sizeof(pl16), cudaMemcpyHostToDevice));
   std::vector<float> b(cw.cout_pad, 0.f);
   if (bias) for (int o = 0; o < cout; ++o) b[o] = bias[o];
   CALD_CUDA_CHECK(cudaMalloc((void**)&cw.bias, b.size() * sizeof(float)));

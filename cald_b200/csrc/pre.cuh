@@ -23,7 +23,8 @@ struct ViewDesc {
   // noise views (cald_helper.py:72-85): planes [3][sh][sw] drawn by the caller from torch's CPU generator
   const float* noise;   // null for the other views
   int noise_mode;       // 1: x + noise * std / 255     2: salt (noise < lo) / pepper (noise > hi)
-  float n0, n1, n2, n3; // mode 1: std            mode 2: lo, hi, salt value, pepper value
+  float n0, n1;         // mode 1: std            mode 2: lo, hi thresholds
+  const int* mm;        // mode 2: device [2] = min, max of the u8 source; salt = max / 255, pepper = min / 255
   int perm;             // ColorSwap (cald_helper.py:56-62): source channel of output channel c = (perm >> 2c) & 3
 };
 constexpr int PERM_IDENTITY = 0 | (1 << 2) | (2 << 4);
@@ -50,8 +51,8 @@ __device__ __forceinline__ float src_pixel(const ViewDesc& d, const CutRects* cu
     if (d.noise_mode == 1) {
       v = v + (nz * d.n0) / 255.0f;
     } else {
-      if (nz < d.n0) v = d.n2;
-      if (nz > d.n1) v = d.n3;
+      if (nz < d.n0) v = (float)d.mm[1] / 255.0f;   // salt = max(image)   (cald_helper.py:81-84)
+      if (nz > d.n1) v = (float)d.mm[0] / 255.0f;   // pepper = min(image)
     }
   }
   return (v - mean) / stdv;
@@ -88,13 +89,13 @@ __global__ void view_preprocess_kernel(const ViewDesc* __restrict__ views, const
 }
 
 // Fused transform + space-to-depth for the stem: writes the padded phase image
-//   S[v][pr][pc][(py*2+px)*3 + c] = input(c, 2*(pr-2)+py, 2*(pc-2)+px)   (channels 12..15 = 0), split bf16,
+//   S[v][pr][pc][(py*2+px)*3 + c] = input(c, 2*(pr-2)+py, 2*(pc-2)+px)   (channels 12..15 = 0), split pl16,
 // with pr in [0, Ho+3), pc in [0, Wo+3).  One thread per (pr, pc): 2 x 32-byte stores.
 // The per-pixel work (resize coordinates, cutout test, flip index) is done once for the three channels, and the two
 // fp32 divisions of F.to_tensor + normalize, (p / 255 - mean) / std, come from a per-block table built with exactly
 // those operations (bit-identical results; noise views, whose values are not u8, take the arithmetic path).
 __global__ void view_stem_input_kernel(const ViewDesc* __restrict__ views, const CutRects* __restrict__ cuts, int Hs,
-                                       int Ws, bf16* __restrict__ ohi, bf16* __restrict__ olo) {
+                                       int Ws, pl16* __restrict__ ohi, pl16* __restrict__ olo) {
   __shared__ float s_unit[256];      // p / 255
   __shared__ float s_norm[3][256];   // (p / 255 - mean_c) / std_c
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -133,8 +134,8 @@ __global__ void view_stem_input_kernel(const ViewDesc* __restrict__ views, const
         if (d.noise_mode == 1) {
           val = val + (nz * d.n0) / 255.0f;
         } else {
-          if (nz < d.n0) val = d.n2;
-          if (nz > d.n1) val = d.n3;
+          if (nz < d.n0) val = (float)d.mm[1] / 255.0f;
+          if (nz > d.n1) val = (float)d.mm[0] / 255.0f;
         }
         out[c] = (val - mean) / stdv;
       }

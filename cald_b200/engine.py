@@ -98,6 +98,7 @@ class Engine:
         L.cald_last_error.restype = c_char_p
         L.cald_last_error.argtypes = [c_void_p]
         L.cald_destroy.argtypes = [c_void_p]
+        L.cald_views_per_pass.argtypes = [c_void_p]
         cfg = Config()
         L.cald_config_default(ctypes.byref(cfg), arch_id, depth, num_classes, min_size, max_size)
         cfg.device, cfg.precision, cfg.conv_impl = device, precision, conv_impl
@@ -169,6 +170,10 @@ class Engine:
         nu = 0 if u is None else u.size
         nz_keep, nz_ptrs = [], None
         if noise:
+            n_noise = sum(1 for v in views if (v if isinstance(v, int) else v[0]) in NOISE_KINDS)
+            if len(noise) != n * n_noise:
+                raise ValueError("expected %d noise planes (%d images x %d noise views), got %d"
+                                 % (n * n_noise, n, n_noise, len(noise)))
             nz_keep = [np.ascontiguousarray(z, dtype=np.float32) for z in noise]
             nz_ptrs = (POINTER(c_float) * len(nz_keep))(*[z.ctypes.data_as(POINTER(c_float)) for z in nz_keep])
         sp = None if swap_perms is None else np.ascontiguousarray(swap_perms, dtype=np.int32)
@@ -234,6 +239,14 @@ class Engine:
         self._check(self._L.cald_score_ltc(self._h, n, ptrs, hs, ws, out.ctypes.data_as(POINTER(c_double))))
         return out
 
+    def last_ref_counts(self, n_images):
+        """Detections of each image's reference view in the last score() / score_lsc() call (0 = the reference skips
+        the image before drawing any augmentation randomness)."""
+        out = np.zeros(n_images, dtype=np.int32)
+        self._L.cald_last_ref_counts.argtypes = [c_void_p, POINTER(c_int), c_int]
+        k = self._L.cald_last_ref_counts(self._h, out.ctypes.data_as(POINTER(c_int)), n_images)
+        return out[:max(k, 0)]
+
     def last_per_view(self, n_images, n_augs):
         out = np.zeros(n_images * n_augs, dtype=np.float32)
         self._L.cald_last_per_view.argtypes = [c_void_p, POINTER(c_float), c_int]
@@ -268,6 +281,48 @@ class Engine:
             out.append({"boxes": boxes[i, :k], "labels": labels[i, :k], "scores": scores[i, :k],
                         "props": props[i, :k], "prob_max": pmax[i, :k], "scores_cls": scls[i, :k]})
         return out
+
+    def debug_views(self, n_images, n_augs):
+        """debug=True: detections of every view of the last score() call -> list (per image) of lists (reference
+        view first, then the augmented views) of dicts boxes / scores / labels / prob_max."""
+        nv = n_images * (1 + n_augs)
+        self._L.cald_debug_views.restype = c_longlong
+        self._L.cald_debug_views.argtypes = [c_void_p, POINTER(c_int), c_int, POINTER(c_float), POINTER(c_float),
+                                             POINTER(c_int), POINTER(c_float), c_longlong]
+        rows = self._L.cald_debug_views(self._h, None, 0, None, None, None, None, 0)
+        counts = np.zeros(nv, dtype=np.int32)
+        boxes = np.zeros((rows, 4), dtype=np.float32)
+        scores = np.zeros(rows, dtype=np.float32)
+        pmax = np.zeros(rows, dtype=np.float32)
+        labels = np.zeros(rows, dtype=np.int32)
+        fp = POINTER(c_float)
+        self._L.cald_debug_views(self._h, counts.ctypes.data_as(POINTER(c_int)), nv, boxes.ctypes.data_as(fp),
+                                 scores.ctypes.data_as(fp), labels.ctypes.data_as(POINTER(c_int)),
+                                 pmax.ctypes.data_as(fp), rows)
+        out, pos, k = [], 0, 0
+        for _ in range(n_images):
+            views = []
+            for _ in range(1 + n_augs):
+                n = int(counts[k]) if k < len(counts) else 0
+                views.append({"boxes": boxes[pos:pos + n], "scores": scores[pos:pos + n],
+                              "labels": labels[pos:pos + n], "prob_max": pmax[pos:pos + n]})
+                pos += n
+                k += 1
+            out.append(views)
+        return out
+
+    def views_per_pass(self):
+        return int(self._L.cald_views_per_pass(self._h))
+
+    def images_per_chunk(self, n_augs):
+        """Images the engine scores per pass (reference views of a chunk run as one batch, its augmented views as
+        another)."""
+        return max(1, self.views_per_pass() // max(1, n_augs))
+
+    def arena_peak(self):
+        self._L.cald_arena_peak.restype = c_longlong
+        self._L.cald_arena_peak.argtypes = [c_void_p]
+        return int(self._L.cald_arena_peak(self._h))
 
     def debug_fetch(self, name):
         self._L.cald_debug_fetch.restype = c_longlong

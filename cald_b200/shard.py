@@ -31,15 +31,25 @@ def merge_shards(parts, n, world):
     return out
 
 
-def get_uncertainty_sharded(eng, images_u8, augs, rank, world, group=None):
-    """Score this rank's shard, all-gather (consistency, class vector) rows, return them in loader order
-    on every rank.  ``images_u8`` is the FULL ordered pool (each rank only touches its shard)."""
+def get_uncertainty_sharded(eng, pool, augs, rank, world, group=None, n=None, chunk=None):
+    """Score this rank's shard, all-gather (consistency, class vector) rows, return them in loader order on every
+    rank.  ``pool`` is either a sequence of u8 HWC images or a callable ``index -> image`` together with ``n`` (the
+    pool size): a rank only ever materialises the images of its own shard, one scoring chunk at a time, so neither
+    the pool nor the shard has to fit in host memory (cfg-5's 118k images are 378 GB).
+
+    Python's ``random`` stream (cutout) is consumed per rank in shard order; seed it per rank if draws matter."""
     import torch
     import torch.distributed as dist
     from . import api
-    n = len(images_u8)
+    fetch = pool if callable(pool) else (lambda i: pool[i])
+    n = len(pool) if n is None else n
     mine = shard_indices(n, rank, world)
-    cons, cls = api.score_images(eng, [images_u8[i] for i in mine], augs)
+    step = chunk or 4 * eng.images_per_chunk(max(1, len(api._aug_kinds(augs))))
+    cons, cls = [], []
+    for pos in range(0, len(mine), step):
+        c, v = api.score_images(eng, [api._to_u8(fetch(int(i))) for i in mine[pos:pos + step]], augs)
+        cons.extend(c)
+        cls.extend(v)
     c1 = eng.num_classes - 1
     rows = np.zeros((padded_count(n, world), 1 + c1), dtype=np.float64)
     if len(mine):

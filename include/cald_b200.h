@@ -55,12 +55,15 @@ typedef struct {
   float box_score_thresh;    /* 0.05 (frcnn_la.py:161) */
   float box_nms_thresh;      /* 0.5 */
   int box_detections_per_img;/* FRCNN: 100 per image (frcnn_la.py:161); RetinaNet: 300 PER CLASS (retinanet_cal.py:333,463) */
-  int retina_max_detections; /* RetinaNet: capacity of one image's concatenated detection list (<= 300*K in the
-                                reference); exceeding it, or 4096 candidates per class, fails the call loudly */
+  int retina_max_detections; /* RetinaNet: capacity of one image's concatenated detection list; default 300 * K =
+                                the most the reference can emit (300 per class, retinanet_cal.py:333, 463), so the
+                                default cannot overflow.  The number of candidates above the score threshold is
+                                unlimited, like in the reference (classes with more than 4096 are scanned in windows) */
   int device;                /* CUDA ordinal */
   int precision;             /* CALD_PREC_* */
   int conv_impl;             /* CALD_CONV_* */
-  int max_views_per_pass;    /* views batched through one forward pass (0 = auto) */
+  int max_views_per_pass;    /* views batched through one forward pass (0 = auto: as many as the arena holds at the
+                                largest padded input, up to 64) */
   size_t workspace_bytes;    /* device arena (0 = auto from free memory) */
   int debug;                 /* 1: keep host copies of stage tensors for cald_debug_fetch */
 } cald_config;
@@ -114,12 +117,30 @@ int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, cons
                 int* counts, float* boxes, float* scores, int64_t* labels, float* props, float* prob_max,
                 float* scores_cls);
 
+/* Number of detections in each image's reference view during the last cald_score() / cald_score_lsc() call (after the
+ * >40 -> 50 sub-sampling for cald_score).  0 marks the images the reference skips before drawing any augmentation
+ * randomness (cald_train.py:118-121, ls_c_train.py:118-120); the host wrapper rewinds its generators with it. */
+int cald_last_ref_counts(cald_engine* e, int* out, int capacity);
+
 /* Per-view consistency of the last cald_score() call: out[n_images][n_augs] (cald_train.py:223). */
 int cald_last_per_view(cald_engine* e, float* out, int capacity);
 
 /* Stage tensors of the LAST forward pass (debug=1): returns element count, or <0.  With buf == NULL only the size
  * is returned.  Names: "input", "c2".."c5", "p2".."p6", "rpn0".."rpn4", "proposals", "proposal_count", "pooled", "head". */
 long long cald_debug_fetch(cald_engine* e, const char* name, float* buf, long long capacity);
+
+/* debug = 1: the detections of every view of the last cald_score() call, ragged: counts[n_images * (1 + n_augs)] in
+ * (image, [reference view, augmented views in order]) order, then that many rows of boxes[.][4] (in the view's own image
+ * coordinates), scores, labels, prob_max.  Returns the total number of rows (call with NULL buffers to size them). */
+long long cald_debug_views(cald_engine* e, int* counts, int counts_capacity, float* boxes, float* scores, int* labels,
+                           float* prob_max, long long rows_capacity);
+
+/* High-water mark of the device arena in bytes since creation (sizing max_views_per_pass / workspace_bytes). */
+long long cald_arena_peak(cald_engine* e);
+
+/* Views (detector forwards) batched through one pass: cfg.max_views_per_pass, or what cald_create derived from the
+ * arena size when that was 0.  A scoring call processes max(1, views / n_augs) images per chunk. */
+int cald_views_per_pass(cald_engine* e);
 
 /* Counters since creation: kernels launched by this engine, algorithmic conv/GEMM FLOPs (2*MAC),
  * and device milliseconds spent inside tcgen05 conv kernels when timing is enabled. */
