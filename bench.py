@@ -1,15 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- unlabeled images scored / s (Faster R-CNN R50-FPN, 800x1333, A = 4 augmentations).
+"""bench.py -- unlabeled images scored / s.
 
-Workload (BASELINE.json configs[1]): synthetic 1333x800 (W x H) u8 pool, nc = 91, min/max size
-800/1333, augmentations F, C, D, R, bp = 1.3, planted weights.  One "step" = one pass of the hot
-path (1 reference + 4 augmented detector forwards + the paired-prediction reduction) over one
-batch of --batch images.  `value` times the step with the u8 pool already resident in HBM
-(cald_score_device); `e2e` times the public API (cald_b200.api.score_images -> cald_score) with
-HOST images, H2D and D2H inside the timed region.  Both are timed with CUDA events recorded on
-the engine's own stream; under torchrun the result is the max over ranks.
+Default workload = BASELINE.json configs[1] ("cfg2"): Faster R-CNN R50-FPN, nc = 91, synthetic 1333x800 (W x H) u8
+pool, min/max size 800/1333, augmentations F, C, D, R, bp = 1.3, planted weights.  One "step" = one pass of the hot
+path (1 reference + A augmented detector forwards + the paired-prediction reduction) over one batch of --batch images
+per GPU; every step scores images it has not seen before.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    value          images/s with the u8 pool already resident in HBM (cald_score_device), NOT instrumented
+    roofline       a second pass over the same steps with every tcgen05 conv/GEMM launch bracketed by CUDA events
+    e2e            the public API (cald_b200.api.score_images -> cald_score) fed from page-locked HOST images, H2D and
+                   D2H inside the timed region; e2e.pageable = the same from ordinary (pageable) numpy arrays
+    cpu_baseline   the oracle port of cald_train.get_uncertainty on the box's host cores (N = 1 only)
+
+All GPU legs are timed with CUDA events recorded on the engine's own stream; under torchrun the result is the max over
+ranks.  Other BASELINE configs: --config cfg3 (RetinaNet R50-FPN), cfg4 (Faster R-CNN R101-FPN, VOC shape, A = 3),
+cfg5 (--mode cycle: a fixed pool sharded over the ranks through cald_b200.shard.get_uncertainty_sharded, one
+all-gather, then the host selection of cald_train.py:439-448 -- strong scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference] [--config cfgN] [--mode cycle]
 """
 import argparse
 import json
@@ -25,28 +33,41 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W = 800, 1333
-NUM_CLASSES = 91
-MIN_SIZE, MAX_SIZE = 800, 1333
-AUGS = ['flip', 'cut_out', 'smaller_resize', 'rotation']
-METRIC = "unlabeled images scored/sec (FRCNN R50-FPN, 800x1333)"
-WORKLOAD = "FRCNN R50-FPN nc=91, synthetic 1333x800 pool, 1 ref + 4 aug (F,C,D,R) forwards per image"
-# --model retinanet = BASELINE.json configs[2] (RetinaNet R50-FPN, retinanet_cal.py), same pool shape and augmentations
-# DRAM bytes per conv launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu) averaged over the 142 igemm_tc_kernel /
-# igemm_tc2_kernel launches of one default step (batch 16: a 16-view reference pass + a 64-view augmented pass); source:
-# profiles/r01_igemm_dram_step.csv, captured with tools/final_measure.sh.  Only valid for the default FRCNN workload.
+CONFIGS = {
+    # name: model, depth, num_classes, (H, W), min/max size, augmentations, BASELINE.json configs[] index
+    "cfg2": dict(model="frcnn", depth=50, nc=91, hw=(800, 1333), size=(800, 1333),
+                 augs=['flip', 'cut_out', 'smaller_resize', 'rotation'], idx=1,
+                 metric="unlabeled images scored/sec (FRCNN R50-FPN, 800x1333)",
+                 workload="FRCNN R50-FPN nc=91, synthetic 1333x800 pool, 1 ref + 4 aug (F,C,D,R) forwards per image"),
+    "cfg3": dict(model="retinanet", depth=50, nc=91, hw=(800, 1333), size=(800, 1333),
+                 augs=['flip', 'cut_out', 'smaller_resize', 'rotation'], idx=2,
+                 metric="unlabeled images scored/sec (RetinaNet R50-FPN, 800x1333)",
+                 workload="RetinaNet R50-FPN nc=91, synthetic 1333x800 pool, 1 ref + 4 aug (F,C,D,R) forwards per image"),
+    "cfg4": dict(model="frcnn", depth=101, nc=21, hw=(375, 500), size=(600, 1000),
+                 augs=['flip', 'cut_out', 'smaller_resize'], idx=3,
+                 metric="unlabeled images scored/sec (FRCNN R101-FPN, VOC shape 500x375, 3 augmentations)",
+                 workload="FRCNN R101-FPN nc=21, synthetic 500x375 pool (600/1000), 1 ref + 3 aug (F,C,D) forwards per image"),
+    "cfg5": dict(model="frcnn", depth=50, nc=91, hw=(800, 1333), size=(800, 1333),
+                 augs=['flip', 'cut_out', 'smaller_resize', 'rotation'], idx=4,
+                 metric="unlabeled images scored/sec, full AL cycle incl. selection (FRCNN R50-FPN, 800x1333)",
+                 workload="FRCNN R50-FPN nc=91, synthetic 1333x800 pool sharded over the GPUs, score -> all-gather -> "
+                          "argsort -> cls_kldiv -> select (cald_train.py:427-448)"),
+}
+# DRAM bytes per conv launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu) averaged over the conv launches of one
+# default cfg2 step (batch 16: a 16-view reference pass + a 64-view augmented pass).  An OFFLINE ncu constant (ncu
+# cannot run inside a timed bench); source file named in the JSON.  Only reported for the workload it was captured on.
 NCU_DRAM_BYTES_PER_CONV_LAUNCH = 1556.2e6
+NCU_DRAM_SOURCE = "profiles/r01_igemm_dram_step.csv"
 NCU_DRAM_BATCH = 16
-METRIC_RETINA = "unlabeled images scored/sec (RetinaNet R50-FPN, 800x1333)"
-WORKLOAD_RETINA = "RetinaNet R50-FPN nc=91, synthetic 1333x800 pool, 1 ref + 4 aug (F,C,D,R) forwards per image"
+BASE_IMAGES = 32
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", 1394.2), d.get("hbm_gbs", 6482.7), "measured"
-    return 1400.0, 6650.0, "fallback"
+        return d.get("bf16_tflops_sustained", 1394.2), d.get("hbm_gbs", 6482.7), "MEASURED_PEAKS.json (sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -97,31 +118,42 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_pool(n, seed=0):
+class Pool:
+    """Deterministic synthetic pool: image i = base image (i mod 32) rolled by an i-dependent offset with an
+    i-dependent channel order -- distinct pixels for every index at a fraction of the cost of synthesising each."""
+
+    def __init__(self, h, w, seed):
+        from cald_b200 import synth
+        self.base = [synth.synth_image(seed * 100000 + i, h, w, 0) for i in range(BASE_IMAGES)]
+        self.perms = [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)]
+
+    def __call__(self, i):
+        b = self.base[i % BASE_IMAGES]
+        k = i // BASE_IMAGES
+        if k == 0:
+            return b
+        out = np.roll(b, ((37 * k) % b.shape[0], (101 * k) % b.shape[1]), axis=(0, 1))
+        return np.ascontiguousarray(out[:, :, list(self.perms[k % 6])])
+
+
+def planted(cfg):
     from cald_b200 import synth
-    return [synth.synth_image(i, H, W, seed) for i in range(n)]
+    if cfg["model"] == "retinanet":
+        return synth.planted_retinanet_weights(cfg["nc"], 0, cls_bias_shift=-11.0 if cfg["nc"] == 91 else -7.0)
+    return synth.planted_frcnn_weights(cfg["depth"], cfg["nc"], 0)
 
 
-def planted(model):
-    from cald_b200 import synth
-    if model == "retinanet":
-        return synth.planted_retinanet_weights(NUM_CLASSES, 0, cls_bias_shift=-11.0)
-    return synth.planted_frcnn_weights(50, NUM_CLASSES, 0)
-
-
-def oracle_forward_fn(model="frcnn"):
+def oracle_forward_fn(cfg):
     """CPU port (oracle/) of the reference path -- the checker, used here only as the timed CPU baseline."""
     import torch
-    from cald_b200 import synth
     from oracle import frcnn_oracle as fo
-    if model == "retinanet":
+    w = {k: torch.from_numpy(v) for k, v in planted(cfg).items()}
+    if cfg["model"] == "retinanet":
         from oracle import retina_oracle as ro
-        w = {k: torch.from_numpy(v) for k, v in planted(model).items()}
-        cfg = ro.Cfg(50, NUM_CLASSES, MIN_SIZE, MAX_SIZE)
-        return lambda x: ro.forward(x, w, cfg)
-    w = {k: torch.from_numpy(v) for k, v in synth.planted_frcnn_weights(50, NUM_CLASSES, 0).items()}
-    cfg = fo.Cfg(50, NUM_CLASSES, MIN_SIZE, MAX_SIZE)
-    return lambda x: fo.forward(x, w, cfg)
+        ocfg = ro.Cfg(cfg["depth"], cfg["nc"], cfg["size"][0], cfg["size"][1])
+        return lambda x: ro.forward(x, w, ocfg)
+    ocfg = fo.Cfg(cfg["depth"], cfg["nc"], cfg["size"][0], cfg["size"][1])
+    return lambda x: fo.forward(x, w, ocfg)
 
 
 def host_threads():
@@ -133,19 +165,20 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline(n_images, threads=None, model="frcnn"):
+def cpu_port_images_per_s(cfg, n_images, warm, seed):
     import torch
     from oracle import cald_oracle as co
-    torch.set_num_threads(threads or host_threads())
-    fwd = oracle_forward_fn(model)
-    imgs = make_pool(n_images + 1, seed=7)
+    torch.set_num_threads(host_threads())
+    fwd = oracle_forward_fn(cfg)
+    pool = Pool(cfg["hw"][0], cfg["hw"][1], seed)
     random.seed(0)
-    co.score_image(fwd, imgs[0][:200, :334].copy(), AUGS, NUM_CLASSES, 1.3)  # warm-up on a small crop
+    for i in range(warm):
+        co.score_image(fwd, pool(i), cfg["augs"], cfg["nc"], 1.3)
     t = time.time()
-    for im in imgs[1:]:
-        co.score_image(fwd, im, AUGS, NUM_CLASSES, 1.3)
+    for i in range(warm, warm + n_images):
+        co.score_image(fwd, pool(i), cfg["augs"], cfg["nc"], 1.3)
     dt = time.time() - t
-    return n_images / dt, torch.get_num_threads()
+    return n_images / dt, dt, torch.get_num_threads()
 
 
 _JSON_FD = None
@@ -167,33 +200,31 @@ def emit(obj):
     os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(obj) + "\n").encode())
 
 
-def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+def common_config(cfg, args):
+    """The `config` object, identical in both arms (the arms describe their own batching elsewhere)."""
+    return {"workload": cfg["workload"], "baseline_config_index": cfg["idx"], "views_per_image": 1 + len(cfg["augs"]),
+            "augmentations": cfg["augs"], "num_classes": cfg["nc"], "image_hw": list(cfg["hw"]),
+            "min_max_size": list(cfg["size"]), "mode": args.mode,
+            "l2": "every step scores images no earlier step has seen; the activations of one step (>10 GB) exceed the "
+                  "126 MB L2 many times over"}
+
+
+def run_reference(args, cfg, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the same ATen CPU kernels in the
+    same order as cald_train.get_uncertainty, profiles/r02_cpu_port_vs_reference.md), all host threads."""
     if rank != 0:
         return
-    import torch
-    from oracle import cald_oracle as co
-    torch.set_num_threads(host_threads())
-    fwd = oracle_forward_fn(args.model)
-    imgs = make_pool(args.warmup + args.steps, seed=11)
-    random.seed(0)
-    for im in imgs[:args.warmup]:
-        co.score_image(fwd, im, AUGS, NUM_CLASSES, 1.3)
-    t = time.time()
-    for im in imgs[args.warmup:]:
-        co.score_image(fwd, im, AUGS, NUM_CLASSES, 1.3)
-    dt = time.time() - t
-    v = args.steps / dt
-    cores = torch.get_num_threads()
-    sample = "%d images (1 per step), oracle port of cald_train.get_uncertainty on torch CPU fp32" % args.steps
-    emit(({
-        "impl": "reference", "metric": METRIC_RETINA if args.model == "retinanet" else METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
+    v, dt, cores = cpu_port_images_per_s(cfg, args.steps, args.warmup, seed=11)
+    sample = "%d images (1 per step, %d warm-up), oracle port of cald_train.get_uncertainty on torch CPU fp32" % (
+        args.steps, args.warmup)
+    emit({
+        "impl": "reference", "metric": cfg["metric"], "value": v, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_RETINA if args.model == "retinanet" else WORKLOAD, "images_per_step": 1},
+        "higher_is_better": True, "scaling": "weak" if args.mode == "weak" else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": common_config(cfg, args),
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
@@ -203,21 +234,31 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=16, help="images per step per GPU")
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--model", default="frcnn", choices=["frcnn", "retinanet"],
-                    help="frcnn = BASELINE.json configs[1] (the headline); retinanet = configs[2]")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="BASELINE.json configuration (default cfg2)")
+    ap.add_argument("--model", default=None, choices=["frcnn", "retinanet"], help="shorthand: retinanet = --config cfg3")
+    ap.add_argument("--mode", default=None, choices=["weak", "cycle"],
+                    help="weak: every rank scores its own --batch images per step (default); cycle: one fixed pool of "
+                         "--pool images sharded over the ranks + all-gather + host selection (default for cfg5)")
+    ap.add_argument("--pool", type=int, default=0, help="cycle mode: pool size (default 128 images per GPU-step budget)")
+    ap.add_argument("--budget", type=int, default=0, help="cycle mode: images to select (default pool / 8, cfg-5: 1000)")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-images", type=int, default=1)
+    ap.add_argument("--cpu-images", type=int, default=5)
     ap.add_argument("--workspace-gb", type=float, default=0.0, help="device arena size (0 = half of free memory)")
+    ap.add_argument("--views-per-pass", type=int, default=0, help="engine max_views_per_pass (0 = the engine's own auto)")
     ap.add_argument("--layers", default=None, help="write the per-layer conv timing table (TSV) to this path")
     args = ap.parse_args()
+    name = args.config or ("cfg3" if args.model == "retinanet" else "cfg2")
+    cfg = CONFIGS[name]
+    if args.mode is None:
+        args.mode = "cycle" if name == "cfg5" else "weak"
 
     claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, cfg, rank)
         return
 
     import torch
@@ -229,64 +270,85 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from cald_b200 import api, synth
+    from cald_b200 import api, shard
     from cald_b200.engine import Engine, PREC_BF16, PREC_BF16X3, ARCH_FRCNN, ARCH_RETINANET, expand_augs
+    AUGS = cfg["augs"]
+    H, W = cfg["hw"]
     kinds = expand_augs(AUGS)
-    retina = args.model == "retinanet"
-    eng = Engine(depth=50, num_classes=NUM_CLASSES, min_size=MIN_SIZE, max_size=MAX_SIZE, device=local_rank,
-                 precision=PREC_BF16 if args.precision == "bf16" else PREC_BF16X3,
-                 max_views_per_pass=args.batch * len(AUGS), arch_id=ARCH_RETINANET if retina else ARCH_FRCNN,
+    retina = cfg["model"] == "retinanet"
+    # the engine is built the way the drop-in builds it (api.engine_for): views per pass come from the engine's own
+    # sizing unless --views-per-pass overrides it
+    eng = Engine(depth=cfg["depth"], num_classes=cfg["nc"], min_size=cfg["size"][0], max_size=cfg["size"][1],
+                 device=local_rank, precision=PREC_BF16 if args.precision == "bf16" else PREC_BF16X3,
+                 max_views_per_pass=args.views_per_pass, arch_id=ARCH_RETINANET if retina else ARCH_FRCNN,
                  workspace_bytes=int(args.workspace_gb * (1 << 30)))
-    eng.load_state_dict(planted(args.model))
-
-    B = args.batch
-    n_steps_total = args.warmup + args.steps
-    # every rank scores its own shard of the pool (distinct images per step; weak scaling)
-    # host pool in page-locked memory (the e2e leg copies from it every step); device copy for the resident leg
-    pinned = [torch.from_numpy(synth.synth_image(rank * 100000 + i, H, W, 0)).pin_memory()
-              for i in range(B * min(n_steps_total, 4))]
-    pool = [t.numpy() for t in pinned]
-    dev_pool = [t.cuda() for t in pinned]
-
-    def step_images(s):
-        idx = [(s * B + j) % len(pool) for j in range(B)]
-        return idx
-
-    def uniforms(s):
-        rs = np.random.RandomState(1234 + s)
-        return rs.random_sample(200 * B)
+    eng.load_state_dict(planted(cfg))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident run: value + roofline
-    for s in range(args.warmup):
-        idx = step_images(s)
-        eng.score_device([dev_pool[i].data_ptr() for i in idx], [H] * B, [W] * B, kinds, 1.3, uniforms(s))
-    barrier()
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    if args.mode == "cycle":
+        run_cycle(args, cfg, eng, rank, local_rank, world, barrier, max_over_ranks)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    B = args.batch
+    n_steps_total = args.warmup + args.steps
+    # every rank scores its own shard of the pool: distinct images for every step (weak scaling).  Host copies in
+    # page-locked memory (e2e leg) and in ordinary pageable memory (e2e.pageable); a device copy for the resident legs.
+    make = Pool(H, W, seed=rank + 1)
+    pinned = [torch.from_numpy(make(i)).pin_memory() for i in range(B * n_steps_total)]
+    pool = [t.numpy() for t in pinned]
+    dev_pool = [t.cuda() for t in pinned]
+
+    def step_images(s):
+        return list(range(s * B, (s + 1) * B))
+
+    def uniforms(s):
+        return np.random.RandomState(1234 + s).random_sample(200 * B)
+
+    def resident_pass(instrument):
+        for s in range(args.warmup):
+            idx = step_images(s)
+            eng.score_device([dev_pool[i].data_ptr() for i in idx], [H] * B, [W] * B, kinds, 1.3, uniforms(s))
+        barrier()
+        eng.profile(instrument)
+        k0, _ = eng.counters()
+        eng.event_record(0)
+        scores = []
+        for s in range(args.warmup, n_steps_total):
+            idx = step_images(s)
+            c, v, _ = eng.score_device([dev_pool[i].data_ptr() for i in idx], [H] * B, [W] * B, kinds, 1.3, uniforms(s))
+            scores.append(c)
+        if world > 1:
+            # the path's single collective: all-gather of the per-image scores
+            t = torch.tensor(np.concatenate(scores), device="cuda")
+            out = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(out, t)
+        eng.event_record(1)
+        barrier()
+        ms = max_over_ranks(eng.event_elapsed_ms(0, 1))
+        k1, _ = eng.counters()
+        return ms, int(k1 - k0)
+
+    # ---------------- leg 1: value (not instrumented)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    eng.profile(True)
-    k0, _ = eng.counters()
-    eng.event_record(0)
-    scores = []
-    for s in range(args.warmup, n_steps_total):
-        idx = step_images(s)
-        c, v, _ = eng.score_device([dev_pool[i].data_ptr() for i in idx], [H] * B, [W] * B, kinds, 1.3, uniforms(s))
-        scores.append(c)
-    gathered = None
-    if world > 1:
-        # the path's single collective: all-gather of the per-image scores
-        t = torch.tensor(np.concatenate(scores), device="cuda")
-        out = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(out, t)
-        gathered = torch.cat(out)
-    eng.event_record(1)
-    barrier()
-    ms = eng.event_elapsed_ms(0, 1)
-    k1, _ = eng.counters()
+    ms, launches = resident_pass(False)
+    clocks = sampler.stop()
+    value = world * B * args.steps / (ms / 1000.0)
+    # ---------------- leg 2: the same steps with per-launch CUDA events on the conv kernels (roofline)
+    ms_instr, _ = resident_pass(True)
     conv_ms, conv_launches, conv_flops = eng.profile_read()
     conv_bytes = sum(r[4] for r in eng.profile_layers()) * 1e6  # algorithmic HBM bytes of the timed conv launches
     if args.layers and rank == 0:
@@ -298,34 +360,29 @@ def main():
                     sig, cnt, lms, 1000.0 * lms / cnt, gf / lms if lms else 0, mb / lms if lms else 0,
                     lms / conv_ms if conv_ms else 0))
     eng.profile(False)
-    clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world * B * args.steps / (ms / 1000.0)
 
-    # ---------------- end-to-end run through the public API with host buffers
-    barrier()
-    for s in range(min(2, args.warmup)):  # warm the host-buffer path (pinned staging, first-touch)
-        random.seed(1000 + s)
-        api.score_images(eng, [pool[i] for i in step_images(s)], AUGS, chunk=B)
-    barrier()
-    t_wall = time.time()
-    eng.event_record(2)
-    for s in range(args.warmup, n_steps_total):
-        idx = step_images(s)
-        random.seed(s)
-        api.score_images(eng, [pool[i] for i in idx], AUGS, chunk=B)
-    eng.event_record(3)
-    barrier()
-    t_wall = time.time() - t_wall
-    ms_e2e = max(eng.event_elapsed_ms(2, 3), 1000.0 * t_wall)  # the call is synchronous: wall clock bounds it too
-    if world > 1:
-        t = torch.tensor([ms_e2e], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    e2e = world * B * args.steps / (ms_e2e / 1000.0)
+    # ---------------- legs 3 + 4: end to end through the public API with host buffers (page-locked, then pageable)
+    def e2e_pass(images):
+        barrier()
+        for s in range(min(2, args.warmup)):  # warm the host-buffer path (staging buffers, first touch)
+            random.seed(1000 + s)
+            api.score_images(eng, [images[i] for i in step_images(s)], AUGS, chunk=B)
+        barrier()
+        t_wall = time.time()
+        eng.event_record(2)
+        for s in range(args.warmup, n_steps_total):
+            random.seed(s)
+            api.score_images(eng, [images[i] for i in step_images(s)], AUGS, chunk=B)
+        eng.event_record(3)
+        barrier()
+        t_wall = time.time() - t_wall
+        # the call is synchronous: wall clock bounds it too
+        return world * B * args.steps / (max_over_ranks(max(eng.event_elapsed_ms(2, 3), 1000.0 * t_wall)) / 1000.0)
+
+    e2e = e2e_pass(pool)
+    pageable = [np.array(a, copy=True) for a in pool[:B * n_steps_total]]
+    e2e_pageable = e2e_pass(pageable)
+    del pageable
 
     if rank != 0:
         if world > 1:
@@ -333,41 +390,104 @@ def main():
         return
     peak_tf, peak_hbm, peak_src = peaks()
     achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
+    A = len(AUGS)
     out = {
-        "metric": METRIC_RETINA if retina else METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "metric": cfg["metric"], "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split-bf16, fp32 accumulate)",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD_RETINA if retina else WORKLOAD, "images_per_step_per_gpu": B, "views_per_image": 1 + len(AUGS),
-                   "precision": args.precision,
-                   "l2": "working set per step (activations of %d views, >10 GB) far exceeds the 126 MB L2; "
-                         "each step scores different images" % (B * (1 + len(AUGS)))},
-        "gpu_launches": int(k1 - k0),
+        "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f16x3 (split-half operands: 22-bit significand, fp32 accumulate)",
+        "data": "synthetic", "config": common_config(cfg, args),
+        "engine": {"images_per_step_per_gpu": B, "views_per_pass": eng.views_per_pass(), "precision": args.precision,
+                   "arena_peak_gb": eng.arena_peak() / 2 ** 30,
+                   "value_instrumented": world * B * args.steps / (ms_instr / 1000.0)},
+        "gpu_launches": launches,
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3 + 200 * B * 8,
-                "d2h_bytes_per_step": B * (len(AUGS) + (1 + len(AUGS)) * (NUM_CLASSES - 1) + 1) * 4 + 4},
+                "d2h_bytes_per_step": B * (A + (1 + A) * (cfg["nc"] - 1) + 1) * 4 + 4,
+                "host_memory": "page-locked", "pageable": {"value": e2e_pageable, "unit": "images/s"}},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None,
-                     "frac_of_bf16x3_ceiling": 3.0 * achieved / peak_tf if peak_tf else None,
-                     "traffic": NCU_DRAM_BYTES_PER_CONV_LAUNCH if (not retina and B == NCU_DRAM_BATCH) else None,
-                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, mean over the 142 conv "
-                                     "launches of one step; profiles/r01_igemm_dram_step.csv)",
+                     "frac_of_x3_ceiling": 3.0 * achieved / peak_tf if peak_tf else None,
+                     "traffic": NCU_DRAM_BYTES_PER_CONV_LAUNCH if (name == "cfg2" and B == NCU_DRAM_BATCH) else None,
+                     "traffic_source": "offline ncu constant (dram__bytes_read+write per launch, mean over the conv "
+                                       "launches of one step): " + NCU_DRAM_SOURCE,
                      "algorithmic_bytes_per_launch": conv_bytes / conv_launches if conv_launches else None,
-                     "kernel": "igemm_tc_kernel + igemm_tc2_kernel (tcgen05 implicit-GEMM conv/GEMM: one-CTA and CTA-pair cta_group::2 instantiations)",
+                     "kernel": "igemm_tc_kernel + igemm_tc2_kernel (tcgen05 implicit-GEMM conv/GEMM: one-CTA and "
+                               "CTA-pair cta_group::2 instantiations)",
                      "launches": int(conv_launches), "kernel_ms_per_step": conv_ms / args.steps,
                      "algorithmic_gflop_per_step": conv_flops / args.steps / 1e9,
-                     "share_of_step": conv_ms / ms if ms else None, "peak_source": peak_src,
+                     "share_of_step": conv_ms / ms_instr if ms_instr else None, "peak_source": peak_src,
                      "note": "achieved = algorithmic 2*MAC of the reference convs/GEMMs / summed CUDA-event kernel "
-                             "time; the fp32-faithful bf16x3 arithmetic issues 3 tensor-core MACs per algorithmic MAC, "
-                             "so the kernel's own ceiling is peak/3"},
+                             "time of the instrumented pass; the fp32-faithful split arithmetic issues 3 tensor-core "
+                             "MACs per algorithmic MAC, so the kernel's own ceiling is peak/3"},
     }
     if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
-        v, cores = cpu_baseline(args.cpu_images, model=args.model)
+        v, dt, cores = cpu_port_images_per_s(cfg, args.cpu_images, warm=1, seed=7)
         out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                               "sample": "%d image(s) of the same workload, oracle port (torch CPU fp32)" % args.cpu_images}
+                               "sample": "%d images of the same workload after 1 warm-up image (%.0f s), oracle port "
+                                         "(torch CPU fp32)" % (args.cpu_images, dt)}
     emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_cycle(args, cfg, eng, rank, local_rank, world, barrier, max_over_ranks):
+    """One selection cycle over a FIXED pool (strong scaling), through the product's own multi-GPU path:
+    shard.get_uncertainty_sharded (round-robin shard, chunked scoring from host images, one all-gather, un-permute)
+    followed by the host selection api.select (argsort -> 1.2 x budget candidates -> cls_kldiv)."""
+    import torch
+    from cald_b200 import api, shard
+    AUGS = cfg["augs"]
+    H, W = cfg["hw"]
+    P = args.pool or 128 * args.steps
+    budget = args.budget or (1000 if P >= 2400 else max(1, P // 8))
+    make = Pool(H, W, seed=1)          # the same pool on every rank; a rank only touches its own shard
+    # the loader stand-in: this rank's shard decoded into (pageable) host memory before the clock starts, like images
+    # handed over by DataLoader workers; fetching one inside the timed region is a dictionary lookup
+    mine = {int(i): make(int(i)) for i in shard.shard_indices(P, rank, world)}
+    fetch = lambda i: mine[i]  # noqa: E731
+    rs = np.random.RandomState(3)
+    labeled = [((None,), ({"labels": torch.from_numpy(rs.randint(1, cfg["nc"], rs.randint(1, 8)))},)) for _ in range(500)]
+    subset = list(range(10 ** 6, 10 ** 6 + P))
+    random.seed(17 + rank)
+    for s in range(args.warmup):       # warm-up: a few chunks outside the timed region
+        api.score_images(eng, [make(P + s * args.batch + j) for j in range(args.batch)], AUGS, chunk=args.batch)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.time()
+    eng.event_record(0)
+    cons, cls = shard.get_uncertainty_sharded(eng, fetch, AUGS, rank, world, n=P, chunk=4 * args.batch)
+    eng.event_record(1)
+    t_score = time.time() - t0
+    t1 = time.time()
+    picked = api.select(cons, cls, subset, labeled, budget)
+    t_select = time.time() - t1
+    barrier()
+    clocks = sampler.stop()
+    # the cycle is host-synchronous: wall clock of score + gather + select, max over ranks
+    ms = max_over_ranks(1000.0 * (t_score + t_select))
+    ms_select = max_over_ranks(1000.0 * t_select)
+    if rank != 0:
+        return
+    k, _ = eng.counters()
+    emit({
+        "metric": cfg["metric"], "value": P / (ms / 1000.0), "unit": "images/s", "n_gpus": world,
+        "steps": (P + world * args.batch - 1) // (world * args.batch), "warmup": args.warmup,
+        "ms_per_step": ms / max(1, (P + world * args.batch - 1) // (world * args.batch)), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16x3 (split-half operands: 22-bit significand, fp32 accumulate)", "data": "synthetic",
+        "config": common_config(cfg, args),
+        "engine": {"images_per_chunk_per_gpu": args.batch, "views_per_pass": eng.views_per_pass()},
+        "cycle": {"pool": P, "budget": budget, "selected": len(picked), "score_gather_ms": 1000.0 * t_score,
+                  "select_host_ms": ms_select, "select_share": ms_select / ms,
+                  "note": "the rank's shard sits decoded in pageable host memory (loader stand-in); the timed region "
+                          "uploads, scores, all-gathers and selects; select = argsort + cls_kldiv on every rank's "
+                          "copy of the gathered rows"},
+        "gpu_launches": int(k), "clocks": clocks,
+        "e2e": {"value": P / (ms / 1000.0), "unit": "images/s", "h2d_bytes_per_step": args.batch * H * W * 3,
+                "d2h_bytes_per_step": args.batch * (len(AUGS) + (1 + len(AUGS)) * (cfg["nc"] - 1) + 1) * 4},
+    })
 
 
 if __name__ == "__main__":

@@ -11,9 +11,9 @@ and, on the same engine, the detection-only baselines and the evaluation forward
 Everything below these calls runs in hand-written sm_100a CUDA behind libcald_b200.so.
 """
 from .api import (get_uncertainty, select, cls_kldiv, score_images, engine_for, lt_c_uncertainty,  # noqa: F401
-                  close_engines,
+                  close_engines, get_uncertainty_files,
                   ls_c_uncertainty, EngineModel)
 from .engine import Engine  # noqa: F401
 
 __all__ = ["get_uncertainty", "select", "cls_kldiv", "score_images", "engine_for", "Engine", "lt_c_uncertainty",
-           "ls_c_uncertainty", "EngineModel", "close_engines"]
+           "ls_c_uncertainty", "EngineModel", "close_engines", "get_uncertainty_files"]

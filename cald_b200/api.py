@@ -169,6 +169,61 @@ def score_images(eng, images, augs, chunk=None):
     return cons_all, cls_all
 
 
+def get_uncertainty_files(task_model, paths, augs, num_cls, device=0, **engine_kw):
+    """get_uncertainty over a pool given as JPEG FILE PATHS (or bytes objects) instead of a DataLoader of PIL images:
+    the pool ingest of SURVEY.md 8(f).  Replaces ``Image.open(path).convert('RGB')`` on DataLoader workers
+    (detection/voc_utils.py:52-58, coco_utils.py:209-220): the files are read on the host, decoded on the device (bit
+    for bit Pillow's pixels) and scored, in loader (= list) order.  Same return value as get_uncertainty.  Consumes
+    python's ``random`` stream like the reference (cutout, ColorSwap); the noise augmentations need a PIL-side image
+    size before drawing and are only available through get_uncertainty."""
+    eng = engine_for(task_model, num_cls, device, **engine_kw)
+    views = _aug_kinds(augs)
+    if any(k in _eng.NOISE_KINDS for k, _ in views):
+        raise ValueError("noise augmentations ('ga', 'sp', ...) are not available on the file path; use get_uncertainty")
+    n_cut = sum(1 for k, _ in views if k == _eng.AUG_CUTOUT)
+    n_swap = sum(1 for k, _ in views if k == _eng.AUG_COLOR_SWAP)
+    group = 1 if (n_swap and n_cut) else 4 * eng.images_per_chunk(max(1, len(views)))
+
+    def read(p):
+        if isinstance(p, (bytes, bytearray, memoryview)):
+            return bytes(p)
+        with open(p, "rb") as f:
+            return f.read()
+    cons_all, cls_all = [], []
+    batches = ([read(p) for p in paths[i:i + group]] for i in range(0, len(paths), group))
+    for files in _prefetched(batches, 2):
+        pos = 0
+        while pos < len(files):
+            part = files[pos:]
+            marks = [None] * len(part)
+            swaps = []
+            for i in range(len(part)):
+                if n_swap:
+                    marks[i] = random.getstate()
+                    swaps += [random.randint(0, 5) for _ in range(n_swap)]
+            u = None
+            if n_cut:
+                state = random.getstate()
+                u = np.array([random.random() for _ in range(200 * n_cut * len(part))], dtype=np.float64)
+            cons, cls, used, _, _ = eng.score_jpeg(part, views, bp, u, swaps if n_swap else None)
+            if n_cut:
+                random.setstate(state)
+                for _ in range(used):
+                    random.random()
+            good = len(part)
+            if n_swap:   # rewind over an image without reference detections (see score_images)
+                ref_counts = eng.last_ref_counts(len(part))
+                for i in range(len(part)):
+                    if ref_counts[i] == 0:
+                        random.setstate(marks[i])
+                        good = i + 1
+                        break
+            cons_all.extend(float(c) for c in cons[:good])
+            cls_all.extend(np.array(r, dtype=np.float64) for r in cls[:good])
+            pos += good
+    return cons_all, cls_all
+
+
 def _prefetched(iterable, depth):
     """Iterate ``iterable`` in a background thread, ``depth`` items ahead (the C call releases the GIL, so the
     DataLoader's collation / PIL decode of the next images overlaps the current scoring pass)."""

@@ -12,6 +12,7 @@
 #include "pre.cuh"
 #include "cons.cuh"
 #include "ret.cuh"
+#include "jpeg.cuh"
 #include "../../include/cald_b200.h"
 
 using namespace cald;
@@ -1027,22 +1028,24 @@ extern "C" int cald_op_color_adjust(const uint8_t* img, int h, int w, double fac
 
 namespace {
 // Pillow-exact resize of a device u8 image (horizontal pass then vertical pass).
-uint8_t* pil_resize_device(cald_engine* e, const uint8_t* src, int h, int w, int oh, int ow, int filter) {
-  Arena& ar = e->arena;
-  cudaStream_t st = e->st;
-  auto coeffs = [&](int in, int out, int*& d_bounds, int*& d_kk, int& ksize) {
+// A real pool has thousands of distinct image sizes: the coefficient cache is emptied once it holds PIL_CACHE_MAX
+// tables.  Called at the start of a chunk only (tables handed out during a chunk stay valid until its kernels are
+// enqueued) and after draining the stream (earlier kernels may still read them).
+void pil_cache_trim(cald_engine* e) {
+  constexpr size_t PIL_CACHE_MAX = 256;
+  if (e->pil_cache.size() < PIL_CACHE_MAX) return;
+  CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  for (auto& kv : e->pil_cache) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+  e->pil_cache.clear();
+  e->pil_ksize.clear();
+}
+
+// device coefficient tables of one Pillow resampling pass (cached per (in, out, filter))
+void pil_coeffs(cald_engine* e, int in, int out, int filter, int*& d_bounds, int*& d_kk, int& ksize) {
+  {
     long long key = ((long long)in << 34) | ((long long)out << 4) | filter;
     auto it = e->pil_cache.find(key);
     if (it == e->pil_cache.end()) {
-      // a real pool has thousands of distinct image sizes: keep at most PIL_CACHE_MAX coefficient tables.  Tables
-      // may still be read by enqueued kernels, so the cache is only flushed after the stream has drained.
-      constexpr size_t PIL_CACHE_MAX = 256;
-      if (e->pil_cache.size() >= PIL_CACHE_MAX) {
-        CALD_CUDA_CHECK(cudaStreamSynchronize(st));
-        for (auto& kv : e->pil_cache) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
-        e->pil_cache.clear();
-        e->pil_ksize.clear();
-      }
       PilCoeffs pc = pil_precompute(in, out, filter);
       int *b, *k;
       CALD_CUDA_CHECK(cudaMalloc((void**)&b, pc.bounds.size() * 4));
@@ -1056,6 +1059,14 @@ uint8_t* pil_resize_device(cald_engine* e, const uint8_t* src, int h, int w, int
     d_bounds = it->second.first;
     d_kk = it->second.second;
     ksize = e->pil_ksize[key];
+  }
+}
+
+uint8_t* pil_resize_device(cald_engine* e, const uint8_t* src, int h, int w, int oh, int ow, int filter) {
+  Arena& ar = e->arena;
+  cudaStream_t st = e->st;
+  auto coeffs = [&](int in, int out, int*& d_bounds, int*& d_kk, int& ksize) {
+    pil_coeffs(e, in, out, filter, d_bounds, d_kk, ksize);
   };
   const uint8_t* cur = src;
   uint8_t* tmp = nullptr;
@@ -1132,6 +1143,7 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
   std::vector<HostView> rv(B);
   for (int b = 0; b < B; ++b) rv[b] = HostView{d_images[b], hs[b], ws[b], 0, -1};
   ViewSet ref = alloc_viewset(e, B);
+  pil_cache_trim(e);
   e->trace("chunk_start");
   detect_views(e, rv, nullptr, ref);
   e->trace("ref_pass_enqueued");
@@ -1196,6 +1208,26 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
   std::vector<HostView> av((size_t)B * A);
   std::vector<AugGeom> geom((size_t)B * A);
   std::vector<uint8_t*> temps;
+  // Pillow-exact resize / rotate of the whole chunk in three launches (nearest rotate, horizontal pass, vertical pass)
+  std::vector<RotJob> rot_jobs;
+  std::vector<PilJob> h_jobs, v_jobs;
+  std::vector<uint8_t*> pil_scratch;
+  // two-pass resample src (h x w) -> (oh x ow) queued as one horizontal and one vertical job; returns the output
+  auto queue_resize = [&](const uint8_t* src, int h, int w, int oh, int ow, int filter) -> uint8_t* {
+    if (ow == w || oh == h) return nullptr;  // a pass Pillow would skip: the per-image path handles it
+    uint8_t* tmp = (uint8_t*)ar.alloc((size_t)h * ow * 3);
+    uint8_t* out = (uint8_t*)ar.alloc((size_t)oh * ow * 3);
+    pil_scratch.push_back(tmp);
+    PilJob hj{src, tmp, h, w, h, ow, nullptr, nullptr, 0}, vj{tmp, out, h, ow, oh, ow, nullptr, nullptr, 0};
+    int *b, *k, ks;
+    pil_coeffs(e, w, ow, filter, b, k, ks);
+    hj.bounds = b; hj.kk = k; hj.ksize = ks;
+    pil_coeffs(e, h, oh, filter, b, k, ks);
+    vj.bounds = b; vj.kk = k; vj.ksize = ks;
+    h_jobs.push_back(hj);
+    v_jobs.push_back(vj);
+    return out;
+  };
   for (int b = 0; b < B; ++b) {
     int cut_i = 0, noise_i = 0, swap_i = 0;
     for (int a = 0; a < A; ++a) {
@@ -1211,7 +1243,8 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
           g.kind = AUG_RESIZE;
           g.ratio = (float)prm;
           int ow = (int)(ws[b] * prm), oh = (int)(hs[b] * prm);
-          uint8_t* t = pil_resize_device(e, d_images[b], hs[b], ws[b], oh, ow, 0);
+          uint8_t* t = queue_resize(d_images[b], hs[b], ws[b], oh, ow, 0);
+          if (!t) t = pil_resize_device(e, d_images[b], hs[b], ws[b], oh, ow, 0);
           temps.push_back(t);
           hv.src = t; hv.sh = oh; hv.sw = ow;
           break;
@@ -1220,10 +1253,16 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
           g.kind = AUG_ROTATE;
           RotateGeom rg = pil_rotate_geom(ws[b], hs[b], prm);
           uint8_t* r = (uint8_t*)ar.alloc((size_t)rg.nh * rg.nw * 3);
-          pil_rotate_nearest_kernel<<<dim3((rg.nw + 127) / 128, rg.nh), 128, 0, st>>>(d_images[b], r, ws[b], hs[b], rg);
-          KLAUNCH(e);
-          uint8_t* t = pil_resize_device(e, r, rg.nh, rg.nw, hs[b], ws[b], 1);
-          ar.free(r);
+          uint8_t* t = queue_resize(r, rg.nh, rg.nw, hs[b], ws[b], 1);
+          if (t) {
+            rot_jobs.push_back(RotJob{d_images[b], r, ws[b], hs[b], rg});
+            pil_scratch.push_back(r);
+          } else {
+            pil_rotate_nearest_kernel<<<dim3((rg.nw + 127) / 128, rg.nh), 128, 0, st>>>(d_images[b], r, ws[b], hs[b], rg);
+            KLAUNCH(e);
+            t = pil_resize_device(e, r, rg.nh, rg.nw, hs[b], ws[b], 1);
+            ar.free(r);
+          }
           temps.push_back(t);
           hv.src = t;
           rotate_box_geom(ws[b], hs[b], prm, rg.nw, rg.nh, g);
@@ -1274,6 +1313,29 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
       }
       av[(size_t)b * A + a] = hv;
     }
+  }
+  if (!h_jobs.empty()) {
+    const size_t nr = rot_jobs.size(), nj = h_jobs.size();
+    RotJob* d_rot = nr ? (RotJob*)ar.alloc(nr * sizeof(RotJob)) : nullptr;
+    PilJob* d_hv = (PilJob*)ar.alloc(2 * nj * sizeof(PilJob));
+    if (nr) CALD_CUDA_CHECK(cudaMemcpyAsync(d_rot, rot_jobs.data(), nr * sizeof(RotJob), cudaMemcpyHostToDevice, st));
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d_hv, h_jobs.data(), nj * sizeof(PilJob), cudaMemcpyHostToDevice, st));
+    CALD_CUDA_CHECK(cudaMemcpyAsync(d_hv + nj, v_jobs.data(), nj * sizeof(PilJob), cudaMemcpyHostToDevice, st));
+    int rw = 0, rh = 0, hw = 0, hh = 0, vw = 0, vh = 0;
+    for (const RotJob& j : rot_jobs) { rw = std::max(rw, j.g.nw); rh = std::max(rh, j.g.nh); }
+    for (const PilJob& j : h_jobs) { hw = std::max(hw, j.out_w); hh = std::max(hh, j.in_h); }
+    for (const PilJob& j : v_jobs) { vw = std::max(vw, j.in_w); vh = std::max(vh, j.out_h); }
+    if (nr) {
+      pil_rotate_nearest_batched_kernel<<<dim3((rw + 127) / 128, rh, (unsigned)nr), 128, 0, st>>>(d_rot);
+      KLAUNCH(e);
+    }
+    pil_resample_h_batched_kernel<<<dim3((hw * 3 + 255) / 256, hh, (unsigned)nj), 256, 0, st>>>(d_hv);
+    pil_resample_v_batched_kernel<<<dim3((vw * 3 + 255) / 256, vh, (unsigned)nj), 256, 0, st>>>(d_hv + nj);
+    CALD_CUDA_CHECK(cudaGetLastError());
+    e->launches += 2;
+    if (d_rot) ar.free(d_rot);
+    ar.free(d_hv);
+    for (uint8_t* t : pil_scratch) ar.free(t);  // stream-ordered reuse: the passes above are enqueued
   }
   ViewSet aug;
   float* d_cons = nullptr;
@@ -1405,64 +1467,163 @@ struct DeviceImages {
 struct UploadPipe {
   cald_engine* e;
   int n_images, per_chunk;
-  const uint8_t* const* imgs;
+  const uint8_t* const* imgs;   // raw mode: u8 HWC images; JPEG mode: the files
   const int* hs;
   const int* ws;
   uint8_t* slab[2] = {nullptr, nullptr};
   size_t slab_bytes = 0;
   bool all_pinned = true;
   int started = 0;  // chunks whose copy has been enqueued
+  // ---- JPEG mode (pool ingest, jpeg.cuh): the compressed scans travel instead of pixels and the chunk is decoded
+  //      into its slab by three kernels on the copy stream, concurrently with the previous chunk's forward passes
+  bool jpeg = false;
+  std::vector<JpegImage> meta;                 // per file, offsets relative to its chunk
+  std::vector<std::vector<JpegHuff>> tabs;     // per file
+  std::vector<size_t> scan_begin, scan_end;
+  std::vector<int> jh, jw;
+  size_t cap_bytes = 0, cap_coef = 0, cap_planes = 0, cap_tabs = 0;
+  uint8_t* d_bytes[2] = {nullptr, nullptr};
+  JpegImage* d_meta[2] = {nullptr, nullptr};
+  JpegHuff* d_tabs[2] = {nullptr, nullptr};
+  short* d_coef[2] = {nullptr, nullptr};
+  uint8_t* d_planes[2] = {nullptr, nullptr};
+  std::vector<JpegImage> h_meta[2];            // host copies must outlive the async H2D of their slot
+  std::vector<JpegHuff> h_tabs[2];
 
   static size_t padded(int h, int w) { return ((size_t)h * w * 3 + 255) & ~(size_t)255; }
   int n_chunks() const { return (n_images + per_chunk - 1) / per_chunk; }
 
   // Both slabs are taken from the arena before anything else of the call and live until its end: arena blocks freed
   // and re-used during the call are only ordered on the compute stream, never against the copy stream.
-  UploadPipe(cald_engine* eng, int n, const uint8_t* const* images, const int* heights, const int* widths, int chunk)
+  UploadPipe(cald_engine* eng, int n, const uint8_t* const* images, const int* heights, const int* widths, int chunk,
+             const size_t* file_sizes = nullptr)
       : e(eng), n_images(n), per_chunk(std::max(1, chunk)), imgs(images), hs(heights), ws(widths) {
+    jpeg = file_sizes != nullptr;
+    if (jpeg) {
+      meta.resize(n); tabs.resize(n); scan_begin.resize(n); scan_end.resize(n); jh.resize(n); jw.resize(n);
+      for (int i = 0; i < n; ++i) {
+        try {
+          jpeg_parse(images[i], file_sizes[i], meta[i], tabs[i], scan_begin[i], scan_end[i]);
+        } catch (const std::exception& ex) {
+          throw std::runtime_error("file " + std::to_string(i) + ": " + ex.what());
+        }
+        jh[i] = meta[i].height; jw[i] = meta[i].width;
+      }
+      hs = jh.data(); ws = jw.data();
+    }
     for (int c = 0; c < n_chunks(); ++c) {
-      size_t b = 0;
-      for (int i = c * per_chunk; i < std::min(n, (c + 1) * per_chunk); ++i) b += padded(hs[i], ws[i]);
+      size_t b = 0, cb = 0, cc = 0, cp = 0, ct = 0;
+      for (int i = c * per_chunk; i < std::min(n, (c + 1) * per_chunk); ++i) {
+        b += padded(hs[i], ws[i]);
+        if (jpeg) {
+          cb += (scan_end[i] - scan_begin[i] + 15) & ~(size_t)15;
+          for (int k = 0; k < meta[i].ncomp; ++k) {
+            const size_t blocks = (size_t)meta[i].comp[k].blocks_w * meta[i].comp[k].blocks_h;
+            cc += blocks * 64;
+            cp += blocks * 64;
+          }
+          ct += tabs[i].size();
+        }
+      }
       slab_bytes = std::max(slab_bytes, b);
+      cap_bytes = std::max(cap_bytes, cb); cap_coef = std::max(cap_coef, cc);
+      cap_planes = std::max(cap_planes, cp); cap_tabs = std::max(cap_tabs, ct);
     }
-    for (int i = 0; i < n && all_pinned; ++i) {
-      cudaPointerAttributes at;
-      if (cudaPointerGetAttributes(&at, imgs[i]) != cudaSuccess) { cudaGetLastError(); all_pinned = false; break; }
-      all_pinned = (at.type == cudaMemoryTypeHost);
+    if (!jpeg) {
+      for (int i = 0; i < n && all_pinned; ++i) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, imgs[i]) != cudaSuccess) { cudaGetLastError(); all_pinned = false; break; }
+        all_pinned = (at.type == cudaMemoryTypeHost);
+      }
+    } else {
+      all_pinned = false;
     }
-    if (n > 0) {
-      slab[0] = (uint8_t*)e->arena.alloc(slab_bytes);
-      if (n_chunks() > 1) slab[1] = (uint8_t*)e->arena.alloc(slab_bytes);
+    const int slots = n == 0 ? 0 : (n_chunks() > 1 ? 2 : 1);
+    for (int k = 0; k < slots; ++k) {
+      slab[k] = (uint8_t*)e->arena.alloc(slab_bytes);
+      if (jpeg) {
+        d_bytes[k] = (uint8_t*)e->arena.alloc(cap_bytes + 16);
+        d_meta[k] = (JpegImage*)e->arena.alloc((size_t)per_chunk * sizeof(JpegImage));
+        d_tabs[k] = (JpegHuff*)e->arena.alloc(std::max<size_t>(1, cap_tabs) * sizeof(JpegHuff));
+        d_coef[k] = (short*)e->arena.alloc(cap_coef * 2 + 16);
+        d_planes[k] = (uint8_t*)e->arena.alloc(cap_planes + 16);
+      }
     }
   }
-  // enqueue the copy of chunk c (no-op if already started or out of range)
+  // page-locked staging buffer of slot k with at least `bytes`, free for writing
+  uint8_t* staging(int k, size_t bytes) {
+    if (e->pinned_cap[k] < bytes) {
+      CALD_CUDA_CHECK(cudaEventSynchronize(e->pinned_free[k]));
+      if (e->pinned[k]) cudaFreeHost(e->pinned[k]);
+      e->pinned[k] = nullptr;
+      CALD_CUDA_CHECK(cudaMallocHost((void**)&e->pinned[k], bytes));
+      e->pinned_cap[k] = bytes;
+    }
+    CALD_CUDA_CHECK(cudaEventSynchronize(e->pinned_free[k]));  // the previous DMA out of this staging buffer
+    return e->pinned[k];
+  }
+  // enqueue the copy (and, for files, the decode) of chunk c; no-op if already started or out of range
   void start(int c) {
     if (c != started || c >= n_chunks()) return;
     const int k = c & 1, i0 = c * per_chunk, i1 = std::min(n_images, i0 + per_chunk);
-    if (all_pinned) {
+    cudaStream_t cs = e->copy_st;
+    if (jpeg) {
+      uint8_t* stage = staging(k, cap_bytes + 16);
+      h_meta[k].clear(); h_tabs[k].clear();
+      size_t ob = 0, oc = 0, op = 0, oo = 0;
+      int max_w = 0, max_h = 0, max_blocks = 0;
+      for (int i = i0; i < i1; ++i) {
+        JpegImage im = meta[i];
+        const size_t len = scan_end[i] - scan_begin[i];
+        memcpy(stage + ob, imgs[i] + scan_begin[i], len);
+        im.scan_off = (long long)ob; im.scan_len = (long long)len;
+        ob += (len + 15) & ~(size_t)15;
+        for (int q = 0; q < im.ncomp; ++q) {
+          const size_t blocks = (size_t)im.comp[q].blocks_w * im.comp[q].blocks_h;
+          im.comp[q].coef_off = (long long)oc; im.comp[q].plane_off = (long long)op;
+          oc += blocks * 64; op += blocks * 64;
+          max_blocks = std::max(max_blocks, (int)blocks);
+        }
+        const int tbase = (int)h_tabs[k].size();
+        for (int q = 0; q < 2; ++q) {
+          if (im.huff_dc[q] >= 0) im.huff_dc[q] += tbase;
+          if (im.huff_ac[q] >= 0) im.huff_ac[q] += tbase;
+        }
+        h_tabs[k].insert(h_tabs[k].end(), tabs[i].begin(), tabs[i].end());
+        im.out_off = (long long)oo;
+        oo += padded(im.height, im.width);
+        max_w = std::max(max_w, im.width); max_h = std::max(max_h, im.height);
+        h_meta[k].push_back(im);
+      }
+      const int nb = i1 - i0;
+      CALD_CUDA_CHECK(cudaMemcpyAsync(d_bytes[k], stage, ob, cudaMemcpyHostToDevice, cs));
+      CALD_CUDA_CHECK(cudaEventRecord(e->pinned_free[k], cs));
+      CALD_CUDA_CHECK(cudaMemcpyAsync(d_meta[k], h_meta[k].data(), (size_t)nb * sizeof(JpegImage), cudaMemcpyHostToDevice, cs));
+      if (!h_tabs[k].empty())
+        CALD_CUDA_CHECK(cudaMemcpyAsync(d_tabs[k], h_tabs[k].data(), h_tabs[k].size() * sizeof(JpegHuff), cudaMemcpyHostToDevice, cs));
+      CALD_CUDA_CHECK(cudaMemsetAsync(d_coef[k], 0, oc * 2, cs));
+      jpeg_huffman_kernel<<<nb, 32, 0, cs>>>(d_meta[k], d_tabs[k], d_bytes[k], d_coef[k]);
+      jpeg_idct_kernel<<<dim3((max_blocks + 127) / 128, nb * 3), 128, 0, cs>>>(d_meta[k], d_coef[k], d_planes[k]);
+      jpeg_rgb_kernel<<<dim3((max_w + 127) / 128, max_h, nb), 128, 0, cs>>>(d_meta[k], d_planes[k], slab[k]);
+      CALD_CUDA_CHECK(cudaGetLastError());
+      e->launches += 3;
+    } else if (all_pinned) {
       size_t off = 0;
       for (int i = i0; i < i1; ++i) {
-        CALD_CUDA_CHECK(cudaMemcpyAsync(slab[k] + off, imgs[i], (size_t)hs[i] * ws[i] * 3, cudaMemcpyHostToDevice, e->copy_st));
+        CALD_CUDA_CHECK(cudaMemcpyAsync(slab[k] + off, imgs[i], (size_t)hs[i] * ws[i] * 3, cudaMemcpyHostToDevice, cs));
         off += padded(hs[i], ws[i]);
       }
     } else {
-      if (e->pinned_cap[k] < slab_bytes) {
-        CALD_CUDA_CHECK(cudaEventSynchronize(e->pinned_free[k]));
-        if (e->pinned[k]) cudaFreeHost(e->pinned[k]);
-        e->pinned[k] = nullptr;
-        CALD_CUDA_CHECK(cudaMallocHost((void**)&e->pinned[k], slab_bytes));
-        e->pinned_cap[k] = slab_bytes;
-      }
-      CALD_CUDA_CHECK(cudaEventSynchronize(e->pinned_free[k]));  // the previous DMA out of this staging buffer
+      uint8_t* stage = staging(k, slab_bytes);
       size_t off = 0;
       for (int i = i0; i < i1; ++i) {
-        memcpy(e->pinned[k] + off, imgs[i], (size_t)hs[i] * ws[i] * 3);
+        memcpy(stage + off, imgs[i], (size_t)hs[i] * ws[i] * 3);
         off += padded(hs[i], ws[i]);
       }
-      CALD_CUDA_CHECK(cudaMemcpyAsync(slab[k], e->pinned[k], off, cudaMemcpyHostToDevice, e->copy_st));
-      CALD_CUDA_CHECK(cudaEventRecord(e->pinned_free[k], e->copy_st));
+      CALD_CUDA_CHECK(cudaMemcpyAsync(slab[k], stage, off, cudaMemcpyHostToDevice, cs));
+      CALD_CUDA_CHECK(cudaEventRecord(e->pinned_free[k], cs));
     }
-    CALD_CUDA_CHECK(cudaEventRecord(e->upload_done[k], e->copy_st));
+    CALD_CUDA_CHECK(cudaEventRecord(e->upload_done[k], cs));
     started = c + 1;
   }
   // device pointers of chunk c; the compute stream waits for its copy
@@ -1642,7 +1803,9 @@ int cald_load_weights(cald_engine* e, int n, const char* const* names, const flo
 static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, bool on_device, const int* heights,
                       const int* widths, int n_augs, const cald_aug* aug_list, double bp, const double* rng_uniforms,
                       int n_uniforms, int* uniforms_consumed, const float* const* noise, const int* swap_perms,
-                      double* out_consistency, double* out_cls, int scorer = 0) {
+                      double* out_consistency, double* out_cls, int scorer = 0,
+                      const size_t* file_sizes = nullptr /* imgs are JPEG files */, int* out_heights = nullptr,
+                      int* out_widths = nullptr) {
   API_TRY(e)
   check_ready(e);
   e->arena.reset();
@@ -1670,7 +1833,14 @@ static int score_impl(cald_engine* e, int n_images, const uint8_t* const* imgs, 
   const int Bmax = std::max(1, maxv / std::max(1, n_augs));
   e->trace("call_start");
   std::unique_ptr<UploadPipe> pipe;
-  if (!on_device) pipe.reset(new UploadPipe(e, n_images, imgs, heights, widths, Bmax));
+  if (!on_device) pipe.reset(new UploadPipe(e, n_images, imgs, heights, widths, Bmax, file_sizes));
+  if (file_sizes) {
+    heights = pipe->hs; widths = pipe->ws;   // sizes come from the files' frame headers
+    for (int i = 0; i < n_images; ++i) {
+      if (out_heights) out_heights[i] = heights[i];
+      if (out_widths) out_widths[i] = widths[i];
+    }
+  }
   // no copy may still be reading the caller's buffers when the call returns, on the error path either
   struct CopyFence { cudaStream_t s; ~CopyFence() { cudaStreamSynchronize(s); } } copy_fence{e->copy_st};
   int chunk = 0;
@@ -1727,6 +1897,57 @@ int cald_score_device(cald_engine* e, int n_images, const uint8_t* const* d_imag
                       double* out_consistency, double* out_cls) {
   return score_impl(e, n_images, d_images, true, heights, widths, n_augs, augs, bp, rng_uniforms, n_uniforms,
                     uniforms_consumed, d_noise, swap_perms, out_consistency, out_cls);
+}
+
+int cald_score_jpeg(cald_engine* e, int n_files, const uint8_t* const* files, const size_t* file_sizes, int n_augs,
+                    const cald_aug* augs, double bp, const double* rng_uniforms, int n_uniforms, int* uniforms_consumed,
+                    const int* swap_perms, double* out_consistency, double* out_cls, int* out_heights, int* out_widths) {
+  if (!file_sizes) { if (e) e->err = "cald_score_jpeg: file_sizes == NULL"; return -1; }
+  for (int i = 0; i < n_augs; ++i)
+    if (augs[i].kind == CALD_AUG_GAUSS || augs[i].kind == CALD_AUG_SALTPEPPER) {
+      e->err = "cald_score_jpeg: noise views need the image size before the call; decode with cald_jpeg_decode first";
+      return -1;
+    }
+  return score_impl(e, n_files, files, false, nullptr, nullptr, n_augs, augs, bp, rng_uniforms, n_uniforms,
+                    uniforms_consumed, nullptr, swap_perms, out_consistency, out_cls, 0, file_sizes, out_heights,
+                    out_widths);
+}
+
+int cald_jpeg_info(const uint8_t* file, size_t size, int* height, int* width, int* components) {
+  try {
+    JpegImage im;
+    std::vector<JpegHuff> t;
+    size_t a, b;
+    jpeg_parse(file, size, im, t, a, b);
+    if (height) *height = im.height;
+    if (width) *width = im.width;
+    if (components) *components = im.ncomp;
+    return 0;
+  } catch (const std::exception& ex) {
+    g_create_err = ex.what();
+    return -1;
+  }
+}
+
+int cald_jpeg_decode(cald_engine* e, int n_files, const uint8_t* const* files, const size_t* file_sizes,
+                     uint8_t* const* out_images) {
+  API_TRY(e)
+  CALD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  e->arena.reset();
+  const int per = 16;
+  UploadPipe pipe(e, n_files, files, nullptr, nullptr, per, file_sizes);
+  struct CopyFence { cudaStream_t s; ~CopyFence() { cudaStreamSynchronize(s); } } copy_fence{e->copy_st};
+  int chunk = 0;
+  for (int pos = 0; pos < n_files; pos += per, ++chunk) {
+    const int B = std::min(per, n_files - pos);
+    DeviceImages di = pipe.get(chunk);
+    pipe.start(chunk + 1);
+    for (int b = 0; b < B; ++b)
+      CALD_CUDA_CHECK(cudaMemcpyAsync(out_images[pos + b], di.ptr[b], (size_t)pipe.hs[pos + b] * pipe.ws[pos + b] * 3,
+                                      cudaMemcpyDeviceToHost, e->st));
+    CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  }
+  API_CATCH(e)
 }
 
 int cald_score_lsc(cald_engine* e, int n_images, const uint8_t* const* images, const int* heights, const int* widths,

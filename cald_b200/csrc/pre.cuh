@@ -312,6 +312,37 @@ __global__ void pil_resample_v_kernel(const uint8_t* __restrict__ in, uint8_t* _
   out[(long long)yy * w * 3 + t] = pil_clip8(acc);
 }
 
+// Batched forms: one launch resamples / rotates a whole chunk's images (blockIdx.z = job); every job carries its own
+// sizes and coefficient tables, threads outside a job's extent exit.
+struct PilJob {
+  const uint8_t* src;
+  uint8_t* dst;
+  int in_h, in_w, out_h, out_w;   // the pass changes ONE of the two dimensions
+  const int* bounds;
+  const int* kk;
+  int ksize;
+};
+__global__ void pil_resample_h_batched_kernel(const PilJob* __restrict__ jobs) {
+  const PilJob j = jobs[blockIdx.z];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (y >= j.in_h || t >= j.out_w * 3) return;
+  const int xx = t / 3, c = t % 3;
+  const int xmin = j.bounds[xx * 2], n = j.bounds[xx * 2 + 1];
+  int acc = 1 << (PIL_PRECISION_BITS - 1);
+  const uint8_t* row = j.src + (long long)y * j.in_w * 3;
+  for (int x = 0; x < n; ++x) acc += (int)row[(xmin + x) * 3 + c] * j.kk[xx * j.ksize + x];
+  j.dst[((long long)y * j.out_w + xx) * 3 + c] = pil_clip8(acc);
+}
+__global__ void pil_resample_v_batched_kernel(const PilJob* __restrict__ jobs) {
+  const PilJob j = jobs[blockIdx.z];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y;
+  if (yy >= j.out_h || t >= j.in_w * 3) return;
+  const int ymin = j.bounds[yy * 2], n = j.bounds[yy * 2 + 1];
+  int acc = 1 << (PIL_PRECISION_BITS - 1);
+  for (int y = 0; y < n; ++y) acc += (int)j.src[(long long)(ymin + y) * j.in_w * 3 + t] * j.kk[yy * j.ksize + y];
+  j.dst[(long long)yy * j.in_w * 3 + t] = pil_clip8(acc);
+}
+
 // PIL Image.rotate(angle, expand=True) geometry (PIL/Image.py) + Geometry.c affine_fixed coefficients
 struct RotateGeom { int nw, nh; int a0, a1, a2, a3, a4, a5; };
 inline double py_round15(double v) { return std::round(v * 1e15) / 1e15; }
@@ -363,6 +394,28 @@ __global__ void pil_rotate_nearest_kernel(const uint8_t* __restrict__ in, uint8_
     r = p[0]; gg = p[1]; b = p[2];
   }
   uint8_t* o = out + ((long long)y * g.nw + x) * 3;
+  o[0] = r; o[1] = gg; o[2] = b;
+}
+
+struct RotJob {
+  const uint8_t* src;
+  uint8_t* dst;
+  int w, h;
+  RotateGeom g;
+};
+__global__ void pil_rotate_nearest_batched_kernel(const RotJob* __restrict__ jobs) {
+  const RotJob j = jobs[blockIdx.z];
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= j.g.nw || y >= j.g.nh) return;
+  const long long xx = (long long)j.g.a2 + (long long)j.g.a1 * y + (long long)j.g.a0 * x;
+  const long long yy = (long long)j.g.a5 + (long long)j.g.a4 * y + (long long)j.g.a3 * x;
+  const int xin = (int)(xx >> 16), yin = (int)(yy >> 16);
+  uint8_t r = 0, gg = 0, b = 0;
+  if (xin >= 0 && xin < j.w && yin >= 0 && yin < j.h) {
+    const uint8_t* p = j.src + ((long long)yin * j.w + xin) * 3;
+    r = p[0]; gg = p[1]; b = p[2];
+  }
+  uint8_t* o = j.dst + ((long long)y * j.g.nw + x) * 3;
   o[0] = r; o[1] = gg; o[2] = b;
 }
 

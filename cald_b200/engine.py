@@ -192,6 +192,64 @@ class Engine:
                                        cls.ctypes.data_as(POINTER(c_double))))
         return cons, cls, consumed.value
 
+    # ------------------------------------------------------------------ pool ingest (JPEG files)
+    @staticmethod
+    def _file_list(files):
+        keep = [np.frombuffer(f, dtype=np.uint8) if isinstance(f, (bytes, bytearray, memoryview)) else
+                np.ascontiguousarray(f, dtype=np.uint8) for f in files]
+        n = len(keep)
+        ptrs = (POINTER(c_uint8) * n)(*[k.ctypes.data_as(POINTER(c_uint8)) for k in keep])
+        sizes = (c_size_t * n)(*[k.size for k in keep])
+        return keep, ptrs, sizes
+
+    def jpeg_info(self, data):
+        """(height, width, components) of one JPEG file (bytes); host-only header walk."""
+        keep, ptrs, sizes = self._file_list([data])
+        h, w, c = c_int(0), c_int(0), c_int(0)
+        self._L.cald_jpeg_info.argtypes = [POINTER(c_uint8), c_size_t, POINTER(c_int), POINTER(c_int), POINTER(c_int)]
+        if self._L.cald_jpeg_info(ptrs[0], sizes[0], ctypes.byref(h), ctypes.byref(w), ctypes.byref(c)) != 0:
+            raise CaldError(self._L.cald_last_error(None).decode())
+        return h.value, w.value, c.value
+
+    def decode_jpeg(self, files):
+        """Decode baseline JPEG files (bytes objects) ON THE DEVICE -> list of HxWx3 u8 arrays, bit-identical to
+        np.asarray(PIL.Image.open(f).convert('RGB'))."""
+        keep, ptrs, sizes = self._file_list(files)
+        n = len(keep)
+        outs = []
+        for f in files:
+            h, w, _ = self.jpeg_info(f)
+            outs.append(np.zeros((h, w, 3), dtype=np.uint8))
+        optrs = (POINTER(c_uint8) * n)(*[o.ctypes.data_as(POINTER(c_uint8)) for o in outs])
+        self._L.cald_jpeg_decode.argtypes = [c_void_p, c_int, POINTER(POINTER(c_uint8)), POINTER(c_size_t),
+                                             POINTER(POINTER(c_uint8))]
+        self._check(self._L.cald_jpeg_decode(self._h, n, ptrs, sizes, optrs))
+        return outs
+
+    def score_jpeg(self, files, views, bp=1.3, uniforms=None, swap_perms=None):
+        """score() over JPEG FILES (bytes objects): decode and scoring both on the device.
+        -> (consistency float64[n], cls float64[n, C-1], consumed, heights, widths)."""
+        keep, ptrs, sizes = self._file_list(files)
+        n = len(keep)
+        a, na = self._aug_array(views)
+        u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
+        sp = None if swap_perms is None else np.ascontiguousarray(swap_perms, dtype=np.int32)
+        consumed = c_int(0)
+        cons = np.zeros(n, dtype=np.float64)
+        cls = np.zeros((n, self.num_classes - 1), dtype=np.float64)
+        hs, ws = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        self._L.cald_score_jpeg.argtypes = [c_void_p, c_int, POINTER(POINTER(c_uint8)), POINTER(c_size_t), c_int,
+                                            POINTER(Aug), c_double, POINTER(c_double), c_int, POINTER(c_int),
+                                            POINTER(c_int), POINTER(c_double), POINTER(c_double), POINTER(c_int),
+                                            POINTER(c_int)]
+        self._check(self._L.cald_score_jpeg(self._h, n, ptrs, sizes, na, a, float(bp),
+                                            None if u is None else u.ctypes.data_as(POINTER(c_double)),
+                                            0 if u is None else u.size, ctypes.byref(consumed),
+                                            None if sp is None else sp.ctypes.data_as(POINTER(c_int)),
+                                            cons.ctypes.data_as(POINTER(c_double)), cls.ctypes.data_as(POINTER(c_double)),
+                                            hs.ctypes.data_as(POINTER(c_int)), ws.ctypes.data_as(POINTER(c_int))))
+        return cons, cls, consumed.value, hs, ws
+
     def score_device(self, d_ptrs, hs, ws, views, bp=1.3, uniforms=None):
         """Like score() but images are already resident in HBM (list of device pointers)."""
         n = len(d_ptrs)

@@ -99,6 +99,24 @@ int cald_score(cald_engine* e, int n_images, const uint8_t* const* images, const
                int* uniforms_consumed, const float* const* noise, const int* swap_perms, double* out_consistency,
                double* out_cls);
 
+/* Pool ingest: the reference reads its pools with PIL on DataLoader workers --
+ * Image.open(path).convert('RGB'), detection/voc_utils.py:52-58, detection/coco_utils.py:209-220.  These entry points
+ * take the FILES instead: the host walks the marker segments, the compressed scan travels to the device and is decoded
+ * there (Huffman, JDCT_ISLOW inverse DCT, fancy chroma upsampling, YCbCr -> RGB: bit for bit what Pillow's libjpeg
+ * produces), overlapped with the previous chunk's forward passes.  Supported: 8-bit sequential Huffman JPEG (SOF0 /
+ * SOF1), grayscale or YCbCr 4:4:4 / 4:2:2 / 4:2:0, restart intervals; anything else fails the call with a message.
+ *
+ * cald_jpeg_info   : frame size of one file (host only, needs no engine).
+ * cald_jpeg_decode : out_images[i] = caller's HOST buffer of height*width*3 bytes (u8 RGB, HWC).
+ * cald_score_jpeg  : cald_score() over files; out_heights / out_widths (optional) return the decoded sizes.  Noise
+ *                    views (GAUSS / SALTPEPPER) need caller-drawn planes of the image size and are refused here. */
+int cald_jpeg_info(const uint8_t* file, size_t size, int* height, int* width, int* components);
+int cald_jpeg_decode(cald_engine* e, int n_files, const uint8_t* const* files, const size_t* file_sizes,
+                     uint8_t* const* out_images);
+int cald_score_jpeg(cald_engine* e, int n_files, const uint8_t* const* files, const size_t* file_sizes, int n_augs,
+                    const cald_aug* augs, double bp, const double* rng_uniforms, int n_uniforms, int* uniforms_consumed,
+                    const int* swap_perms, double* out_consistency, double* out_cls, int* out_heights, int* out_widths);
+
 /* The two detection-only baseline scorers of the reference, on the same engine:
  * LS+C  ls_c_train.get_uncertainty (ls_c_train.py:108-155): stability of the 30 most confident reference boxes under
  *       6 Gaussian-noise views (std 8..48) minus max(1 - prob_max).  noise: torch.randn(image.size()) planes, 6 per

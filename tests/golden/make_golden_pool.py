@@ -130,6 +130,10 @@ def run_pool(tag, ct, model, imgs):
     for i, c in enumerate(rec.calls):
         off[i + 1] = off[i] + len(c["scores"])
     det = {"det_" + key: np.concatenate([c[key].numpy() for c in rec.calls]) for key in KEYS}
+    det["det_labels"] = det["det_labels"].astype(np.int8)
+    if off[-1] > 100000:   # RetinaNet keeps up to 300 detections per class: scores and labels only, to stay small
+        det.pop("det_boxes")
+        det.pop("det_prob_max")
     print("  [%s] run A done: %.0f s, %d forwards, %d detections" % (tag, time.time() - t0, len(rec.calls), off[-1]), flush=True)
 
     # ---- selection at budget 10 with the reference's own inline code (cald_train.py:439-447)

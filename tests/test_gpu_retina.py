@@ -144,13 +144,26 @@ def test_batched_equals_single(setup):
     assert np.abs(np.array(a) - np.array(b)).max() < 1e-6
 
 
-def test_capacity_overflow_fails_loudly():
-    """a detector whose every anchor fires exceeds the fixed candidate capacity: the call must raise, not truncate"""
+def test_every_anchor_firing_is_scored_not_refused():
+    """A detector whose every anchor fires has tens of thousands of candidates per class.  The reference has no limit
+    (retinanet_cal.py:436-463): it keeps the first 300 survivors of every class.  The engine scans such classes in
+    windows and returns the same 300 x K rows; only an explicitly too small retina_max_detections still fails, loudly."""
     from cald_b200 import synth
     from cald_b200._lib import CaldError
     from cald_b200.engine import Engine, ARCH_RETINANET
     w = synth.planted_retinanet_weights(NC, 0, cls_bias_shift=+9.0)
     eng = Engine(depth=50, num_classes=NC, min_size=160, max_size=256, arch_id=ARCH_RETINANET)
     eng.load_state_dict(w)
+    det = eng.detect([synth.synth_image(0, 120, 160)])[0]
+    counts = np.bincount(det["labels"], minlength=NC)
+    assert counts.max() <= 300 and counts.sum() == len(det["scores"]) and counts.min() > 0
+    # within a class the rows are in descending score order (torchvision nms returns them sorted)
+    for c in range(NC):
+        sc = det["scores"][det["labels"] == c]
+        assert np.all(np.diff(sc) <= 0)
+    eng.close()
+    small = Engine(depth=50, num_classes=NC, min_size=160, max_size=256, arch_id=ARCH_RETINANET,
+                   retina_max_detections=64)
+    small.load_state_dict(w)
     with pytest.raises(CaldError):
-        eng.detect([synth.synth_image(0, 120, 160)])
+        small.detect([synth.synth_image(0, 120, 160)])

@@ -1,0 +1,95 @@
+"""Build container (no GPU): explain every pool image whose engine score differs from the reference's by more than
+1e-3.  Inputs: the reference fixture (tests/golden/pool_*_nc21.npz) and the engine dump tools/pool_parity.py wrote on the
+GPU box.  For each outlier it names the view(s) whose per-view consistency moved and what changed in that view's
+detection list: a detection present on one side only (score next to the 0.05 threshold -> "score threshold";
+otherwise a proposal / NMS decision -> "NMS / proposal set"), or the same list with a moved box / score.
+
+    python tools/pool_diagnose.py tests/golden/pool_frcnn_r50_nc21.npz gpurun_out/pool_engine_frcnn_fp16.npz [out.md]
+"""
+import sys
+
+import numpy as np
+
+VIEWS = ["reference", "flip", "cut_out", "smaller_resize", "rotation"]
+
+
+def views_of(d, n_views=None):
+    """-> list over images of list over views of dict(boxes, scores, labels, prob_max)."""
+    off = d["det_offsets"]
+    out, k = [], 0
+    n_img = len(d["consistency"])
+    for i in range(n_img):
+        nv = int(n_views[i]) if n_views is not None else 5
+        row = []
+        for _ in range(nv):
+            a, b = int(off[k]), int(off[k + 1])
+            row.append({key: d["det_" + key][a:b] for key in ("boxes", "scores", "labels", "prob_max")})
+            k += 1
+        out.append(row)
+    return out
+
+
+def match(ref, eng, tol_box=0.5):
+    """Greedy match of detections (same label, boxes within tol_box px) -> (pairs, only_ref, only_eng)."""
+    used = set()
+    pairs, only_ref = [], []
+    for i in range(len(ref["scores"])):
+        best, bj = None, -1
+        for j in range(len(eng["scores"])):
+            if j in used or ref["labels"][i] != eng["labels"][j]:
+                continue
+            d = np.abs(ref["boxes"][i] - eng["boxes"][j]).max()
+            if d < tol_box and (best is None or d < best):
+                best, bj = d, j
+        if bj >= 0:
+            used.add(bj)
+            pairs.append((i, bj))
+        else:
+            only_ref.append(i)
+    only_eng = [j for j in range(len(eng["scores"])) if j not in used]
+    return pairs, only_ref, only_eng
+
+
+def main():
+    g = np.load(sys.argv[1])
+    e = np.load(sys.argv[2])
+    out = open(sys.argv[3], "w") if len(sys.argv) > 3 else sys.stdout
+    rv = views_of(g, g["n_views"])
+    ev = views_of(e)
+    err = np.abs(e["consistency"] - g["consistency"])
+    bad = np.where(err > 1e-3)[0]
+    n = len(err)
+    print("%d images; |score - reference|: median %.2e, p90 %.2e, p99 %.2e, max %.2e; %d above 1e-3 (%.0f %% within)" % (
+        n, np.median(err), np.percentile(err, 90), np.percentile(err, 99), err.max(), len(bad),
+        100.0 * (1 - len(bad) / n)), file=out)
+    stages = {}
+    for i in bad:
+        pv = np.abs(e["per_view"][i] - g["per_view"][i])
+        print("\nimage %d: engine %.6f reference %.6f (|diff| %.2e); per-view |diff| %s" % (
+            i, e["consistency"][i], g["consistency"][i], err[i], np.array2string(pv, precision=4)), file=out)
+        for v in range(min(len(rv[i]), 5)):
+            pairs, only_r, only_e = match(rv[i][v], ev[i][v])
+            ds = max((abs(float(rv[i][v]["scores"][a]) - float(ev[i][v]["scores"][b])) for a, b in pairs), default=0.0)
+            if not only_r and not only_e:
+                if v > 0 and pv[v - 1] > 1e-3:
+                    print("  %-15s same %d detections, max |dscore| %.1e -> reduction input (argmax-IoU partner or min "
+                          "changed by a near tie)" % (VIEWS[v], len(pairs), ds), file=out)
+                    stages["near-tie in the reduction"] = stages.get("near-tie in the reduction", 0) + 1
+                continue
+            why = []
+            for a in only_r:
+                s = float(rv[i][v]["scores"][a])
+                why.append("reference-only det score %.4f" % s)
+            for b in only_e:
+                s = float(ev[i][v]["scores"][b])
+                why.append("engine-only det score %.4f" % s)
+            near_thr = all(abs(float(x.split()[-1]) - 0.05) < 2e-3 for x in why)
+            stage = "score threshold 0.05" if near_thr else "NMS / proposal set"
+            stages[stage] = stages.get(stage, 0) + 1
+            print("  %-15s reference %d dets, engine %d: %s  => %s" % (
+                VIEWS[v], len(rv[i][v]["scores"]), len(ev[i][v]["scores"]), "; ".join(why[:4]), stage), file=out)
+    print("\nflipping stages over the outliers:", stages, file=out)
+
+
+if __name__ == "__main__":
+    main()
