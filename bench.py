@@ -241,7 +241,8 @@ def main():
                          "--pool images sharded over the ranks + all-gather + host selection (default for cfg5)")
     ap.add_argument("--pool", type=int, default=0, help="cycle mode: pool size (default 128 images per GPU-step budget)")
     ap.add_argument("--budget", type=int, default=0, help="cycle mode: images to select (default pool / 8, cfg-5: 1000)")
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f16"],
+                    help="f16x3 = split-half operands, fp32-faithful (the product); f16 = single pass, not parity")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=5)
     ap.add_argument("--workspace-gb", type=float, default=0.0, help="device arena size (0 = half of free memory)")
@@ -271,7 +272,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from cald_b200 import api, shard
-    from cald_b200.engine import Engine, PREC_BF16, PREC_BF16X3, ARCH_FRCNN, ARCH_RETINANET, expand_augs
+    from cald_b200.engine import Engine, PREC_F16, PREC_F16X3, ARCH_FRCNN, ARCH_RETINANET, expand_augs
     AUGS = cfg["augs"]
     H, W = cfg["hw"]
     kinds = expand_augs(AUGS)
@@ -279,7 +280,7 @@ def main():
     # the engine is built the way the drop-in builds it (api.engine_for): views per pass come from the engine's own
     # sizing unless --views-per-pass overrides it
     eng = Engine(depth=cfg["depth"], num_classes=cfg["nc"], min_size=cfg["size"][0], max_size=cfg["size"][1],
-                 device=local_rank, precision=PREC_BF16 if args.precision == "bf16" else PREC_BF16X3,
+                 device=local_rank, precision=PREC_F16 if args.precision == "f16" else PREC_F16X3,
                  max_views_per_pass=args.views_per_pass, arch_id=ARCH_RETINANET if retina else ARCH_FRCNN,
                  workspace_bytes=int(args.workspace_gb * (1 << 30)))
     eng.load_state_dict(planted(cfg))
@@ -395,7 +396,7 @@ def main():
         "metric": cfg["metric"], "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f16x3 (split-half operands: 22-bit significand, fp32 accumulate)",
+        "dtype": "f16" if args.precision == "f16" else "f16x3 (split-half operands: 22-bit significand, fp32 accumulate)",
         "data": "synthetic", "config": common_config(cfg, args),
         "engine": {"images_per_step_per_gpu": B, "views_per_pass": eng.views_per_pass(), "precision": args.precision,
                    "arena_peak_gb": eng.arena_peak() / 2 ** 30,

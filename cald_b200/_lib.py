@@ -7,8 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# CALD_LIB names an alternative build of the same sources next to this file (./build.sh ab), for A/B measurements
-LIB_PATH = os.path.join(_HERE, os.environ.get("CALD_LIB", "libcald_b200.so"))
+LIB_PATH = os.path.join(_HERE, "libcald_b200.so")
 _lib = None
 
 

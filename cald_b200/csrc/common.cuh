@@ -23,53 +23,27 @@
 namespace cald {
 
 // ---------------------------------------------------------------------------------
-// Split 16-bit activation / weight format.  A real value v is stored as two 16-bit planes
-//   hi = rn16(v),  lo = rn16((v - hi) * LO_SCALE)            =>  v ~= hi + lo * LO_INV
-// and the tensor-core path multiplies A_hi*B_hi + (A_hi*B_lo + A_lo*B_hi) * LO_INV with fp32
-// accumulation in TMEM (the cross terms have their own accumulator columns, igemm.cuh XSEP),
-// which is what keeps the detector's discrete stages (top-k / NMS / arg-max) on the same side
-// of their thresholds as the reference's fp32 CPU run.
-//
-// Two element types, chosen at compile time (CALD_SPLIT_FP16):
-//   1 (default)  IEEE half planes, LO_SCALE = 2^11: 11 + 11 significand bits -- the operands carry 22-23 bits,
-//                i.e. fp32's own precision, at the same tcgen05 kind::f16 rate and the same 4 B / element.  The lo
-//                plane is pre-scaled so that it stays in half's normal range; conversions saturate at +-65504.
-//   0            bfloat16 planes, LO_SCALE = 1: 8 + 8 bits (round 1's format; kept for A/B measurements).
+// Split-half activation / weight format.  A real value v is stored as two IEEE half planes
+//   hi = rn16(v),  lo = rn16((v - hi) * 2^11)            =>  v ~= hi + lo * 2^-11
+// 11 + 11 significand bits: the operands carry fp32's own precision (measured: fp32 FMAs on the split operands land
+// on the same error as torch's CPU fp32 conv, tools/conv_accuracy.py) at the tcgen05 kind::f16 rate and 4 B / element.
+// The tensor-core path multiplies A_hi*B_hi + (A_hi*B_lo + A_lo*B_hi) * 2^-11 with fp32 accumulation in TMEM (the
+// cross terms have their own accumulator columns, igemm.cuh XSEP), which is what keeps the detector's discrete
+// stages (top-k / NMS / arg-max) on the same side of their thresholds as the reference's fp32 CPU run.
+// The lo plane is pre-scaled so that it stays in half's normal range; conversions saturate at +-65504 instead of
+// producing inf.  (Round 1 used bfloat16 planes: 8 + 8 bits, 64x coarser.)
 // ---------------------------------------------------------------------------------
-#ifndef CALD_SPLIT_FP16
-#define CALD_SPLIT_FP16 1
-#endif
-#if CALD_SPLIT_FP16
 typedef __half pl16;
 #define CALD_LO_SCALE 2048.0f
 #define CALD_LO_INV (1.0f / 2048.0f)
-#else
-typedef __nv_bfloat16 pl16;
-#define CALD_LO_SCALE 1.0f
-#define CALD_LO_INV 1.0f
-#endif
 // tcgen05 instruction-descriptor operand format field (a_format bits [7,10), b_format bits [10,13)): 0 = F16, 1 = BF16
-constexpr uint32_t PL16_MMA_FMT = CALD_SPLIT_FP16 ? 0u : 1u;
+constexpr uint32_t PL16_MMA_FMT = 0u;
 
-__host__ __device__ inline float pl16_to_float(pl16 v) {
-#if CALD_SPLIT_FP16
-  return __half2float(v);
-#else
-  return pl16_to_float(v);
-#endif
-}
+__host__ __device__ inline float pl16_to_float(pl16 v) { return __half2float(v); }
 __host__ __device__ inline pl16 float_to_pl16(float v) {
-#if CALD_SPLIT_FP16
   // saturate instead of producing inf (an inf operand would turn a whole accumulator row into NaN)
   v = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
   return __float2half_rn(v);
-#else
-#ifdef __CUDA_ARCH__
-  return __float2bfloat16_rn(v);
-#else
-  return float_to_pl16(v);
-#endif
-#endif
 }
 
 __host__ __device__ inline void split_pl(float v, pl16& hi, pl16& lo) {
@@ -81,7 +55,6 @@ __device__ __forceinline__ float join_pl(pl16 hi, pl16 lo) {
   return fmaf(pl16_to_float(lo), CALD_LO_INV, pl16_to_float(hi));  // the scale is a power of two: exact product
 }
 
-#if CALD_SPLIT_FP16
 // two floats -> packed half2 word (first argument in the low half), saturating
 __device__ __forceinline__ uint32_t cvt_pack2(float a, float b) {
   uint32_t r;
@@ -92,40 +65,24 @@ __device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
   a = f.x; b = f.y;
 }
-#else
-__device__ __forceinline__ uint32_t cvt_pack2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
-  a = __uint_as_float(w << 16);
-  b = __uint_as_float(w & 0xffff0000u);
-}
-#endif
+// x * 2^11 by adding 11 to the exponent field: an integer add on the ALU pipe instead of one more FP32 multiply in the
+// (FP32-pipe bound) epilogue.  Exact for normal x; +-0 becomes +-2^-116, which the half conversion rounds back to +-0.
+__device__ __forceinline__ float scale_2p11(float x) { return __int_as_float(__float_as_int(x) + (11 << 23)); }
 
 // Two floats -> packed (hi plane, lo plane) words
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
   hi = cvt_pack2(a, b);
   float ha, hb;
   unpack2(hi, ha, hb);
-#if CALD_SPLIT_FP16
-  lo = cvt_pack2((a - ha) * CALD_LO_SCALE, (b - hb) * CALD_LO_SCALE);
-#else
-  lo = cvt_pack2(a - ha, b - hb);
-#endif
+  lo = cvt_pack2(scale_2p11(a - ha), scale_2p11(b - hb));
 }
 // packed (hi, lo plane) words -> two floats
 __device__ __forceinline__ void join_pack2(uint32_t hi, uint32_t lo, float& a, float& b) {
   float ha, hb, la, lb;
   unpack2(hi, ha, hb);
   unpack2(lo, la, lb);
-#if CALD_SPLIT_FP16
   a = fmaf(la, CALD_LO_INV, ha);
   b = fmaf(lb, CALD_LO_INV, hb);
-#else
-  a = ha + la;
-  b = hb + lb;
-#endif
 }
 
 __device__ __forceinline__ uint32_t pack_pl16x2(pl16 a, pl16 b) {
@@ -180,11 +137,6 @@ struct ConvParams {
   float* head_part;
   int head_ld;
   long long head_rows;
-  // Round-toward-zero compensation.  tcgen05.mma adds into the fp32 TMEM accumulator with truncation, which shrinks
-  // the result by a relative beta per accumulate on average (measured); coherent over ~50
-  // layers that is the engine's largest deviation from an fp32 CPU run.  acc_gain = 1 + beta * (MMA instructions
-  // accumulated into one main accumulator) is applied to the main accumulator when the epilogue reads it.
-  float acc_gain;
 };
 
 // ATen nearest-neighbour source index (UpSampleKernel: nearest_idx), float scale.

@@ -10,8 +10,14 @@
 #include "igemm.cuh"
 #include "igemm2.cuh"
 
-#ifndef CALD_RZ_BETA_DEFAULT
-#define CALD_RZ_BETA_DEFAULT 0.0
+// Relative loss of the fp32 TMEM accumulator per tcgen05.mma accumulate.  The tensor core adds into the accumulator
+// with truncation (round toward zero): each of the n MMA k-steps of a contraction shrinks the running sum by c on
+// average, so a product that enters at step j is shrunk (n - j) times -- measured on B200 as a signed bias of
+// -(1.6e-8 * n) of the result for every K from 64 to 12544 (tools/conv_accuracy.py, profiles/r02_conv_accuracy.txt),
+// i.e. c = 3.2e-8.  Coherent over ~50 layers this was the engine's largest deviation from an fp32 CPU run.  It is
+// removed where it costs nothing: the WEIGHTS of k-step j are uploaded multiplied by 1 + c * (n - j) (RzPlan).
+#ifndef CALD_RZ_C_DEFAULT
+#define CALD_RZ_C_DEFAULT 3.2e-8
 #endif
 
 namespace cald {
@@ -32,6 +38,32 @@ struct ConvW {
   float* bias = nullptr;
   int cout = 0, cout_pad = 0, cin = 0, taps = 1;
   size_t plane_elems() const { return (size_t)cout_pad * taps * cin; }
+};
+
+// Where a weight tensor's k-steps sit in the accumulation of the launch that uses it (see CALD_RZ_C_DEFAULT):
+// steps_before = MMA k-steps (16 K-elements each) accumulated before this tensor's first one, steps_total = all real
+// k-steps of the launch (a following identity-routed residual block counts as one), chunk_steps = accumulator restart
+// period of a chunked launch (0 = one accumulation).
+struct RzPlan {
+  int steps_before = 0;
+  int steps_total = 0;     // 0 = derive from the tensor itself: taps * cin / 16
+  int chunk_steps = -1;    // -1 = derive from the engine's chunking rule
+  double c = -1.0;         // < 0 = CALD_RZ_C (environment) or the measured default
+  // multiplier of the weights that enter at k-step j of the tensor
+  double factor(int j_local, int own_steps) const {
+    const double cc = c >= 0 ? c : rz_c();
+    const int total = steps_total > 0 ? steps_total : own_steps;
+    const int j = steps_before + j_local;
+    if (chunk_steps > 0) {
+      const int jj = j % chunk_steps, chunk_len = std::min(chunk_steps, total - (j - jj));
+      return 1.0 + cc * (double)(chunk_len - jj);
+    }
+    return 1.0 + cc * (double)(total - j);
+  }
+  static double rz_c() {   // read at every weight upload: experiments can change it between engines of one process
+    const char* e = getenv("CALD_RZ_C");
+    return e && *e ? atof(e) : CALD_RZ_C_DEFAULT;
+  }
 };
 
 struct ConvOpts {
@@ -157,12 +189,14 @@ struct ConvEngine {
   int resmma_max_kb = env_int("CALD_RESMMA_MAX_KB", 1 << 20);
   int cta2_min_kb = env_int("CALD_CTA2_MIN_KB", 16);
   int cta2_min_kb64 = env_int("CALD_CTA2_MIN_KB64", 9);
-  // relative shrink of the fp32 TMEM accumulator per truncating tcgen05.mma accumulate (ConvParams::acc_gain);
-  // CALD_RZ_BETA overrides the measured default
-  double rz_beta = env_double("CALD_RZ_BETA", CALD_RZ_BETA_DEFAULT);
   static double env_double(const char* name, double dflt) {
     const char* v = getenv(name);
     return v && *v ? atof(v) : dflt;
+  }
+  // chunking rule of run(), for callers that need to know it before the launch (weight upload, RzPlan)
+  static bool chunked_for(int num_kb, int block_n_max128 = 1) {
+    const int kc_ = env_int("CALD_KC", 8), above = env_int("CALD_CHUNK_ABOVE_KB", 40);
+    return kc_ > 0 && num_kb > kc_ && num_kb > above && block_n_max128;
   }
   static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -188,7 +222,7 @@ struct ConvEngine {
   }
   int kc = env_int("CALD_KC", 8);  // split mode: k-blocks (of 64) per accumulation chunk; 0 = never chunk
   // chunk only contractions longer than this many k-blocks (K > 2560): up to there the cross-term-separated
-  // accumulator (igemm.cuh XSEP) with the truncation compensation (acc_gain) is as accurate and faster
+  // accumulator (igemm.cuh XSEP) with the truncation pre-compensated in the weights (RzPlan) is as accurate and faster
   int chunk_above_kb = env_int("CALD_CHUNK_ABOVE_KB", 40);
   long long launches = 0;  // kernels launched (bench's gpu_launches)
   double flops = 0;        // algorithmic 2*MAC of the launches
@@ -445,15 +479,8 @@ struct ConvEngine {
     const int num_kb = w.taps * (w.cin / 64) + p.res_kb;
     const bool chunked = split && kc > 0 && num_kb > kc && num_kb > chunk_above_kb && BN <= 128;
     p.kc = chunked ? kc : num_kb;
-    if (CALD_SPLIT_FP16 && split && BN > 128)
+    if (split && BN > 128)
       throw std::runtime_error("conv: the scaled-lo half format needs the cross-term accumulator (BLOCK_N <= 128)");
-    {
-      // accumulates that can truncate the main accumulator of one output: 4 MMA k-steps per 64-wide k-block; an
-      // identity-routed residual block adds one non-zero term per column
-      const int real_kb = w.taps * (w.cin / 64) + (p.res_conv ? p.res_kb : 0);
-      const int adds = chunked ? kc * 4 : real_kb * 4 + ((p.res_kb && !p.res_conv) ? 1 : 0);
-      p.acc_gain = (float)(1.0 + rz_beta * (double)adds);
-    }
     // the pair kernel pays a cross-CTA handshake per tile: at BLOCK_N = 128 it wins from 16 k-blocks per tile up
     // (measured, +8..22 % on the 3x3 and K >= 1024 layers) and loses below 8 (the short-K layers are epilogue / HBM
     // bound).  BLOCK_N = 64: the layer1 3x3 convs gain 5 %; the stem (4 k-blocks) loses 12 % and stays on one CTA.

@@ -18,7 +18,8 @@
 using namespace cald;
 
 namespace cald {
-ConvW upload_conv_weight(const float* w, const float* bias, int cout, int cin, int k, bool split, const float* scale);
+ConvW upload_conv_weight(const float* w, const float* bias, int cout, int cin, int k, bool split, const float* scale,
+                         RzPlan plan);
 void free_conv_weight(ConvW& w);
 }
 
@@ -189,8 +190,15 @@ std::string canonical_key(const std::string& n) {
   return n;
 }
 
+// truncation pre-compensation only applies to the tensor-core kernels (the SIMT checker accumulates with fp32 FMAs)
+RzPlan base_plan(cald_engine* e) {
+  RzPlan p;
+  if (e->cfg.conv_impl == CALD_CONV_SIMT) p.c = 0.0;
+  return p;
+}
+
 // conv + FrozenBatchNorm2d folded: scale = w_bn * rsqrt(var + eps), bias = b_bn - mean * scale (tv:ops/misc.py:54-63)
-ConvW fold_conv_bn(cald_engine* e, const std::string& conv, const std::string& bn) {
+ConvW fold_conv_bn(cald_engine* e, const std::string& conv, const std::string& bn, RzPlan plan) {
   const HostTensor& w = need(e, conv + ".weight");
   const HostTensor& g = need(e, bn + ".weight");
   const HostTensor& b = need(e, bn + ".bias");
@@ -202,14 +210,14 @@ ConvW fold_conv_bn(cald_engine* e, const std::string& conv, const std::string& b
     scale[o] = g.v[o] * (1.0f / sqrtf(v.v[o] + 1e-5f));
     bias[o] = b.v[o] - m.v[o] * scale[o];
   }
-  return upload_conv_weight(w.v.data(), bias.data(), cout, cin, k, e->split, scale.data());
+  return upload_conv_weight(w.v.data(), bias.data(), cout, cin, k, e->split, scale.data(), plan);
 }
 
 ConvW plain_conv(cald_engine* e, const std::string& name) {
   const HostTensor& w = need(e, name + ".weight");
   const HostTensor& b = need(e, name + ".bias");
   int k = w.shape.size() == 4 ? (int)w.shape[2] : 1;
-  return upload_conv_weight(w.v.data(), b.v.data(), (int)w.shape[0], (int)w.shape[1], k, e->split, nullptr);
+  return upload_conv_weight(w.v.data(), b.v.data(), (int)w.shape[0], (int)w.shape[1], k, e->split, nullptr, base_plan(e));
 }
 
 void finalize_weights(cald_engine* e) {
@@ -240,7 +248,7 @@ void finalize_weights(cald_engine* e) {
             }
     }
     // upload as a "4-tap" conv with Cin = 64: layout [o][tap][64] == [o][256]
-    ConvW cw = upload_conv_weight(w2.data(), bias.data(), 64, 256, 1, e->split, nullptr);
+    ConvW cw = upload_conv_weight(w2.data(), bias.data(), 64, 256, 1, e->split, nullptr, base_plan(e));
     cw.cin = 64;
     cw.taps = 4;
     e->stem = cw;
@@ -250,13 +258,27 @@ void finalize_weights(cald_engine* e) {
     for (int bi = 0; bi < nb[li]; ++bi) {
       Block blk;
       std::string pre = "backbone.body.layer" + std::to_string(li + 1) + "." + std::to_string(bi);
-      blk.c1 = fold_conv_bn(e, pre + ".conv1", pre + ".bn1");
-      blk.c2 = fold_conv_bn(e, pre + ".conv2", pre + ".bn2");
-      blk.c3 = fold_conv_bn(e, pre + ".conv3", pre + ".bn3");
+      blk.c1 = fold_conv_bn(e, pre + ".conv1", pre + ".bn1", base_plan(e));
+      blk.c2 = fold_conv_bn(e, pre + ".conv2", pre + ".bn2", base_plan(e));
       blk.stride = (bi == 0 && li > 0) ? 2 : 1;
+      // conv3's accumulation continues after its own k-steps: with the fused projection shortcut (first block of
+      // layer1-3, run_body) by the shortcut's k-steps, otherwise by the identity-routed residual (one more accumulate)
+      const HostTensor& w3 = need(e, pre + ".conv3.weight");
+      const int c3_steps = (int)w3.shape[1] / 16;
+      const bool fused_ds = bi == 0 && li < 3 && ConvEngine::env_flag("CALD_FUSE_DS", true) &&
+                            e->cfg.conv_impl != CALD_CONV_SIMT;
+      RzPlan p3 = base_plan(e), pd = base_plan(e);
+      if (bi == 0) {
+        const HostTensor& wd = need(e, pre + ".downsample.0.weight");
+        const int ds_steps = (int)wd.shape[1] / 16;
+        if (fused_ds) { p3.steps_total = pd.steps_total = c3_steps + ds_steps; pd.steps_before = c3_steps; }
+      } else {
+        p3.steps_total = c3_steps + 1;
+      }
+      blk.c3 = fold_conv_bn(e, pre + ".conv3", pre + ".bn3", p3);
       if (bi == 0) {
         blk.has_ds = true;
-        blk.ds = fold_conv_bn(e, pre + ".downsample.0", pre + ".downsample.1");
+        blk.ds = fold_conv_bn(e, pre + ".downsample.0", pre + ".downsample.1", pd);
         // out = relu(bn3(conv3(y)) + bn_d(conv_d(x))): with both BNs folded the two biases simply add
         std::vector<float> b3(blk.c3.cout_pad), bd(blk.ds.cout_pad);
         if (b3.size() != bd.size()) throw std::runtime_error("downsample / conv3 channel mismatch");
@@ -304,7 +326,7 @@ void finalize_weights(cald_engine* e) {
     memcpy(w.data() + 3 * 256, wb.v.data(), 12 * 256 * 4);
     for (int i = 0; i < 3; ++i) b[i] = bc.v[i];
     for (int i = 0; i < 12; ++i) b[3 + i] = bb.v[i];
-    e->rpn_out = upload_conv_weight(w.data(), b.data(), 15, 256, 1, e->split, nullptr);
+    e->rpn_out = upload_conv_weight(w.data(), b.data(), 15, 256, 1, e->split, nullptr, base_plan(e));
     std::vector<float> w16(16 * 256, 0.f), b16(16, 0.f);
     memcpy(w16.data(), w.data(), 15 * 256 * 4);
     memcpy(b16.data(), b.data(), 15 * 4);
@@ -322,7 +344,7 @@ void finalize_weights(cald_engine* e) {
     for (int o = 0; o < out; ++o)
       for (int c = 0; c < 256; ++c)
         for (int s = 0; s < 49; ++s) w2[(size_t)o * 12544 + s * 256 + c] = w.v[(size_t)o * 12544 + c * 49 + s];
-    e->fc6 = upload_conv_weight(w2.data(), b.v.data(), out, 12544, 1, e->split, nullptr);
+    e->fc6 = upload_conv_weight(w2.data(), b.v.data(), out, 12544, 1, e->split, nullptr, base_plan(e));
   }
   e->fc7 = plain_conv(e, "roi_heads.box_head.fc7");
   {
@@ -337,7 +359,7 @@ void finalize_weights(cald_engine* e) {
     memcpy(w.data() + (size_t)C * 1024, wb.v.data(), (size_t)4 * C * 1024 * 4);
     for (int i = 0; i < C; ++i) b[i] = bc.v[i];
     for (int i = 0; i < 4 * C; ++i) b[C + i] = bb.v[i];
-    e->pred = upload_conv_weight(w.data(), b.data(), 5 * C, 1024, 1, e->split, nullptr);
+    e->pred = upload_conv_weight(w.data(), b.data(), 5 * C, 1024, 1, e->split, nullptr, base_plan(e));
     e->head_ld = e->pred.cout_pad;
   }
   e->staged.clear();
@@ -1680,7 +1702,7 @@ int cald_config_default(cald_config* cfg, int arch, int depth, int num_classes, 
   if (arch == CALD_ARCH_RETINANET) cfg->box_detections_per_img = 300;  /* per class, retinanet_cal.py:333,463 */
   /* the reference keeps up to 300 detections per class (retinanet_cal.py:333, 463): 300 * K rows can never overflow */
   cfg->retina_max_detections = std::min(32768, 300 * num_classes);
-  cfg->device = 0; cfg->precision = CALD_PREC_BF16X3; cfg->conv_impl = CALD_CONV_TCGEN05;
+  cfg->device = 0; cfg->precision = CALD_PREC_F16X3; cfg->conv_impl = CALD_CONV_TCGEN05;
   cfg->max_views_per_pass = 0; cfg->workspace_bytes = 0; cfg->debug = 0;
   return 0;
 }
@@ -1709,7 +1731,7 @@ int cald_create(const cald_config* cfg, cald_engine** out) {
     if (prop.major != 10) throw std::runtime_error("this library contains sm_100a code only (Blackwell B200 required)");
     e = new cald_engine();
     e->cfg = *cfg;
-    e->split = cfg->precision == CALD_PREC_BF16X3;
+    e->split = cfg->precision == CALD_PREC_F16X3;
     e->C = cfg->num_classes;
     e->retina = retina;
     if (retina) {

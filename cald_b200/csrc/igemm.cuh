@@ -111,15 +111,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // 32 accumulator columns = main + cross-term columns (XSEP): both TMEM loads are in flight before the one wait, so a
 // 64-channel group costs two TMEM round trips instead of four (the epilogue of the short-K layers is latency-bound:
 // ncu stall samples sat on the first FADD after every LDTM)
-// The cross-term accumulator holds LO_SCALE * (A_hi*B_lo + A_lo*B_hi) (common.cuh); `gain` is the round-toward-zero
-// compensation of the main accumulator (ConvParams::acc_gain).
-__device__ __forceinline__ void tmem_ld32_sum2(uint32_t t_main, uint32_t t_cross, float gain, float* v) {
+// The cross-term accumulator holds LO_SCALE * (A_hi*B_lo + A_lo*B_hi) (common.cuh).
+__device__ __forceinline__ void tmem_ld32_sum2(uint32_t t_main, uint32_t t_cross, float* v) {
   uint32_t a[32], b[32];
   tmem_ld32_nowait(t_main, a);
   tmem_ld32_nowait(t_cross, b);
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(b[i]), CALD_LO_INV, __uint_as_float(a[i]) * gain);
+  for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(b[i]), CALD_LO_INV, __uint_as_float(a[i]));
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -379,10 +378,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tmem_ld32(t0 + cc, r);
             if (ch == 0) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) accv[cc + i] = __uint_as_float(r[i]) * p.acc_gain;
+              for (int i = 0; i < 32; ++i) accv[cc + i] = __uint_as_float(r[i]);
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) accv[cc + i] = fmaf(__uint_as_float(r[i]), p.acc_gain, accv[cc + i]);
+              for (int i = 0; i < 32; ++i) accv[cc + i] = accv[cc + i] + __uint_as_float(r[i]);
             }
             if (XSEP) {  // the chunk's cross-term columns
               tmem_ld32(t0 + BLOCK_N + cc, r);
@@ -410,16 +409,16 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int i = 0; i < 64; ++i) v[i] = accv[(g * 64 + i) % NACC];
         } else {
           if (XSEP) {
-            tmem_ld32_sum2(t0 + g * 64, t0 + BLOCK_N + g * 64, p.acc_gain, v);
-            tmem_ld32_sum2(t0 + g * 64 + 32, t0 + BLOCK_N + g * 64 + 32, p.acc_gain, v + 32);
+            tmem_ld32_sum2(t0 + g * 64, t0 + BLOCK_N + g * 64, v);
+            tmem_ld32_sum2(t0 + g * 64 + 32, t0 + BLOCK_N + g * 64 + 32, v + 32);
           } else {
             uint32_t r[32];
             tmem_ld32(t0 + g * 64, r);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.acc_gain;
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
             tmem_ld32(t0 + g * 64 + 32, r);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]) * p.acc_gain;
+            for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
           }
           if (g == BLOCK_N / 64 - 1) {  // accumulator fully drained: hand the TMEM stage back to the MMA warp
             tcgen05_fence_before();

@@ -297,10 +297,10 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld32(tc + cc, r);
             if (ch == 0) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) accv[cc + i] = __uint_as_float(r[i]) * p.acc_gain;
+              for (int i = 0; i < 32; ++i) accv[cc + i] = __uint_as_float(r[i]);
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) accv[cc + i] = fmaf(__uint_as_float(r[i]), p.acc_gain, accv[cc + i]);
+              for (int i = 0; i < 32; ++i) accv[cc + i] = accv[cc + i] + __uint_as_float(r[i]);
             }
             tmem_ld32(tc + BLOCK_N + cc, r);  // the chunk's cross-term columns (scaled by LO_SCALE, common.cuh)
 #pragma unroll
@@ -324,8 +324,8 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = accv[CHUNKED ? g * 64 + i : 0];
         } else {
-          tmem_ld32_sum2(t0 + g * 64, t0 + BLOCK_N + g * 64, p.acc_gain, v);
-          tmem_ld32_sum2(t0 + g * 64 + 32, t0 + BLOCK_N + g * 64 + 32, p.acc_gain, v + 32);
+          tmem_ld32_sum2(t0 + g * 64, t0 + BLOCK_N + g * 64, v);
+          tmem_ld32_sum2(t0 + g * 64 + 32, t0 + BLOCK_N + g * 64 + 32, v + 32);
           if (g == BLOCK_N / 64 - 1) {  // accumulator drained: hand the stage back to the leader's MMA thread
             tcgen05_fence_before();
             __syncwarp();

@@ -21,8 +21,10 @@ extern "C" long long cald_ops_pair_launches(void) { return pair_launch_counter()
 
 namespace cald {
 // Upload torch-layout weights [cout][cin][k][k] as [2][cout_pad][(r,s,cin)] split pl16 (+ fp32 bias).
+// plan: position of this tensor's k-steps in its launch (RzPlan, conv_host.cuh): the truncating tensor-core accumulate
+// is pre-compensated here, in double, before the value is split into its two half planes.
 ConvW upload_conv_weight(const float* w, const float* bias, int cout, int cin, int k, bool split,
-                         const float* scale /*per-cout or null*/) {
+                         const float* scale /*per-cout or null*/, RzPlan plan) {
   ConvW cw;
   cw.cout = cout;
   cw.cout_pad = (cout + 7) / 8 * 8;
@@ -31,6 +33,14 @@ ConvW upload_conv_weight(const float* w, const float* bias, int cout, int cin, i
   size_t pe = cw.plane_elems();
   std::vector<pl16> h(pe * (split ? 2 : 1));
   for (auto& v : h) v = float_to_pl16(0.f);
+  const int own_steps = cw.taps * cin / 16;
+  if (plan.chunk_steps < 0) {
+    const int num_kb = (plan.steps_total > 0 ? plan.steps_total : own_steps) / 4;
+    plan.chunk_steps = (split && ConvEngine::chunked_for(num_kb)) ? ConvEngine::env_int("CALD_KC", 8) * 4 : 0;
+  }
+  std::vector<float> fac(std::max(1, own_steps), 1.0f);
+  if (split)
+    for (int j = 0; j < own_steps; ++j) fac[j] = (float)plan.factor(j, own_steps);
   for (int o = 0; o < cout; ++o)
     for (int c = 0; c < cin; ++c)
       for (int r = 0; r < k; ++r)
@@ -38,6 +48,7 @@ ConvW upload_conv_weight(const float* w, const float* bias, int cout, int cin, i
           float v = w[(((size_t)o * cin + c) * k + r) * k + s];
           if (scale) v *= scale[o];
           size_t idx = (size_t)o * cw.taps * cin + (size_t)(r * k + s) * cin + c;
+          if (split && own_steps > 0) v = (float)((double)v * (double)fac[((size_t)(r * k + s) * cin + c) / 16]);
           pl16 hi, lo;
           split_pl(v, hi, lo);
           h[idx] = hi;
@@ -77,7 +88,14 @@ extern "C" int cald_op_conv2d(const float* x, int n, int h, int w, int cin, cons
   eng.split = split;
   eng.force_block_n = block_n;
   if (kc >= 0) eng.kc = kc;
-  ConvW cw = upload_conv_weight(weight, bias, cout, cin, k, split, nullptr);
+  RzPlan plan;
+  if (impl) plan.c = 0.0;   // the SIMT checker accumulates with fp32 FMAs: nothing to compensate
+  {
+    const int num_kb = k * k * (cin / 64);
+    const bool ch = split && eng.kc > 0 && num_kb > eng.kc && num_kb > eng.chunk_above_kb;
+    plan.chunk_steps = ch ? eng.kc * 4 : 0;
+  }
+  ConvW cw = upload_conv_weight(weight, bias, cout, cin, k, split, nullptr, plan);
   float* dx = (float*)ar.alloc(in_e * 4);
   CALD_CUDA_CHECK(cudaMemcpy(dx, x, in_e * 4, cudaMemcpyHostToDevice));
   Act a = alloc_act(ar, n, h, w, cin, split);
@@ -143,8 +161,11 @@ extern "C" int cald_op_conv2d_dual(const float* x, int n, int h, int w, int cin,
   int dev;
   CALD_CUDA_CHECK(cudaGetDevice(&dev));
   CALD_CUDA_CHECK(cudaDeviceGetAttribute(&eng.num_sms, cudaDevAttrMultiProcessorCount, dev));
-  ConvW cw = upload_conv_weight(weight, bias, cout, cin, k, true, nullptr);
-  ConvW cw2 = upload_conv_weight(weight2, bias2, cout, cin2, 1, true, nullptr);
+  RzPlan p1, p2;   // one accumulation: the main contraction's k-steps first, then the second one's
+  p1.steps_total = p2.steps_total = k * k * cin / 16 + cin2 / 16;
+  p2.steps_before = k * k * cin / 16;
+  ConvW cw = upload_conv_weight(weight, bias, cout, cin, k, true, nullptr, p1);
+  ConvW cw2 = upload_conv_weight(weight2, bias2, cout, cin2, 1, true, nullptr, p2);
   std::vector<float> bs(cout_pad, 0.f);
   for (int o = 0; o < cout; ++o) bs[o] = (bias ? bias[o] : 0.f) + (bias2 ? bias2[o] : 0.f);
   float* dbs = (float*)ar.alloc(bs.size() * 4);

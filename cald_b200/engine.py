@@ -8,7 +8,8 @@ from . import arch
 from ._lib import CaldError, lib
 
 ARCH_FRCNN, ARCH_RETINANET = 0, 1
-PREC_BF16X3, PREC_BF16 = 0, 1
+PREC_F16X3, PREC_F16 = 0, 1   # split-half x3 (fp32-faithful, the product mode) / single-pass half
+PREC_BF16X3, PREC_BF16 = PREC_F16X3, PREC_F16  # round-1 names
 CONV_TCGEN05, CONV_SIMT = 0, 1
 AUG_FLIP, AUG_CUTOUT, AUG_RESIZE, AUG_ROTATION, AUG_GAUSS, AUG_SALTPEPPER = 0, 1, 2, 3, 4, 5
 AUG_COLOR_ADJUST, AUG_COLOR_SWAP = 6, 7
@@ -90,7 +91,7 @@ def _u8_list(images):
 class Engine:
     """The scoring engine for one detector on one GPU."""
 
-    def __init__(self, depth=50, num_classes=21, min_size=600, max_size=1000, device=0, precision=PREC_BF16X3,
+    def __init__(self, depth=50, num_classes=21, min_size=600, max_size=1000, device=0, precision=PREC_F16X3,
                  conv_impl=CONV_TCGEN05, max_views_per_pass=0, workspace_bytes=0, debug=False,
                  arch_id=ARCH_FRCNN, **overrides):
         L = lib()

@@ -25,7 +25,9 @@ extern "C" {
 typedef struct cald_engine cald_engine;
 
 enum { CALD_ARCH_FRCNN = 0, CALD_ARCH_RETINANET = 1 };
-enum { CALD_PREC_BF16X3 = 0, CALD_PREC_BF16 = 1 };
+/* F16X3: split-half operands (22-bit significand), three tensor-core passes per product -- fp32-faithful, the product's
+ * only validated mode.  F16: one pass over the hi planes (11 bits) -- a speed-of-light reference point, not parity. */
+enum { CALD_PREC_F16X3 = 0, CALD_PREC_F16 = 1 };
 enum { CALD_CONV_TCGEN05 = 0, CALD_CONV_SIMT = 1 };
 /* augmentation kinds (cald/cald_helper.py); `param` carries the reference's per-call argument */
 enum {

@@ -1,12 +1,15 @@
-"""Accuracy of the tcgen05 conv variants against an fp64 reference (run on the GPU box).
+"""Accuracy of the tcgen05 conv kernel against an fp64 reference (run on the GPU box).
 
-For every shape: relative rms and signed bias of (a) torch CPU fp32, (b) the engine's default launch, (c) forced
-chunked accumulation with kc = 2 / 4 / 8 k-blocks per chunk, (d) the fp32-FMA SIMT checker on the same split operands
-(the representation floor).  With CALD_RZ_BETA=0 the signed bias of (b) divided by the number of truncating accumulates
-is the per-accumulate shrink `beta` that ConvParams::acc_gain compensates; the last column re-runs (b) with the beta
-given on the command line.
+For every shape: relative rms and signed bias (mean of the error projected on the sign of the exact value, relative to
+the mean magnitude) of
+  (a) torch CPU fp32 -- the reference's own arithmetic,
+  (b) fp32 FMAs on the engine's split-half operands (SIMT checker) -- the representation floor,
+  (c) the tensor-core kernel without truncation compensation (CALD_RZ_C=0): its bias divided by the number of MMA
+      accumulates is the per-accumulate shrink of the truncating fp32 accumulate,
+  (d) the tensor-core kernel with the weight pre-compensation (RzPlan, conv_host.cuh) for a few values of c,
+  (e) forced chunked accumulation (kc = 2 / 4 k-blocks per chunk) for comparison.
 
-    python tools/conv_accuracy.py [beta]
+    python tools/conv_accuracy.py [c ...]          default c values: 2.8e-8 3.2e-8 3.6e-8
 """
 import os, sys
 import numpy as np
@@ -15,14 +18,14 @@ import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cald_b200 import ops
 
-BETA = sys.argv[1] if len(sys.argv) > 1 else None
+CS = sys.argv[1:] or ["2.8e-8", "3.2e-8", "3.6e-8"]
 
 
-def run(x, wt, **env):
+def run(x, wt, simt=False, **env):
     old = {k: os.environ.get(k) for k in env}
     os.environ.update({k: str(v) for k, v in env.items()})
     try:
-        return ops.conv2d(x, wt, None, relu=False, **({"impl": 1} if env.pop("SIMT", None) else {}))
+        return ops.conv2d(x, wt, None, relu=False, impl=1 if simt else 0)
     finally:
         for k, v in old.items():
             if v is None:
@@ -46,20 +49,17 @@ def case(n, h, w, cin, cout, k, relu_in=True, seed=1):
         rms = np.sqrt((d ** 2).mean()) / np.sqrt((ref64 ** 2).mean())
         bias = (d * np.sign(ref64)).mean() / np.abs(ref64).mean()
         extra = "  bias / accumulate %.3e" % (bias / adds) if adds else ""
-        print("  %-34s rms %.2e  bias %+.2e%s" % (tag, rms, bias, extra))
-        return bias
+        print("  %-36s rms %.2e  bias %+.2e%s" % (tag, rms, bias, extra))
     K = cin * k * k
     adds = K // 16
     print("conv %dx%dx%d k%d %d->%d  (K = %d, %d accumulates, relu_in=%s)" % (n, h, w, k, cin, cout, K, adds, relu_in))
     rep("torch CPU fp32", ref32)
-    rep("simt fp32 fma on split operands", run(x, wt, SIMT=1))
-    rep("engine default, beta 0", run(x, wt, CALD_RZ_BETA=0), adds if K // 64 <= 40 else 32)
-    rep("unchunked, beta 0", run(x, wt, CALD_RZ_BETA=0, CALD_KC=0), adds)
-    for kc in (2, 4, 8):
-        rep("chunked kc=%d, beta 0" % kc, run(x, wt, CALD_RZ_BETA=0, CALD_KC=kc, CALD_CHUNK_ABOVE_KB=0), kc * 4)
-    if BETA:
-        rep("engine default, beta %s" % BETA, run(x, wt, CALD_RZ_BETA=BETA))
-        rep("unchunked, beta %s" % BETA, run(x, wt, CALD_RZ_BETA=BETA, CALD_KC=0))
+    rep("fp32 FMA on split operands (SIMT)", run(x, wt, simt=True))
+    rep("tensor core, c = 0", run(x, wt, CALD_RZ_C=0), adds if K // 64 <= 40 else 32)
+    for c in CS:
+        rep("tensor core, c = %s" % c, run(x, wt, CALD_RZ_C=c))
+    for kc in (2, 4):
+        rep("chunked kc=%d, c = %s" % (kc, CS[len(CS) // 2]), run(x, wt, CALD_RZ_C=CS[len(CS) // 2], CALD_KC=kc, CALD_CHUNK_ABOVE_KB=0))
 
 
 case(1, 24, 32, 64, 64, 3)
