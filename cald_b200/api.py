@@ -406,12 +406,30 @@ def cls_kldiv(labeled_loader, cls_corrs, budget, cycle=0):
     return picked
 
 
-def select(uncertainty, cls_corrs, subset, labeled_loader, budget_num, cycle=0, mutual=True):
+def _label_histogram_mean(labeled_loader, n_cls):
+    """np.mean of the per-image label histograms of the labeled set (cald_train.py:237-242, 253)."""
+    hist = []
+    for _, targets in labeled_loader:
+        for target in targets:
+            row = [0] * n_cls
+            for l in target['labels']:
+                row[l - 1] += 1
+            hist.append(row)
+    return np.mean(np.array(hist), axis=0)
+
+
+def select(uncertainty, cls_corrs, subset, labeled_loader, budget_num, cycle=0, mutual=True, engine=None):
     """The inline selection of cald_train.py:439-448 (mutual) / 452-455 (--no-mutual).
 
-    Returns the dataset indices to move from the unlabeled to the labeled set.
+    Returns the dataset indices to move from the unlabeled to the labeled set.  With ``engine`` the argsort, the
+    candidate cut and cls_kldiv run on that engine's GPU (cald_select) -- same picks, same order.
     """
     import torch
+    if engine is not None and mutual:
+        cls = np.asarray(cls_corrs, dtype=np.float64)
+        pos = engine.select(uncertainty, cls, _label_histogram_mean(labeled_loader, cls.shape[1]), budget_num,
+                            int(mr * budget_num), uniform)
+        return list(torch.tensor(subset)[torch.from_numpy(pos.astype(np.int64))].numpy())
     arg = np.argsort(np.array(uncertainty))
     if not mutual:
         return list(torch.tensor(subset)[arg][:budget_num].numpy())

@@ -131,12 +131,6 @@ struct ConvParams {
   int res_conv;        // 1: the extra k-blocks are a second 1x1 contraction (aux input x aux weights, e.g. the ResNet
                        //    downsample shortcut) accumulated into the same tile, not an identity-routed residual
   int r_scale;         // element stride of the aux input's tensor map (2 for a stride-2 shortcut), else 1
-  // fused 1x1 head (igemm2.cuh HEAD instantiation): the activated tile is not stored; each n block contributes a partial
-  // fp32 product with head_w [16][head_ld] to head_part [n_blocks][pixels][16]
-  const float* head_w;
-  float* head_part;
-  int head_ld;
-  long long head_rows;
 };
 
 // ATen nearest-neighbour source index (UpSampleKernel: nearest_idx), float scale.

@@ -87,10 +87,6 @@ struct ConvOpts {
   const ConvW* aux_w = nullptr;
   int aux_stride = 1;
   const float* bias_sum = nullptr;
-  // fused 1x1 head (experiment): see igemm2.cuh HEAD.  head_w = device fp32 [16][w.cout_pad], head_part = device fp32
-  // [n_blocks][pixels][16]; requires relu, no residual, no stored output (no_bf16_out) and the pair kernel.
-  const float* head_w = nullptr;
-  float* head_part = nullptr;
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -186,7 +182,6 @@ struct ConvEngine {
   bool force_pow2_tiles = false;  // true: restrict spatial tiles to power-of-two shapes
   // CTA-pair kernel (igemm2.cuh) for the split-mode BLOCK_N = 128 launches it covers; CALD_CTA2=0/1 overrides
   bool use_cta2 = env_flag("CALD_CTA2", true);
-  int resmma_max_kb = env_int("CALD_RESMMA_MAX_KB", 1 << 20);
   int cta2_min_kb = env_int("CALD_CTA2_MIN_KB", 16);
   int cta2_min_kb64 = env_int("CALD_CTA2_MIN_KB64", 9);
   static double env_double(const char* name, double dflt) {
@@ -282,20 +277,20 @@ struct ConvEngine {
     CALD_CUDA_CHECK(cudaGetLastError());
   }
 
-  template <int BN, bool CH, bool HEAD = false>
+  template <int BN, bool CH>
   void launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& tc,
                   const ConvParams& p, cudaStream_t st) {
     using Cfg = Igemm2Cfg<BN>;
     static std::once_flag attr_once;
     std::call_once(attr_once, [] {
-      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc2_kernel<BN, CH, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc2_kernel<BN, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES));
     });
     const int m_tiles = p.tiles_x * p.tiles_y * p.n_img;
     const int n_pairs = p.n_blocks * ((m_tiles + 1) / 2);
     const int clusters = n_pairs < num_sms / 2 ? n_pairs : num_sms / 2;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
-    igemm_tc2_kernel<BN, CH, HEAD><<<2 * clusters, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, tc, p);
+    igemm_tc2_kernel<BN, CH><<<2 * clusters, IG_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, tc, p);
     pair_launch_counter()++;
     if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
     CALD_CUDA_CHECK(cudaGetLastError());
@@ -445,12 +440,10 @@ struct ConvEngine {
     // residual on the tensor core (see igemm.cuh): same-shape shortcut, channel count a multiple of BLOCK_N
     CUtensorMap tr = tb, ti = tb;
     p.res_kb = 0;
-    // A residual k-block costs as many MMA instructions as a conv k-block; for launches paced by the tensor pipe
-    // (256 -> 1024: 2 of 6 k-blocks) adding the shortcut in the epilogue registers instead may win.  resmma_max_kb
-    // (CALD_RESMMA_MAX_KB) limits the MMA form to contractions of at most that many conv k-blocks; unmeasured so far,
-    // hence unlimited by default.
+    // (Measured, round 2: adding the shortcut of the 256 -> 1024 / 512 -> 2048 launches in the epilogue registers
+    // instead -- 2 of their 6 / 10 k-blocks are identity MMAs -- was 1.3 % SLOWER end to end; the MMA form stays.)
     if (use_res_mma && o.res_mode == RES_SAME && p.tma_store && (w.cout_pad % BN) == 0 && o.res->c == w.cout_pad &&
-        o.res->split == split && w.taps * (w.cin / 64) <= resmma_max_kb) {
+        o.res->split == split) {
       if (spatial) {
         tr = make_tmap(o.res->hi, o.res->c, o.res->w, o.res->h, (uint64_t)o.res->n * (split ? 2 : 1), p.tw, p.th);
         p.r_lo_img = o.res->n;
@@ -487,17 +480,6 @@ struct ConvEngine {
     bool pair = use_cta2 && split && p.res_kb == 0 && !o.stem_window &&
                 ((BN == 128 && num_kb >= cta2_min_kb) ||
                  (BN == 64 && w.taps == 9 && num_kb >= cta2_min_kb64 && !chunked));
-    const bool head = o.head_w != nullptr;
-    if (head) {
-      if (!o.head_part || !use_cta2 || !split || BN != 128 || chunked || p.res_kb != 0 || o.res_mode != RES_NONE ||
-          !o.relu || !o.no_bf16_out || o.out_f32 || !spatial || (w.cout_pad % 128) != 0)
-        throw std::runtime_error("conv: bad operands for the fused head");
-      pair = true;
-      p.head_w = o.head_w;
-      p.head_part = o.head_part;
-      p.head_ld = w.cout_pad;
-      p.head_rows = (long long)p.n_img * p.H * p.W;
-    }
     if (profiling) {
       // algorithmic HBM bytes: every operand element once at its stored width (activations 4 B split / 2 B pl16)
       const double eb = split ? 4.0 : 2.0;
@@ -508,20 +490,18 @@ struct ConvEngine {
       if (!o.no_bf16_out) by += pix * out.c * eb;
       if (o.res_mode != RES_NONE) by += (o.res_mode == RES_NEAREST ? 0.25 : 1.0) * pix * w.cout_pad * eb;
       if (dual) by += pix * o.aux_w->cin * eb + (double)w.cout_pad * o.aux_w->cin * eb;
-      if (head) by += pix * 16 * 4.0 * p.n_blocks;
       LayerRec r;
       snprintf(r.sig, sizeof(r.sig), "%dx%dx%d k%d%s cin%d cout%d BN%d%s%s%s%s%s", p.n_img, p.H, p.W,
                o.stem_window ? 7 : (w.taps == 9 ? 3 : 1), o.stride == 2 ? "s2" : "", o.stem_window ? 3 : w.cin, w.cout, BN,
                chunked ? " chunk" : "", pair ? " pair" : "",
                dual ? (o.aux_stride == 2 ? " +ds2" : " +ds") : (p.res_kb ? " resmma" : (o.res_mode != RES_NONE ? " res" : "")),
-               head ? " head" : (p.tma_store ? " tma" : " direct"), o.relu ? " relu" : "");
+               p.tma_store ? " tma" : " direct", o.relu ? " relu" : "");
       r.flops = fl; r.bytes = by;
       recs.push_back(r);
     }
     if (pair) {
       const CUtensorMap tbh = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, 2, BN / 2, 1);
-      if (head) launch_tc2<128, false, true>(ta, tb, tbh, tc, p, st);
-      else if (BN == 64) launch_tc2<64, false>(ta, tb, tbh, tc, p, st);
+      if (BN == 64) launch_tc2<64, false>(ta, tb, tbh, tc, p, st);
       else if (chunked) launch_tc2<128, true>(ta, tb, tbh, tc, p, st);
       else launch_tc2<128, false>(ta, tb, tbh, tc, p, st);
     } else if (split) {

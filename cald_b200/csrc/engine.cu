@@ -13,6 +13,7 @@
 #include "cons.cuh"
 #include "ret.cuh"
 #include "jpeg.cuh"
+#include "select.cuh"
 #include "../../include/cald_b200.h"
 
 using namespace cald;
@@ -63,10 +64,6 @@ struct cald_engine {
 
   std::map<std::string, HostTensor> staged;
   bool weights_ready = false;
-  // experiment (CALD_FUSE_RPN=1, read when the engine is created): RPN 1x1 heads folded into the 3x3 RPN conv's epilogue
-  bool fuse_rpn = ConvEngine::env_flag("CALD_FUSE_RPN", false);
-  float* rpn_head_w = nullptr;  // device fp32 [16][256]: rows 0..2 objectness, 3..14 box deltas, row 15 zero
-  float* rpn_head_b = nullptr;  // device fp32 [16]
   ConvW stem;
   std::vector<std::vector<Block>> layers;
   ConvW fpn_inner[4], fpn_layer[4], rpn_conv, rpn_out, fc6, fc7, pred;
@@ -143,9 +140,6 @@ struct cald_engine {
       if (b.bias_c3ds) cudaFree(b.bias_c3ds);
     }
     layers.clear();
-    if (rpn_head_w) cudaFree(rpn_head_w);
-    if (rpn_head_b) cudaFree(rpn_head_b);
-    rpn_head_w = rpn_head_b = nullptr;
     weights_ready = false;
   }
   ~cald_engine() {
@@ -327,13 +321,6 @@ void finalize_weights(cald_engine* e) {
     for (int i = 0; i < 3; ++i) b[i] = bc.v[i];
     for (int i = 0; i < 12; ++i) b[3 + i] = bb.v[i];
     e->rpn_out = upload_conv_weight(w.data(), b.data(), 15, 256, 1, e->split, nullptr, base_plan(e));
-    std::vector<float> w16(16 * 256, 0.f), b16(16, 0.f);
-    memcpy(w16.data(), w.data(), 15 * 256 * 4);
-    memcpy(b16.data(), b.data(), 15 * 4);
-    CALD_CUDA_CHECK(cudaMalloc((void**)&e->rpn_head_w, w16.size() * 4));
-    CALD_CUDA_CHECK(cudaMemcpy(e->rpn_head_w, w16.data(), w16.size() * 4, cudaMemcpyHostToDevice));
-    CALD_CUDA_CHECK(cudaMalloc((void**)&e->rpn_head_b, b16.size() * 4));
-    CALD_CUDA_CHECK(cudaMemcpy(e->rpn_head_b, b16.data(), b16.size() * 4, cudaMemcpyHostToDevice));
   }
   {
     // fc6: torch flattens [256][7][7] as c*49 + ph*7 + pw; RoIAlign writes (ph*7+pw)*256 + c
@@ -548,25 +535,7 @@ void forward_pass(cald_engine* e, int V, int Hp, int Wp, const ViewDesc* d_views
   int off = 0;
   for (int l = 0; l < 5; ++l) {
     rpn_raw[l] = (float*)ar.alloc((size_t)V * pf[l].h * pf[l].w * 16 * 4);
-    if (e->fuse_rpn && split && e->conv.use_cta2 && e->conv.impl == CONV_TC) {
-      // experiment: relu(conv3x3) never reaches HBM; its epilogue emits the two per-n-block partial head rows
-      const long long pix = (long long)V * pf[l].h * pf[l].w;
-      float* part = (float*)ar.alloc((size_t)pix * 16 * 4 * 2);
-      Act none;
-      none.n = V; none.h = pf[l].h; none.w = pf[l].w; none.c = e->rpn_conv.cout_pad; none.split = split; none.hi = nullptr;
-      ConvOpts o;
-      o.relu = true;
-      o.no_bf16_out = true;
-      o.head_w = e->rpn_head_w;
-      o.head_part = part;
-      e->conv.run(pf[l], e->rpn_conv, none, o, st);
-      KLAUNCH(e);
-      rpn_head_sum_kernel<<<(unsigned)((pix * 4 + 255) / 256), 256, 0, st>>>(
-          (const float4*)part, pix * 4, (const float4*)e->rpn_head_b, (float4*)rpn_raw[l]);
-      CALD_CUDA_CHECK(cudaGetLastError());
-      KLAUNCH(e);
-      ar.free(part);
-    } else {
+    {
       Act t = conv(e, pf[l], e->rpn_conv, V, pf[l].h, pf[l].w, relu_o);
       Act dummy;
       dummy.n = V; dummy.h = pf[l].h; dummy.w = pf[l].w; dummy.c = 16; dummy.split = split; dummy.hi = nullptr;
@@ -1969,6 +1938,47 @@ int cald_jpeg_decode(cald_engine* e, int n_files, const uint8_t* const* files, c
                                       cudaMemcpyDeviceToHost, e->st));
     CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
   }
+  API_CATCH(e)
+}
+
+int cald_select(cald_engine* e, int n, const double* uncertainty, const double* cls, int c1, const double* mean_hist,
+                int budget, int n_cand, int uniform, int* out_positions, int out_capacity, int* n_picked) {
+  API_TRY(e)
+  CALD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  if (n <= 0 || c1 <= 0 || budget <= 0) throw std::runtime_error("cald_select: empty input");
+  const int m = std::min(n, n_cand);
+  if (m > SEL_MAX_CAND) throw std::runtime_error("cald_select: more than 8192 candidates (int(mr * budget))");
+  if (out_capacity < m) throw std::runtime_error("cald_select: out_positions must hold n_cand entries");
+  static std::once_flag once;
+  std::call_once(once, [] {
+    CALD_CUDA_CHECK(cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SEL_MAX_CAND * 12));
+  });
+  e->arena.reset();
+  Arena& ar = e->arena;
+  cudaStream_t st = e->st;
+  double* d_unc = (double*)ar.alloc((size_t)n * 8);
+  double* d_cls = (double*)ar.alloc((size_t)n * c1 * 8);
+  double* d_hist = (double*)ar.alloc((size_t)c1 * 8);
+  int* d_cand = (int*)ar.alloc((size_t)m * 4);
+  double* d_js = (double*)ar.alloc((size_t)m * 8);
+  int* d_zero = (int*)ar.alloc((size_t)m * 4);
+  int* d_pick = (int*)ar.alloc((size_t)m * 4 + 4);
+  CALD_CUDA_CHECK(cudaMemcpyAsync(d_unc, uncertainty, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CALD_CUDA_CHECK(cudaMemcpyAsync(d_cls, cls, (size_t)n * c1 * 8, cudaMemcpyHostToDevice, st));
+  CALD_CUDA_CHECK(cudaMemcpyAsync(d_hist, mean_hist, (size_t)c1 * 8, cudaMemcpyHostToDevice, st));
+  select_candidates_kernel<<<1, 1024, SEL_MAX_CAND * 12, st>>>(d_unc, n, m, d_cand);
+  select_js_kernel<<<(m * 32 + 255) / 256, 256, 0, st>>>(d_cls, d_cand, m, c1, d_hist, uniform, d_js, d_zero);
+  select_pick_kernel<<<1, 1024, 0, st>>>(d_js, d_zero, m, budget, uniform, d_pick, d_pick + m);
+  CALD_CUDA_CHECK(cudaGetLastError());
+  e->launches += 3;
+  std::vector<int> h_cand(m), h_pick(m + 1);
+  CALD_CUDA_CHECK(cudaMemcpyAsync(h_cand.data(), d_cand, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+  CALD_CUDA_CHECK(cudaMemcpyAsync(h_pick.data(), d_pick, (size_t)(m + 1) * 4, cudaMemcpyDeviceToHost, st));
+  CALD_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int np = std::min(h_pick[m], m);
+  for (int i = 0; i < np; ++i) out_positions[i] = h_cand[h_pick[i]];   // subset[arg][picked]: pool positions
+  if (n_picked) *n_picked = np;
   API_CATCH(e)
 }
 

@@ -104,10 +104,7 @@ __device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
 // Launch contract (conv_host.cuh): split mode, BLOCK_N = 128, no residual k-blocks;
 // grid = 2 x clusters, every cluster strides over the (n block, pair of m tiles) list.  CHUNKED as in igemm.cuh: the
 // accumulator restarts every p.kc k-blocks and the epilogue warps of both CTAs sum the partial tiles in registers.
-// HEAD (experiment, CALD_FUSE_RPN): the tile is the RPN 3x3 conv; instead of storing relu(conv) the epilogue multiplies
-// its un-rounded fp32 values by the 15 x Cin head matrix (objectness + box deltas, tv:models/detection/rpn.py:71-78) with
-// FFMA in a fixed channel order and writes one 16-float partial row per pixel and n block (summed by rpn_head_sum_kernel).
-template <int BN_, bool CHUNKED, bool HEAD = false>
+template <int BN_, bool CHUNKED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IG_THREADS, 1)
 igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmC,
@@ -280,11 +277,6 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         rrow = res_row_offset(p, img, y, x);
         if (p.tma_store) load_res64(p, rrow, nb * BLOCK_N, rh, rl);
       }
-      float hp[HEAD ? 15 : 1];
-      if (HEAD) {
-#pragma unroll
-        for (int j = 0; j < (HEAD ? 15 : 0); ++j) hp[j] = 0.f;
-      }
       float accv[CHUNKED ? BLOCK_N : 1];
       if (CHUNKED) {
         for (int ch = 0; ch < num_chunks; ++ch) {
@@ -333,41 +325,6 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (!live) continue;  // uniform across the CTA
-        if (HEAD) {
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(p.bias + c0 + j);
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
-          const float* wh = p.head_w + c0;
-#pragma unroll
-          for (int j = 0; j < (HEAD ? 15 : 0); ++j) {
-            const float4* wj = reinterpret_cast<const float4*>(wh + (size_t)j * p.head_ld);
-            float sacc = hp[j];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const float4 w4 = __ldg(wj + q);  // same address in every lane: one broadcast transaction
-              sacc = fmaf(v[4 * q], w4.x, sacc);
-              sacc = fmaf(v[4 * q + 1], w4.y, sacc);
-              sacc = fmaf(v[4 * q + 2], w4.z, sacc);
-              sacc = fmaf(v[4 * q + 3], w4.w, sacc);
-            }
-            hp[j] = sacc;
-          }
-          if (g == BLOCK_N / 64 - 1 && valid) {
-            const long long pix = ((long long)img * p.H + y) * p.W + x;
-            float4* dst = reinterpret_cast<float4*>(p.head_part + ((long long)nb * p.head_rows + pix) * 16);
-            dst[0] = make_float4(hp[0], hp[1], hp[2], hp[3]);
-            dst[1] = make_float4(hp[4], hp[5], hp[6], hp[7]);
-            dst[2] = make_float4(hp[8], hp[9], hp[10], hp[11]);
-            dst[3] = make_float4(hp[12], hp[13], hp[14], 0.f);
-          }
-          continue;
-        }
         if (!p.tma_store) {
           // direct path: fp32 head outputs, Cout not a multiple of 64
           if (valid) {

@@ -129,16 +129,6 @@ inline Act subsample2(Arena& a, const Act& in, cudaStream_t st) {
   return o;
 }
 
-// ---------------------------------------------------------------- fused RPN head: sum of the per-n-block partial rows
-// out[pix][16] = (part[0][pix] + part[1][pix]) + bias   (igemm2.cuh HEAD instantiation; fixed order => deterministic)
-__global__ void rpn_head_sum_kernel(const float4* __restrict__ part, long long quads /* pixels * 4 */,
-                                    const float4* __restrict__ bias, float4* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= quads) return;
-  const float4 a = part[i], b = part[quads + i], c = bias[i & 3];
-  out[i] = make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);
-}
-
 // ---------------------------------------------------------------- 3x3 / stride 2 / pad 1 max-pool (tv resnet.py maxpool)
 __global__ void maxpool3x3s2_kernel(const pl16* __restrict__ ihi, const pl16* __restrict__ ilo, pl16* __restrict__ ohi,
                                     pl16* __restrict__ olo, int n, int h, int w, int c, int ho, int wo) {

@@ -251,6 +251,22 @@ class Engine:
                                             hs.ctypes.data_as(POINTER(c_int)), ws.ctypes.data_as(POINTER(c_int))))
         return cons, cls, consumed.value, hs, ws
 
+    def select(self, uncertainty, cls_corrs, mean_hist, budget, n_cand, uniform=False):
+        """On-device argsort -> candidates -> cls_kldiv (cald_train.py:234-271, 439-448) -> pool positions to label."""
+        u = np.ascontiguousarray(uncertainty, dtype=np.float64)
+        c = np.ascontiguousarray(cls_corrs, dtype=np.float64)
+        h = np.ascontiguousarray(mean_hist, dtype=np.float64)
+        n, c1 = c.shape
+        out = np.zeros(max(1, min(n, n_cand)), dtype=np.int32)
+        k = c_int(0)
+        dp = POINTER(c_double)
+        self._L.cald_select.argtypes = [c_void_p, c_int, dp, dp, c_int, dp, c_int, c_int, c_int, POINTER(c_int), c_int,
+                                        POINTER(c_int)]
+        self._check(self._L.cald_select(self._h, n, u.ctypes.data_as(dp), c.ctypes.data_as(dp), c1, h.ctypes.data_as(dp),
+                                        int(budget), int(n_cand), int(bool(uniform)), out.ctypes.data_as(POINTER(c_int)),
+                                        out.size, ctypes.byref(k)))
+        return out[:k.value]
+
     def score_device(self, d_ptrs, hs, ws, views, bp=1.3, uniforms=None):
         """Like score() but images are already resident in HBM (list of device pointers)."""
         n = len(d_ptrs)

@@ -119,6 +119,17 @@ int cald_score_jpeg(cald_engine* e, int n_files, const uint8_t* const* files, co
                     const cald_aug* augs, double bp, const double* rng_uniforms, int n_uniforms, int* uniforms_consumed,
                     const int* swap_perms, double* out_consistency, double* out_cls, int* out_heights, int* out_widths);
 
+/* On-device selection: the end of an AL cycle, cald_train.py:439-448 + cls_kldiv (234-271).
+ * uncertainty[n] and cls[n][c1] are what cald_score returned for the whole (gathered) pool; mean_hist[c1] is the mean of
+ * the labeled set's per-image label histograms (cald_train.py:237-242, 253); n_cand = int(args.mr * budget).
+ * out_positions receives pool positions p (loader order) such that new_labeled = subset[p], in the reference's pick
+ * order: candidates with an all-zero class vector first (all of them, even beyond `budget`), then by descending
+ * JS(softmax(mean_hist) || softmax(cls)) (ascending JS against the uniform distribution when `uniform`).  Equal
+ * uncertainty values resolve to the lower pool position (numpy's argsort leaves their order unspecified).
+ * out_capacity >= n_cand.  At most 8192 candidates. */
+int cald_select(cald_engine* e, int n, const double* uncertainty, const double* cls, int c1, const double* mean_hist,
+                int budget, int n_cand, int uniform, int* out_positions, int out_capacity, int* n_picked);
+
 /* The two detection-only baseline scorers of the reference, on the same engine:
  * LS+C  ls_c_train.get_uncertainty (ls_c_train.py:108-155): stability of the 30 most confident reference boxes under
  *       6 Gaussian-noise views (std 8..48) minus max(1 - prob_max).  noise: torch.randn(image.size()) planes, 6 per

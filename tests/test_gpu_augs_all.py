@@ -46,15 +46,9 @@ def test_aug_kinds_match_oracle(setup, augs):
     assert tail_e == tail_o  # both RNG streams left exactly where the reference leaves them
     err = np.abs(np.array(got) - np.array(want))
     print(augs, "engine", np.round(got, 5), "oracle", np.round(want, 5))
-    assert err.max() <= 2e-3, err
-    # Class vectors: means over the 1 + A views of per-class score maxima.  One proposal in ~10^3 may land on the other
-    # side of an NMS / top-k comparison at 16-bit operand precision (tools/conv_accuracy.py: per-layer rms error 1e-6
-    # vs 1e-7 for fp32), which adds or removes ONE low-score detection in ONE view: at most two class maxima move,
-    # each by at most (that detection's score, here < 0.2) / (1 + A); a proposal can carry detections of two classes.
-    n_views = 1 + len(api._aug_kinds(augs))
+    assert err.max() <= 1e-3, err
     for g, wv in zip(got_cls, want_cls):
-        d = np.abs(g - wv)
-        assert (d > 1e-3).sum() <= 2 and d.max() <= 0.2 / n_views, (d.max(), np.where(d > 1e-3)[0])
+        assert np.abs(g - wv).max() <= 1e-3, np.abs(g - wv).max()
 
 
 def test_multi_color_adjust_raises_like_the_reference(setup):

@@ -47,9 +47,7 @@ def test_ls_c_matches_reference_fixture(setup):
     got = np.array(api.ls_c_uncertainty(model, loader))
     print("LS+C engine", got, "reference", g["lsc"])
     err = np.abs(got - g["lsc"])
-    # noisy views carry many low-confidence boxes: one may flip at 16-bit operand precision and move one of the
-    # 30 x 6 best-IoU terms; the pool-level statistic must still agree to 1e-3 on most images and 1e-2 on all
-    assert (err <= 1e-3).mean() >= 0.8 and err.max() <= 1e-2, err
+    assert err.max() <= 1e-3, err
     assert np.array_equal(np.argsort(got), np.argsort(g["lsc"]))  # same selection order
 
 
@@ -74,7 +72,8 @@ def test_engine_model_serves_the_evaluation_loop(setup):
     outs = m([torch.from_numpy(im).permute(2, 0, 1).float().div(255) for im in ims])
     for k, o in enumerate(outs):
         assert set(o) >= {"boxes", "labels", "scores"} and o["labels"].dtype == torch.int64
-        n = min(10, len(det["%d_scores" % k]), len(o["scores"]))
+        assert len(o["scores"]) == len(det["%d_scores" % k])
+        n = len(o["scores"])
         assert np.array_equal(o["labels"].numpy()[:n], det["%d_labels" % k][:n])
         assert np.abs(o["scores"].numpy()[:n] - det["%d_scores" % k][:n]).max() < 1e-3
         assert np.abs(o["boxes"].numpy()[:n] - det["%d_boxes" % k][:n]).max() < 5e-2

@@ -48,7 +48,7 @@ def test_cfg1_voc2007_shape_scores_and_selection():
     got, got_cls = _engine_scores(eng, imgs, augs, seeds)
     err = np.abs(np.array(got) - np.array(want))
     print("cfg-1 engine", np.round(got, 5), "oracle", np.round(want, 5), "err", err)
-    assert (err <= 1e-3).mean() >= 0.85 and np.median(err) <= 2e-4 and err.max() <= 2e-2, err
+    assert err.max() <= 1e-3 and np.median(err) <= 2e-5, err
     # selection: the k most inconsistent images (np.argsort ascending, cald_train.py:439-441) ...
     k = 3
     assert set(np.argsort(got)[:k]) == set(np.argsort(want)[:k])
@@ -83,5 +83,5 @@ def test_cfg4_r101_three_augmentations():
     got, got_cls = _engine_scores(eng, imgs, augs, seeds)
     err = np.abs(np.array(got) - np.array(want))
     print("cfg-4 engine", np.round(got, 5), "oracle", np.round(want, 5), "err", err)
-    assert np.median(err) <= 1e-3 and err.max() <= 2e-2, err
+    assert err.max() <= 1e-3, err
     eng.close()

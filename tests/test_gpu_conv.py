@@ -2,8 +2,8 @@
 
 Oracle for this stage = torch.nn.functional.conv2d on CPU in fp32 (the exact op the
 reference's CPU run executes: tv resnet.py / feature_pyramid_network.py / rpn.py).
-Tolerances: split-bf16 x3 mode carries ~16 mantissa bits per operand -> relative
-error ~2e-5 of the output scale; single-pass bf16 ~1e-2.
+Tolerances: the split-half x3 mode carries 22 significand bits per operand and the truncating accumulate is
+pre-compensated: error at the fp32 level (~1e-6 of the output scale); single-pass half ~1e-3.
 """
 import os
 
@@ -70,15 +70,21 @@ def test_conv_split_matches_fp32(case, impl):
     got = ops.conv2d(x, wt, b, stride=stride, relu=True, res=res, res_mode=res_mode, prec=0, impl=impl)
     scale = np.abs(want).max()
     err = np.abs(got - want).max()
-    assert err <= 3e-5 * scale + 1e-6, (err, scale)
+    assert err <= 5e-6 * scale + 1e-6, (err, scale)
 
 
 @pytest.mark.parametrize("block_n", [64, 128, 256])
 def test_conv_block_n_variants(block_n):
     from cald_b200 import ops
+    from cald_b200._lib import CaldError
     x, wt, b, _ = _case(7, 1, 24, 40, 128, 256, 3)
     want = _ref(x, wt, b, 1, False)
-    for prec, tol in ((0, 3e-5), (1, 2e-2)):
+    for prec, tol in ((0, 5e-6), (1, 2e-3)):
+        if prec == 0 and block_n == 256:
+            # the split-half format keeps the (scaled) cross terms in their own accumulator columns: BLOCK_N <= 128
+            with pytest.raises(CaldError):
+                ops.conv2d(x, wt, b, prec=prec, impl=0, block_n=block_n)
+            continue
         got = ops.conv2d(x, wt, b, prec=prec, impl=0, block_n=block_n)
         assert np.abs(got - want).max() <= tol * np.abs(want).max()
 
@@ -94,7 +100,7 @@ def test_conv_stride2_odd_sizes():
         for impl in (0, 1):
             got = ops.conv2d(x, wt, b, stride=2, relu=True, prec=0, impl=impl)
             assert got.shape == want.shape
-            assert np.abs(got - want).max() <= 3e-5 * np.abs(want).max() + 1e-6, (n, h, w, cin, cout, k, impl)
+            assert np.abs(got - want).max() <= 5e-6 * np.abs(want).max() + 1e-6, (n, h, w, cin, cout, k, impl)
 
 
 def test_conv_large_k_chunked_accumulation():
@@ -159,7 +165,7 @@ def test_conv_cta_pair_kernel_matches_fp32_and_single_cta(case, monkeypatch):
     got = ops.conv2d(x, wt, b, stride=stride, relu=True, res=res, res_mode=res_mode, prec=0, impl=0)
     assert L.cald_ops_pair_launches() == before + 1, "the launch did not take the pair kernel"
     scale = np.abs(want).max()
-    assert np.abs(got - want).max() <= 3e-5 * scale + 1e-6
+    assert np.abs(got - want).max() <= 5e-6 * scale + 1e-6
     # same split operands, same cross-term-separated accumulation: the two kernels agree far below the fp32 tolerance
     assert np.abs(got - single).max() <= 2e-6 * scale + 1e-7
 
@@ -190,23 +196,4 @@ def test_conv_fused_projection_shortcut(case):
     want = F.relu(a + b).permute(0, 2, 3, 1).contiguous().numpy()
     got = ops.conv2d_dual(y, w3, b3, x, wd, bd, stride2=s2, relu=True)
     assert got.shape == want.shape
-    assert np.abs(got - want).max() <= 3e-5 * np.abs(want).max() + 1e-6
-
-
-@pytest.mark.skipif(os.environ.get("CALD_TEST_EXPERIMENTAL") != "1",
-                    reason="CALD_RESMMA_MAX_KB is an experiment switch that has not run on a B200 yet "
-                           "(the round's GPU budget was spent); set CALD_TEST_EXPERIMENTAL=1 to run it")
-def test_conv_shortcut_in_epilogue_registers(monkeypatch):
-    """CALD_RESMMA_MAX_KB limits the residual-as-MMA form to short contractions; above it the same-shape shortcut is
-    added in the epilogue registers.  Both forms against torch fp32 and against each other."""
-    from cald_b200 import ops
-    case = (2, 19, 25, 256, 1024, 1, 1, 1, None)
-    n, h, w, cin, cout, k, stride, res_mode, res_hw = case
-    x, wt, b, res = _case(11, n, h, w, cin, cout, k, stride, True, True, res_mode, res_hw)
-    want = _ref(x, wt, b, stride, True, res, res_mode)
-    outs = {}
-    for lim in ("1000000", "2"):
-        monkeypatch.setenv("CALD_RESMMA_MAX_KB", lim)
-        outs[lim] = ops.conv2d(x, wt, b, relu=True, res=res, res_mode=1, prec=0, impl=0)
-        assert np.abs(outs[lim] - want).max() <= 3e-5 * np.abs(want).max() + 1e-6, lim
-    assert np.abs(outs["2"] - outs["1000000"]).max() <= 4e-6 * np.abs(want).max()
+    assert np.abs(got - want).max() <= 5e-6 * np.abs(want).max() + 1e-6

@@ -39,18 +39,18 @@ def test_dense_stages_match_oracle(setup):
         want = _nhwc(st["c"][i])
         got = eng.debug_fetch(name).reshape(want.shape)
         err = np.abs(got - want).max() / np.abs(want).max()
-        assert err < 2e-4, (name, err)
+        assert err < 2e-5, (name, err)
     for i, name in enumerate(("p2", "p3", "p4", "p5", "p6")):
         want = _nhwc(st["p"][i])
         got = eng.debug_fetch(name).reshape(want.shape)
         err = np.abs(got - want).max() / np.abs(want).max()
-        assert err < 3e-4, (name, err)
+        assert err < 2e-5, (name, err)
     for l in range(5):
         lg, dl = st["rpn"][l]
         h, wd = st["p"][l].shape[-2:]
         got = eng.debug_fetch("rpn%d" % l).reshape(h, wd, 16)
-        assert np.abs(got[..., :3].reshape(-1) - lg.numpy()).max() < 2e-3
-        assert np.abs(got[..., 3:15].reshape(-1, 4) - dl.numpy()).max() < 1e-3
+        assert np.abs(got[..., :3].reshape(-1) - lg.numpy()).max() < 1e-4
+        assert np.abs(got[..., 3:15].reshape(-1, 4) - dl.numpy()).max() < 1e-4
 
 
 def test_roialign_matches_oracle_on_engine_inputs(setup):
@@ -89,11 +89,9 @@ def test_proposals_match_oracle(setup):
     n = int(eng.debug_fetch("proposal_count")[0])
     got = eng.debug_fetch("proposals").reshape(-1, 4)[:n]
     want = st["proposals"].numpy()
-    assert abs(n - len(want)) <= 2
-    # same set of proposals up to fp32-level coordinate noise: match each oracle box to its nearest engine box
-    d = np.abs(want[:, None, :] - got[None, :, :]).max(-1)
-    frac = (d.min(1) < 5e-2).mean()
-    assert frac > 0.99, frac
+    assert n == len(want)
+    # the same proposals in the same order (score-sorted, tv:rpn.py:242-297), up to fp32-level coordinate noise
+    assert np.abs(want - got).max() < 5e-2
 
 
 def test_detections_match_oracle(setup):
@@ -103,9 +101,9 @@ def test_detections_match_oracle(setup):
     for img, got in zip(imgs, outs):
         want = fo.forward(torch.from_numpy(img).permute(2, 0, 1).float().div(255), w, cfg)
         nw = len(want["scores"])
-        assert abs(len(got["scores"]) - nw) <= 1
-        k = min(len(got["scores"]), nw, 10)
-        # the confident head of the list must agree in order, label, score and box
+        assert len(got["scores"]) == nw
+        k = nw
+        # the whole list must agree in order, label, score and box
         assert np.array_equal(got["labels"][:k], want["labels"].numpy()[:k])
         assert np.abs(got["scores"][:k] - want["scores"].numpy()[:k]).max() < 1e-3
         assert np.abs(got["boxes"][:k] - want["boxes"].numpy()[:k]).max() < 5e-2
@@ -126,34 +124,4 @@ def test_simt_and_tcgen05_paths_agree(setup):
     pa, pb = e1.debug_fetch("p2"), e2.debug_fetch("p2")
     assert np.abs(pa - pb).max() / np.abs(pb).max() < 1e-4
     k = min(len(a["scores"]), len(b["scores"]), 10)
-    assert np.abs(a["scores"][:k] - b["scores"][:k]).max() < 1e-3
-
-
-@pytest.mark.skipif(__import__("os").environ.get("CALD_TEST_EXPERIMENTAL") != "1",
-                    reason="CALD_FUSE_RPN is an experiment switch that has not run on a B200 yet; "
-                           "set CALD_TEST_EXPERIMENTAL=1 to run it")
-def test_fused_rpn_head_matches_separate_launches(setup, monkeypatch):
-    """CALD_FUSE_RPN=1 folds the RPN 1x1 heads into the 3x3 RPN conv's epilogue (fp32 FFMA on the un-rounded activations).
-    Objectness logits / box deltas must agree with the two-launch form and with the oracle; detections must agree."""
-    eng, w, cfg, fo, synth = setup
-    from cald_b200.engine import Engine
-    img = synth.synth_image(5, 200, 300)
-    st = {}
-    fo.forward(torch.from_numpy(img).permute(2, 0, 1).float().div(255), w, cfg, st)
-    monkeypatch.setenv("CALD_FUSE_RPN", "1")
-    e2 = Engine(depth=50, num_classes=21, min_size=320, max_size=512, debug=True, max_views_per_pass=4)
-    e2.load_state_dict(w)
-    a = eng.detect([img])[0]
-    b = e2.detect([img])[0]
-    for l in range(5):
-        lg, dl = st["rpn"][l]
-        h, wd = st["p"][l].shape[-2:]
-        sep = eng.debug_fetch("rpn%d" % l).reshape(h, wd, 16)
-        fus = e2.debug_fetch("rpn%d" % l).reshape(h, wd, 16)
-        assert np.abs(fus[..., :15] - sep[..., :15]).max() < 2e-3
-        assert np.abs(fus[..., :3].reshape(-1) - lg.numpy()).max() < 2e-3
-        assert np.abs(fus[..., 3:15].reshape(-1, 4) - dl.numpy()).max() < 1e-3
-    k = min(len(a["scores"]), len(b["scores"]), 10)
-    assert abs(len(a["scores"]) - len(b["scores"])) <= 1
-    assert np.array_equal(a["labels"][:k], b["labels"][:k])
     assert np.abs(a["scores"][:k] - b["scores"][:k]).max() < 1e-3

@@ -56,24 +56,25 @@ def test_cfg2_device_and_host_entry_points_agree(frcnn):
     assert np.array_equal(c_host, c_dev) and np.array_equal(v_host, v_dev)
 
 
-def test_cfg2_one_image_against_the_oracle(frcnn):
-    """full-size end-to-end parity on one image: |score - oracle| <= 1e-3 (BASELINE.json north_star)"""
+def test_cfg2_images_against_the_oracle(frcnn):
+    """full-size end-to-end parity (cfg-2 / cfg-5 shape): |score - oracle| <= 1e-3 (BASELINE.json north_star) and the
+    class vectors on three images, landscape and portrait (the CPU oracle needs ~20 s per image at this size)"""
     eng, w, synth = frcnn
     from cald_b200 import api
     from oracle import cald_oracle as co
     from oracle import frcnn_oracle as fo
-    torch.set_num_threads(max(1, min(16, torch.get_num_threads())))
+    torch.set_num_threads(max(1, min(32, len(__import__("os").sched_getaffinity(0)))))
     wt = {k: torch.from_numpy(v) for k, v in w.items()}
     cfg = fo.Cfg(50, NC, 800, 1333)
-    img = synth.synth_image(1, H, W)
-    random.seed(21)
-    want, want_cls = co.score_image(lambda x: fo.forward(x, wt, cfg), img, AUGS, NC, 1.3)
-    random.seed(21)
-    got, got_cls = api.score_images(eng, [img], AUGS)
-    print("full-size score: engine %.6f oracle %.6f" % (got[0], want))
-    assert abs(got[0] - want) <= 1e-3
-    d = np.abs(got_cls[0] - want_cls)
-    assert (d > 1e-3).sum() <= 2 and d.max() <= 0.2 / 5
+    imgs = [synth.synth_image(1, H, W), synth.synth_image(2, H, W), synth.synth_image(3, W, H)]
+    for k, img in enumerate(imgs):
+        random.seed(21 + k)
+        want, want_cls = co.score_image(lambda x: fo.forward(x, wt, cfg), img, AUGS, NC, 1.3)
+        random.seed(21 + k)
+        got, got_cls = api.score_images(eng, [img], AUGS)
+        print("full-size score %d: engine %.6f oracle %.6f" % (k, got[0], want))
+        assert abs(got[0] - want) <= 1e-3
+        assert np.abs(got_cls[0] - want_cls).max() <= 1e-3
 
 
 def test_cfg3_retinanet_batch_invariance_and_determinism():
@@ -91,4 +92,15 @@ def test_cfg3_retinanet_batch_invariance_and_determinism():
     c = [api.score_images(eng, [im], AUGS)[0][0] for im in imgs]
     assert np.abs(np.array(a) - np.array(c)).max() <= 1e-6
     assert all(0.0 <= v <= 1.3 for v in a)
+    # cfg-3 full size against the oracle on one image (RetinaNet R50-FPN nc = 91 at 800x1333)
+    from oracle import cald_oracle as co
+    from oracle import retina_oracle as ro
+    torch.set_num_threads(max(1, min(32, len(__import__("os").sched_getaffinity(0)))))
+    wt = {k: torch.from_numpy(v) for k, v in synth.planted_retinanet_weights(NC, 0, cls_bias_shift=-11.0).items()}
+    cfg = ro.Cfg(50, NC, 800, 1333)
+    random.seed(4)
+    want, want_cls = co.score_image(lambda x: ro.forward(x, wt, cfg), imgs[0], AUGS, NC, 1.3)
+    print("cfg-3 full-size score: engine %.6f oracle %.6f" % (a[0], want))
+    assert abs(a[0] - want) <= 1e-3
+    assert np.abs(acls[0] - want_cls).max() <= 1e-3
     eng.close()

@@ -32,8 +32,8 @@ def test_detections_match_reference_fixture(eng):
     outs = eng.detect(imgs)
     for k, got in enumerate(outs):
         want_scores = g["%d_scores" % k]
-        assert abs(len(got["scores"]) - len(want_scores)) <= 1
-        n = min(10, len(want_scores), len(got["scores"]))
+        assert len(got["scores"]) == len(want_scores)      # every row of the detection list, not only its head
+        n = len(want_scores)
         assert np.array_equal(got["labels"][:n], g["%d_labels" % k][:n])
         assert np.abs(got["scores"][:n] - want_scores[:n]).max() < 1e-3
         assert np.abs(got["boxes"][:n] - g["%d_boxes" % k][:n]).max() < 5e-2
@@ -76,5 +76,4 @@ def test_topk_selection_identical(eng):
     for img, s in zip(imgs, g["seeds"]):
         random.seed(int(s))
         cons.append(api.score_images(eng, [img], AUGS)[0][0])
-    k = 2
-    assert set(np.argsort(cons)[:k]) == set(np.argsort(g["consistency"])[:k])
+    assert np.array_equal(np.argsort(cons), np.argsort(g["consistency"]))   # the complete selection order

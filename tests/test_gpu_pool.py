@@ -58,9 +58,17 @@ def test_pool_scores_selection_and_class_vectors(kind):
         kind, np.median(err), np.percentile(err, 90), err.max(), np.where(err > 1e-3)[0].tolist()))
     # the reference's own two runs (8 vs 3 intra-op threads) agree exactly on this pool, so every deviation is ours
     assert np.abs(g["noise_consistency"] - g["consistency"]).max() == 0.0
-    assert (err <= 1e-3).mean() >= 0.99, np.where(err > 1e-3)[0]
-    assert np.median(err) <= 2e-5
-    assert (cerr <= 1e-3).mean() >= 0.97, np.where(cerr > 1e-3)[0]
+    assert np.median(err) <= 5e-6
+    if kind == "frcnn":
+        # measured (profiles/r02_parity.md): max 6.3e-6 over the 100 images
+        assert err.max() <= 1e-4, (err.max(), np.where(err > 1e-4)[0])
+        # image 37: two detections of the reference view whose scores differ by 8.5e-7 swap ranks 86 / 87, which moves
+        # the 50-point linspace sub-sample (cald_train.py:110-113) to the other one; its score is unaffected
+        assert (cerr > 1e-3).sum() <= 1, np.where(cerr > 1e-3)[0]
+    else:
+        # image 24 (1.27e-3): one class-0 box of the reference view sits on the NMS IoU threshold 0.5 to within 1e-6
+        assert (err > 1e-3).sum() <= 1 and err.max() <= 2e-3, (err.max(), np.where(err > 1e-3)[0])
+        assert (cerr > 1e-3).sum() <= 2, np.where(cerr > 1e-3)[0]
     # selection with the reference's inline code path on the engine's scores: the identical index set (north_star)
     sel = api.select(list(cons), [c for c in cls], list(g["subset"]), _Labeled(g["label_rows"]), int(g["budget"]))
     assert sorted(int(v) for v in sel) == sorted(int(v) for v in g["selected"])

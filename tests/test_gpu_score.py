@@ -50,17 +50,11 @@ def test_scores_match_oracle(setup):
     per_view = None
     err = np.abs(np.array(got_c) - np.array(want_c))
     print("scores engine", np.round(got_c, 5), "oracle", np.round(want_c, 5))
-    assert (err <= 1e-3).mean() >= 0.8, err
-    assert np.median(err) <= 2e-4, err
-    # Class vectors: every entry within 1e-3, except that one RPN proposal in ~10^4 lands on the other side of a
-    # top-k / NMS threshold at 16-bit operand precision (tools/diag_views.py shows 1 of 1000 proposals differing in
-    # one flip view here); such a flip moves ONE class maximum of ONE view, i.e. <= max_score / (1 + A) in the mean.
-    n_flipped = 0
+    # hard bound on every image (north_star: 1e-3); the split-half operands + truncation pre-compensation put the
+    # engine within ~2x of the fp32 CPU run's own rounding noise (tools/stage_error.py), so 1e-4 holds with margin
+    assert err.max() <= 1e-4, err
     for g, wv in zip(got_v, want_v):
-        d = np.abs(g - wv)
-        assert (d > 1e-3).sum() <= 1 and d.max() <= 2e-2, d
-        n_flipped += int((d > 1e-3).sum())
-    assert n_flipped <= 1
+        assert np.abs(g - wv).max() <= 1e-3, np.abs(g - wv)
 
 
 def test_rng_stream_is_consumed_like_the_reference(setup):
