@@ -204,12 +204,24 @@ def clip_boxes(boxes, hw):
     return b
 
 
+# Timing mode (bench.py's CPU arm only): run NMS and RoIAlign through torchvision's own CPU kernels -- the very
+# kernels the reference calls (tv:ops/boxes.py nms, tv:ops/roi_align.py) -- instead of the numpy restatements below,
+# which are 1.3-1.8x slower per image than the reference's loop (profiles/r02_cpu_port_vs_reference.md) and would
+# flatter the GPU/CPU ratio.  Results are bit-identical either way (tests/test_oracle_kat.py); the parity tests keep
+# the independent numpy restatements.
+USE_TORCHVISION_OPS = False
+
+
 def nms_numpy(boxes, scores, thresh):
     """Greedy NMS, same arithmetic as torchvision's CPU kernel (fp32; > thresh suppresses).
 
     Candidates are visited by descending score with ties broken by ascending index
     (stable); returns kept indices in that order.
     """
+    if USE_TORCHVISION_OPS:
+        import torchvision
+        return torchvision.ops.nms(torch.as_tensor(np.asarray(boxes, dtype=np.float32)),
+                                   torch.as_tensor(np.asarray(scores, dtype=np.float32)), float(thresh)).numpy()
     boxes = np.asarray(boxes, dtype=np.float32)
     scores = np.asarray(scores, dtype=np.float32)
     n = boxes.shape[0]
@@ -282,6 +294,10 @@ def roi_align_level(feat, rois, scale, out=7, sr=2):
     k = rois.shape[0]
     if k == 0:
         return feat.new_zeros((0, c, out, out))
+    if USE_TORCHVISION_OPS:
+        import torchvision
+        return torchvision.ops.roi_align(feat[None], [rois], (out, out), spatial_scale=scale, sampling_ratio=sr,
+                                         aligned=False)
     x1 = rois[:, 0] * scale
     y1 = rois[:, 1] * scale
     x2 = rois[:, 2] * scale

@@ -73,7 +73,8 @@ def test_pool_scores_selection_and_class_vectors(kind):
     sel = api.select(list(cons), [c for c in cls], list(g["subset"]), _Labeled(g["label_rows"]), int(g["budget"]))
     assert sorted(int(v) for v in sel) == sorted(int(v) for v in g["selected"])
     k = int(g["budget"])
-    assert set(np.argsort(cons)[:k]) == set(np.argsort(g["consistency"])[:k])
+    # (stable sort: the RetinaNet pool has 12 images that tie at exactly 0.0 -- no reference detections)
+    assert set(np.argsort(cons, kind="stable")[:k]) == set(np.argsort(g["consistency"], kind="stable")[:k])
     eng.close()
 
 

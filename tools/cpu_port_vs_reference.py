@@ -35,8 +35,9 @@ def main():
     print("# CPU arm calibration: oracle port vs the unmodified reference\n", file=out)
     print("Host: %d threads, torch %s.  One warm-up image, then n timed images; python RNG seeded identically.\n" % (
         threads, torch.__version__), file=out)
-    print("| workload | n | unmodified `cald_train.get_uncertainty` s/image | oracle port s/image | port / reference | "
-          "max abs score difference |", file=out)
+    print("| workload | n | unmodified `cald_train.get_uncertainty` s/image | oracle port, numpy NMS / RoIAlign (parity "
+          "tests) s/image | oracle port, torchvision NMS / RoIAlign kernels (bench.py CPU arm) s/image | max abs score "
+          "difference vs the reference (both ports) |", file=out)
     print("|---|---|---|---|---|---|", file=out)
     for name, nc, h, w, mn, mx, n in CASES:
         wnp = synth.planted_frcnn_weights(50, nc, 0)
@@ -59,14 +60,20 @@ def main():
         t = time.time()
         ref, _ = ct.get_uncertainty(m, L(imgs[1:]), AUGS, nc)
         t_ref = (time.time() - t) / n
-        random.seed(1)
         fwd = lambda x: fo.forward(x, wt, cfg)  # noqa: E731
-        co.score_image(fwd, imgs[0], AUGS, nc, 1.3)
-        t = time.time()
-        port = [co.score_image(fwd, im, AUGS, nc, 1.3)[0] for im in imgs[1:]]
-        t_port = (time.time() - t) / n
-        d = float(np.abs(np.array(ref, dtype=np.float64) - np.array(port, dtype=np.float64)).max())
-        print("| %s | %d | %.2f | %.2f | %.2f | %.1e |" % (name, n, t_ref, t_port, t_port / t_ref, d), file=out)
+        res = {}
+        for fast in (False, True):
+            fo.USE_TORCHVISION_OPS = fast
+            random.seed(1)
+            co.score_image(fwd, imgs[0], AUGS, nc, 1.3)
+            t = time.time()
+            port = [co.score_image(fwd, im, AUGS, nc, 1.3)[0] for im in imgs[1:]]
+            res[fast] = ((time.time() - t) / n,
+                         float(np.abs(np.array(ref, dtype=np.float64) - np.array(port, dtype=np.float64)).max()))
+        fo.USE_TORCHVISION_OPS = False
+        print("| %s | %d | %.2f | %.2f (x%.2f) | %.2f (x%.2f) | %.1e / %.1e |" % (
+            name, n, t_ref, res[False][0], res[False][0] / t_ref, res[True][0], res[True][0] / t_ref, res[False][1],
+            res[True][1]), file=out)
         out.flush()
 
 
