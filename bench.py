@@ -232,9 +232,9 @@ def run_reference(args, cfg, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=16, help="images per step per GPU")
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="images per step per GPU (one engine chunk = 64 images)")
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="BASELINE.json configuration (default cfg2)")
     ap.add_argument("--model", default=None, choices=["frcnn", "retinanet"], help="shorthand: retinanet = --config cfg3")
@@ -447,7 +447,7 @@ def run_cycle(args, cfg, eng, rank, local_rank, world, barrier, max_over_ranks):
     from cald_b200 import api, shard
     AUGS = cfg["augs"]
     H, W = cfg["hw"]
-    P = args.pool or 128 * args.steps
+    P = args.pool or 2048
     budget = args.budget or (1000 if P >= 2400 else max(1, P // 8))
     make = Pool(H, W, seed=1)          # the same pool on every rank; a rank only touches its own shard
     # the loader stand-in: this rank's shard decoded into (pageable) host memory before the clock starts, like images
@@ -465,7 +465,7 @@ def run_cycle(args, cfg, eng, rank, local_rank, world, barrier, max_over_ranks):
     sampler.start()
     t0 = time.time()
     eng.event_record(0)
-    cons, cls = shard.get_uncertainty_sharded(eng, fetch, AUGS, rank, world, n=P, chunk=4 * args.batch)
+    cons, cls = shard.get_uncertainty_sharded(eng, fetch, AUGS, rank, world, n=P, chunk=2 * args.batch)
     eng.event_record(1)
     t_score = time.time() - t0
     t1 = time.time()

@@ -124,7 +124,7 @@ def score_images(eng, images, augs, chunk=None):
     n_swap = sum(1 for k, _ in views if k == _eng.AUG_COLOR_SWAP)
     has_noise = any(k in _eng.NOISE_KINDS for k, _ in views)
     if chunk is None:
-        chunk = 4 * eng.images_per_chunk(len(views))  # several engine passes per call: the upload pipeline overlaps them
+        chunk = 2 * eng.images_per_chunk(len(views))  # several engine passes per call: the upload pipeline overlaps them
     if (n_swap or has_noise) and n_cut:
         # swap / noise draws of an image precede the same image's data-dependent cutout draws in the reference's
         # streams: keep both exact by scoring one image per call
@@ -182,7 +182,7 @@ def get_uncertainty_files(task_model, paths, augs, num_cls, device=0, **engine_k
         raise ValueError("noise augmentations ('ga', 'sp', ...) are not available on the file path; use get_uncertainty")
     n_cut = sum(1 for k, _ in views if k == _eng.AUG_CUTOUT)
     n_swap = sum(1 for k, _ in views if k == _eng.AUG_COLOR_SWAP)
-    group = 1 if (n_swap and n_cut) else 4 * eng.images_per_chunk(max(1, len(views)))
+    group = 1 if (n_swap and n_cut) else 2 * eng.images_per_chunk(max(1, len(views)))
 
     def read(p):
         if isinstance(p, (bytes, bytearray, memoryview)):
@@ -261,7 +261,7 @@ def get_uncertainty(task_model, unlabeled_loader, augs, num_cls, device=0, **eng
     loader while the current one is on the GPU.
     """
     eng = engine_for(task_model, num_cls, device, **engine_kw)
-    group = 4 * eng.images_per_chunk(max(1, len(_eng.expand_augs(augs))))
+    group = 2 * eng.images_per_chunk(max(1, len(_eng.expand_augs(augs))))
     cons_all, cls_all, pending = [], [], []
 
     def flush():

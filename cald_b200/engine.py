@@ -389,10 +389,10 @@ class Engine:
     def views_per_pass(self):
         return int(self._L.cald_views_per_pass(self._h))
 
-    def images_per_chunk(self, n_augs):
-        """Images the engine scores per pass (reference views of a chunk run as one batch, its augmented views as
-        another)."""
-        return max(1, self.views_per_pass() // max(1, n_augs))
+    def images_per_chunk(self, n_augs=0):
+        """Images the engine scores per chunk: as many as one pass holds views (a chunk's reference views run as one
+        full pass, its augmented views as n_augs more)."""
+        return max(1, self.views_per_pass())
 
     def arena_peak(self):
         self._L.cald_arena_peak.restype = c_longlong

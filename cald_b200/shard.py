@@ -44,7 +44,7 @@ def get_uncertainty_sharded(eng, pool, augs, rank, world, group=None, n=None, ch
     fetch = pool if callable(pool) else (lambda i: pool[i])
     n = len(pool) if n is None else n
     mine = shard_indices(n, rank, world)
-    step = chunk or 4 * eng.images_per_chunk(max(1, len(api._aug_kinds(augs))))
+    step = chunk or 2 * eng.images_per_chunk(max(1, len(api._aug_kinds(augs))))
     cons, cls = [], []
     for pos in range(0, len(mine), step):
         c, v = api.score_images(eng, [api._to_u8(fetch(int(i))) for i in mine[pos:pos + step]], augs)
