@@ -250,6 +250,8 @@ def main():
     ap.add_argument("--workspace-gb", type=float, default=0.0, help="device arena size (0 = half of free memory)")
     ap.add_argument("--views-per-pass", type=int, default=0, help="engine max_views_per_pass (0 = the engine's own auto)")
     ap.add_argument("--layers", default=None, help="write the per-layer conv timing table (TSV) to this path")
+    ap.add_argument("--quick", action="store_true",
+                    help="skip the instrumented (roofline) and pageable-host legs: value + e2e only (multi-GPU runs)")
     ap.add_argument("--only-value", action="store_true",
                     help="run the device-resident leg only (for short runs under ncu; prints no JSON line)")
     args = ap.parse_args()
@@ -356,10 +358,13 @@ def main():
         return
     value = world * B * args.steps / (ms / 1000.0)
     # ---------------- leg 2: the same steps with per-launch CUDA events on the conv kernels (roofline)
-    ms_instr, _ = resident_pass(True)
-    conv_ms, conv_launches, conv_flops = eng.profile_read()
-    conv_bytes = sum(r[4] for r in eng.profile_layers()) * 1e6  # algorithmic HBM bytes of the timed conv launches
-    if args.layers and rank == 0:
+    if args.quick:
+        ms_instr, conv_ms, conv_launches, conv_flops, conv_bytes = ms, 0.0, 0, 0.0, 0.0
+    else:
+        ms_instr, _ = resident_pass(True)
+        conv_ms, conv_launches, conv_flops = eng.profile_read()
+        conv_bytes = sum(r[4] for r in eng.profile_layers()) * 1e6  # algorithmic HBM bytes of the timed conv launches
+    if args.layers and rank == 0 and not args.quick:
         rows = sorted(eng.profile_layers(), key=lambda r: -r[2])
         with open(args.layers, "w") as f:
             f.write("layer\tcount\tms_total\tus_per_launch\tTFLOPs_algorithmic\tGBs_algorithmic\tshare\n")
@@ -388,9 +393,12 @@ def main():
         return world * B * args.steps / (max_over_ranks(max(eng.event_elapsed_ms(2, 3), 1000.0 * t_wall)) / 1000.0)
 
     e2e = e2e_pass(pool)
-    pageable = [np.array(a, copy=True) for a in pool[:B * n_steps_total]]
-    e2e_pageable = e2e_pass(pageable)
-    del pageable
+    if args.quick:
+        e2e_pageable = None
+    else:
+        pageable = [np.array(a, copy=True) for a in pool[:B * n_steps_total]]
+        e2e_pageable = e2e_pass(pageable)
+        del pageable
 
     if rank != 0:
         if world > 1:
@@ -412,8 +420,9 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3 + 200 * B * 8,
                 "d2h_bytes_per_step": B * (A + (1 + A) * (cfg["nc"] - 1) + 1) * 4 + 4,
-                "host_memory": "page-locked", "pageable": {"value": e2e_pageable, "unit": "images/s"}},
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "host_memory": "page-locked",
+                "pageable": None if e2e_pageable is None else {"value": e2e_pageable, "unit": "images/s"}},
+        "roofline": None if args.quick else {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None,
                      "frac_of_x3_ceiling": 3.0 * achieved / peak_tf if peak_tf else None,
                      "traffic": NCU_DRAM_BYTES_PER_CONV_LAUNCH if (name == "cfg2" and B == NCU_DRAM_BATCH) else None,
