@@ -141,3 +141,39 @@ def test_baseline_scorers_oracle_matches_reference_fixture(model):
     torch.manual_seed(int(g["lsc_seed"]))
     got = co.lsc_stability(fwd, imgs[:1])
     assert abs(got[0] - g["lsc"][0]) <= 1e-4
+
+
+def test_oracle_matches_pool_fixture_and_timing_mode_is_bit_identical():
+    """The 100-image pool fixture (tests/golden/make_golden_pool.py, unmodified reference): the oracle reproduces the
+    first images exactly, also in its timing mode (NMS / RoIAlign through torchvision's CPU kernels, what bench.py's
+    CPU arm runs), and the recorded per-view detections are what the oracle's forward returns."""
+    from cald_b200 import synth
+    from oracle import cald_oracle as co
+    from oracle import frcnn_oracle as fo
+    g = np.load(os.path.join(GOLD, "pool_frcnn_r50_nc21.npz"))
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    w = {k: torch.from_numpy(v) for k, v in synth.planted_frcnn_weights(50, 21, 0).items()}
+    cfg = fo.Cfg(50, 21, int(g["min_size"]), int(g["max_size"]))
+    fwd = lambda x: fo.forward(x, w, cfg)  # noqa: E731
+    idx, h, wd = (int(v) for v in g["images"][0])
+    img = synth.synth_image(idx, h, wd)
+    results = []
+    for fast in (False, True):
+        fo.USE_TORCHVISION_OPS = fast
+        try:
+            random.seed(int(g["seeds"][0]))
+            tr = {}
+            c, v = co.score_image(fwd, img, AUGS, 21, 1.3, trace=tr)
+        finally:
+            fo.USE_TORCHVISION_OPS = False
+        results.append((float(c), np.asarray(v), tr))
+    assert results[0][0] == results[1][0] and np.array_equal(results[0][1], results[1][1])
+    assert abs(results[0][0] - float(g["consistency"][0])) <= 5e-6
+    assert np.abs(results[0][1] - g["cls"][0]).max() <= 5e-6
+    assert np.abs(np.array(results[0][2]["per_view"]) - g["per_view"][0]).max() <= 5e-6
+    # recorded detections of the reference view == the oracle's reference forward
+    a, b = int(g["det_offsets"][0]), int(g["det_offsets"][1])
+    ref = results[0][2]["ref_full"]
+    assert len(ref["scores"]) == b - a
+    assert np.abs(ref["scores"].numpy() - g["det_scores"][a:b]).max() <= 2e-5
+    assert np.array_equal(ref["labels"].numpy(), g["det_labels"][a:b].astype(np.int64))
