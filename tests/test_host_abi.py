@@ -108,3 +108,23 @@ def test_bench_prints_exactly_one_json_line_on_stdout():
     assert r.returncode == 0, r.stderr
     assert r.stdout == '{"metric": "m", "value": 1.5}\n'
     assert "library noise" in r.stderr and "raw fd-1 noise" in r.stderr
+
+
+def test_bench_reference_arm_emits_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the engine arm): one JSON line with the contract
+    keys, the same `config` object the engine arm emits, kind "port"."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "cfg4",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    want = bench.common_config(bench.CONFIGS["cfg4"], argparse.Namespace(mode="weak"))
+    assert d["config"] == want            # identical in both arms (the driver's same_config check)
