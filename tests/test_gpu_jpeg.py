@@ -87,3 +87,40 @@ def test_unsupported_files_fail_loudly(eng):
     good = jpeg_bytes(img, quality=80)
     out = eng.decode_jpeg([good[:len(good) // 2]])
     assert out[0].shape == (64, 64, 3)
+
+
+def test_get_uncertainty_files_equals_the_pil_loader_path(tmp_path):
+    """The pool given as JPEG paths (decoded on the device) against the same files through PIL and the reference-style
+    loader entry point: identical scores, class vectors and python RNG position."""
+    import torch
+    import cald_b200
+    from cald_b200 import synth
+
+    class ModelLike:
+        def __init__(self, w):
+            self.sd = {k: torch.from_numpy(v) for k, v in w.items()}
+            self.transform = type("T", (), {"min_size": (320,), "max_size": 512})()
+
+        def state_dict(self):
+            return self.sd
+
+    model = ModelLike(synth.planted_frcnn_weights(50, 21, 0))
+    paths = []
+    for i in range(7):
+        p = tmp_path / ("img%d.jpg" % i)
+        h, w = ((200, 300), (300, 200), (167, 250))[i % 3]
+        Image.fromarray(synth.synth_image(40 + i, h, w)).save(str(p), format="JPEG", quality=88)
+        paths.append(str(p))
+
+    class Loader:
+        def __iter__(self):
+            for p in paths:
+                yield (Image.open(p).convert("RGB"),), (None,)     # detection/voc_utils.py:52-58
+    random.seed(3)
+    want, want_cls = cald_b200.get_uncertainty(model, Loader(), AUGS, 21)
+    tail_want = random.random()
+    random.seed(3)
+    got, got_cls = cald_b200.get_uncertainty_files(model, paths, AUGS, 21)
+    assert random.random() == tail_want
+    assert got == want and all(np.array_equal(a, b) for a, b in zip(got_cls, want_cls))
+    cald_b200.close_engines()

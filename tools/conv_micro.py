@@ -16,10 +16,8 @@ for (n, h, w, cin, cout, k) in [(8, 200, 336, 256, 256, 3), (8, 200, 336, 64, 64
     shape = "%dx%dx%d k%d %d->%d" % (n, h, w, k, cin, cout)
     run(shape + " x3 BN128 chunk8", n, h, w, cin, cout, k, prec=0, block_n=0, kc=8)
     run(shape + " x3 BN128 nochunk", n, h, w, cin, cout, k, prec=0, block_n=128, kc=0)
-    if cout >= 256:
-        run(shape + " x3 BN256 nochunk", n, h, w, cin, cout, k, prec=0, block_n=256, kc=0)
     run(shape + " x3 BN64 nochunk", n, h, w, cin, cout, k, prec=0, block_n=64, kc=0)
-    run(shape + " bf16 BN128", n, h, w, cin, cout, k, prec=1, block_n=128, kc=0)
+    run(shape + " single-pass half BN128", n, h, w, cin, cout, k, prec=1, block_n=128, kc=0)
     if cout >= 256:
-        run(shape + " bf16 BN256", n, h, w, cin, cout, k, prec=1, block_n=256, kc=0)
-    run(shape + " bf16 BN64", n, h, w, cin, cout, k, prec=1, block_n=64, kc=0)
+        run(shape + " single-pass half BN256", n, h, w, cin, cout, k, prec=1, block_n=256, kc=0)
+    run(shape + " single-pass half BN64", n, h, w, cin, cout, k, prec=1, block_n=64, kc=0)
