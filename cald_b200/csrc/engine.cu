@@ -1320,8 +1320,8 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
       pil_rotate_nearest_batched_kernel<<<dim3((rw + 127) / 128, rh, (unsigned)nr), 128, 0, st>>>(d_rot);
       KLAUNCH(e);
     }
-    pil_resample_h_batched_kernel<<<dim3((hw * 3 + 255) / 256, hh, (unsigned)nj), 256, 0, st>>>(d_hv);
-    pil_resample_v_batched_kernel<<<dim3((vw * 3 + 255) / 256, vh, (unsigned)nj), 256, 0, st>>>(d_hv + nj);
+    pil_resample_h_batched_kernel<<<dim3((hw + 127) / 128, hh, (unsigned)nj), 128, 0, st>>>(d_hv);
+    pil_resample_v_batched_kernel<<<dim3(((vw * 3 + 3) / 4 + 127) / 128, vh, (unsigned)nj), 128, 0, st>>>(d_hv + nj);
     CALD_CUDA_CHECK(cudaGetLastError());
     e->launches += 2;
     if (d_rot) ar.free(d_rot);

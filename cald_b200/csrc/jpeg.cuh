@@ -198,13 +198,25 @@ struct JpegBits {
   const uint8_t* end;
   unsigned long long acc;   // bits are consumed from the top
   int n;                    // valid bits in acc
+  // source bytes are fetched eight at a time (one aligned 64-bit load per eight bytes instead of one load per byte:
+  // the walk is a single dependent instruction chain, so every load's latency is exposed)
+  unsigned long long win;   // the aligned 8-byte window that contains *p
+  const uint8_t* win_at;    // its address (null = none loaded)
+  __device__ __forceinline__ unsigned byte_at(const uint8_t* q) {
+    const uint8_t* a = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)7);
+    if (a != win_at) {
+      win = *reinterpret_cast<const unsigned long long*>(a);   // the scan buffer is padded to 16 bytes
+      win_at = a;
+    }
+    return (unsigned)(win >> (8 * (unsigned)(q - a))) & 0xffu;
+  }
   __device__ __forceinline__ void fill() {
     while (n <= 56) {
       unsigned b = 0;
       if (p < end) {
-        b = *p;
+        b = byte_at(p);
         if (b == 0xFF) {
-          const unsigned nx = (p + 1 < end) ? p[1] : 0xD9u;
+          const unsigned nx = (p + 1 < end) ? byte_at(p + 1) : 0xD9u;
           if (nx == 0) p += 2;       // stuffed zero
           else b = 0;                // a marker: feed zeros and stay in front of it (jdhuff.c)
         } else {
@@ -236,7 +248,7 @@ struct JpegBits {
   }
   __device__ void restart() {                  // byte-align and step over the RSTn marker
     acc = 0; n = 0;
-    while (p + 1 < end && !(p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7)) ++p;
+    while (p + 1 < end && !(byte_at(p) == 0xFF && byte_at(p + 1) >= 0xD0 && byte_at(p + 1) <= 0xD7)) ++p;
     if (p + 1 < end) p += 2;
   }
 };
@@ -259,27 +271,38 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __res
       for (int i = threadIdx.x; i < (int)(sizeof(JpegHuff) / 4); i += 32) dst[i] = src[i];
     }
   }
+  // the per-component fields the walk needs, out of the 700-byte descriptor in global memory
+  __shared__ int s_h[3], s_v[3], s_bw[3], s_td[3], s_ta[3];
+  __shared__ long long s_off[3];
+  if (threadIdx.x < 3 && threadIdx.x < im.ncomp) {
+    const JpegComp& cp = im.comp[threadIdx.x];
+    s_h[threadIdx.x] = cp.h; s_v[threadIdx.x] = cp.v; s_bw[threadIdx.x] = cp.blocks_w;
+    s_td[threadIdx.x] = cp.td & 1; s_ta[threadIdx.x] = 2 + (cp.ta & 1); s_off[threadIdx.x] = cp.coef_off;
+  }
   __syncwarp();
   if (threadIdx.x != 0) return;
   JpegBits br;
   br.p = bytes + im.scan_off;
   br.end = br.p + im.scan_len;
   br.acc = 0; br.n = 0;
+  br.win = 0; br.win_at = nullptr;
   int pred[3] = {0, 0, 0};
-  int left = im.restart;
-  for (int my = 0; my < im.mcuy; ++my) {
-    for (int mx = 0; mx < im.mcux; ++mx) {
-      if (im.restart) {
-        if (left == 0) { br.restart(); pred[0] = pred[1] = pred[2] = 0; left = im.restart; }
+  const int ncomp = im.ncomp, mcux = im.mcux, mcuy = im.mcuy, restart = im.restart;
+  int left = restart;
+  for (int my = 0; my < mcuy; ++my) {
+    for (int mx = 0; mx < mcux; ++mx) {
+      if (restart) {
+        if (left == 0) { br.restart(); pred[0] = pred[1] = pred[2] = 0; left = restart; }
         --left;
       }
-      for (int c = 0; c < im.ncomp; ++c) {
-        const JpegComp& cp = im.comp[c];
-        const JpegHuff& dc = s_t[cp.td & 1];
-        const JpegHuff& ac = s_t[2 + (cp.ta & 1)];
-        for (int by = 0; by < cp.v; ++by) {
-          for (int bx = 0; bx < cp.h; ++bx) {
-            short* blk = coef + cp.coef_off + ((long long)(my * cp.v + by) * cp.blocks_w + (mx * cp.h + bx)) * 64;
+      for (int c = 0; c < ncomp; ++c) {
+        const JpegHuff& dc = s_t[s_td[c]];
+        const JpegHuff& ac = s_t[s_ta[c]];
+        const int ch = s_h[c], cv = s_v[c], bw = s_bw[c];
+        short* cbase = coef + s_off[c];
+        for (int by = 0; by < cv; ++by) {
+          for (int bx = 0; bx < ch; ++bx) {
+            short* blk = cbase + ((long long)(my * cv + by) * bw + (mx * ch + bx)) * 64;
             const int t = br.decode(dc) & 15;
             if (t) pred[c] += br.receive_extend(t);
             blk[0] = (short)pred[c];

@@ -322,25 +322,45 @@ struct PilJob {
   const int* kk;
   int ksize;
 };
+// one thread per output PIXEL: the three channels share the coefficient loads and the loop (same integer arithmetic)
 __global__ void pil_resample_h_batched_kernel(const PilJob* __restrict__ jobs) {
   const PilJob j = jobs[blockIdx.z];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (y >= j.in_h || t >= j.out_w * 3) return;
-  const int xx = t / 3, c = t % 3;
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (y >= j.in_h || xx >= j.out_w) return;
   const int xmin = j.bounds[xx * 2], n = j.bounds[xx * 2 + 1];
-  int acc = 1 << (PIL_PRECISION_BITS - 1);
-  const uint8_t* row = j.src + (long long)y * j.in_w * 3;
-  for (int x = 0; x < n; ++x) acc += (int)row[(xmin + x) * 3 + c] * j.kk[xx * j.ksize + x];
-  j.dst[((long long)y * j.out_w + xx) * 3 + c] = pil_clip8(acc);
+  int a0 = 1 << (PIL_PRECISION_BITS - 1), a1 = a0, a2 = a0;
+  const uint8_t* px = j.src + ((long long)y * j.in_w + xmin) * 3;
+  const int* k = j.kk + (long long)xx * j.ksize;
+  for (int x = 0; x < n; ++x) {
+    const int c = k[x];
+    a0 += (int)px[0] * c; a1 += (int)px[1] * c; a2 += (int)px[2] * c;
+    px += 3;
+  }
+  uint8_t* o = j.dst + ((long long)y * j.out_w + xx) * 3;
+  o[0] = pil_clip8(a0); o[1] = pil_clip8(a1); o[2] = pil_clip8(a2);
 }
+// one thread per four consecutive bytes of an output row (the coefficient of a tap is the same for the whole row)
 __global__ void pil_resample_v_batched_kernel(const PilJob* __restrict__ jobs) {
   const PilJob j = jobs[blockIdx.z];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y;
-  if (yy >= j.out_h || t >= j.in_w * 3) return;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) * 4, yy = blockIdx.y;
+  const int rowb = j.in_w * 3;
+  if (yy >= j.out_h || t >= rowb) return;
   const int ymin = j.bounds[yy * 2], n = j.bounds[yy * 2 + 1];
-  int acc = 1 << (PIL_PRECISION_BITS - 1);
-  for (int y = 0; y < n; ++y) acc += (int)j.src[(long long)(ymin + y) * j.in_w * 3 + t] * j.kk[yy * j.ksize + y];
-  j.dst[(long long)yy * j.in_w * 3 + t] = pil_clip8(acc);
+  const int m = min(4, rowb - t);
+  int acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q] = 1 << (PIL_PRECISION_BITS - 1);
+  const uint8_t* p = j.src + (long long)ymin * rowb + t;
+  const int* k = j.kk + (long long)yy * j.ksize;
+  for (int y = 0; y < n; ++y) {
+    const int c = k[y];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (q < m) acc[q] += (int)p[q] * c;
+    p += rowb;
+  }
+  uint8_t* o = j.dst + (long long)yy * rowb + t;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) if (q < m) o[q] = pil_clip8(acc[q]);
 }
 
 // PIL Image.rotate(angle, expand=True) geometry (PIL/Image.py) + Geometry.c affine_fixed coefficients
