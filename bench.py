@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="images per step per GPU (one engine chunk = 64 images)")
+    ap.add_argument("--batch", type=int, default=64, help="images per step per GPU (two engine chunks of 32 images)")
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="BASELINE.json configuration (default cfg2)")
     ap.add_argument("--model", default=None, choices=["frcnn", "retinanet"], help="shorthand: retinanet = --config cfg3")

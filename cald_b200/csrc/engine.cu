@@ -1733,14 +1733,16 @@ int cald_create(const cald_config* cfg, cald_engine** out) {
     if (cfg->max_views_per_pass > 0) {
       e->views_per_pass = cfg->max_views_per_pass;
     } else {
-      // auto: as many views as the arena holds at the detector's largest padded input, up to 64 (= 16 images with
-      // four augmentations; larger passes measured no faster).  Peak arena use per view is ~ARENA_BYTES_PER_PIXEL of
-      // the padded input (measured with cald_arena_peak: activations of the widest point of the pass + RoI features
-      // + per-view result buffers); two chunk-sized image slabs come on top.
+      // auto: as many views as the arena holds at the detector's largest padded input, up to 32.  Measured on one box
+      // (profiles/r02_summary.md): 16 / 64 / 128 views per pass give 128.8 / 129.7 / 130.1 img/s -- pass size no
+      // longer matters for the kernels -- while a chunk of 32 images lets a 64-image call overlap half of its host ->
+      // device traffic with compute.  Peak arena use per view is ~ARENA_BYTES_PER_PIXEL of the padded input (measured
+      // with cald_arena_peak: 290 B; activations of the widest point of the pass + RoI features + per-view result
+      // buffers); two chunk-sized image slabs come on top.
       const double per_view = (double)pad32(cfg->min_size) * (double)pad32(cfg->max_size) * ARENA_BYTES_PER_PIXEL +
                               (retina ? (double)e->det_cap * (cfg->num_classes + 16) * 4.0 : 8.0e6);
       const double fit = 0.85 * (double)ws / per_view;
-      e->views_per_pass = (int)std::max(4.0, std::min(64.0, std::floor(fit)));
+      e->views_per_pass = (int)std::max(4.0, std::min(32.0, std::floor(fit)));
     }
     CALD_CUDA_CHECK(cudaFuncSetAttribute(nms_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM));
     CALD_CUDA_CHECK(cudaFuncSetAttribute(det_class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -65,7 +65,7 @@ typedef struct {
   int precision;             /* CALD_PREC_* */
   int conv_impl;             /* CALD_CONV_* */
   int max_views_per_pass;    /* views batched through one forward pass (0 = auto: as many as the arena holds at the
-                                largest padded input, up to 64) */
+                                largest padded input, up to 32) */
   size_t workspace_bytes;    /* device arena (0 = auto from free memory) */
   int debug;                 /* 1: keep host copies of stage tensors for cald_debug_fetch */
 } cald_config;
