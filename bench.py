@@ -53,12 +53,12 @@ CONFIGS = {
                  workload="FRCNN R50-FPN nc=91, synthetic 1333x800 pool sharded over the GPUs, score -> all-gather -> "
                           "argsort -> cls_kldiv -> select (cald_train.py:427-448)"),
 }
-# DRAM bytes per conv launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu) averaged over the conv launches of one
-# default cfg2 step (batch 16: a 16-view reference pass + a 64-view augmented pass).  An OFFLINE ncu constant (ncu
-# cannot run inside a timed bench); source file named in the JSON.  Only reported for the workload it was captured on.
-NCU_DRAM_BYTES_PER_CONV_LAUNCH = 1556.2e6
-NCU_DRAM_SOURCE = "profiles/r01_igemm_dram_step.csv"
-NCU_DRAM_BATCH = 16
+# DRAM traffic of the conv kernels per scored image (dram__bytes_read.sum + dram__bytes_write.sum, ncu, summed over the 142
+# igemm_tc_kernel / igemm_tc2_kernel launches of one 16-image cfg2 step: 220.77 GB / 16).  An OFFLINE ncu constant (ncu
+# cannot run inside a timed bench), independent of the pass size to first order (every activation is written and read
+# once per image); `roofline.traffic` = this x images per step / conv launches per step.  Only reported for cfg2.
+NCU_DRAM_BYTES_PER_IMAGE = 13.798e9
+NCU_DRAM_SOURCE = "profiles/r02_launches_step.csv"
 BASE_IMAGES = 32
 POOL_MAX_IMAGES = 1024   # distinct images per rank (3.3 GB at 1333x800); longer runs cycle through them
 
@@ -428,9 +428,10 @@ def main():
         "roofline": None if args.quick else {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None,
                      "frac_of_x3_ceiling": 3.0 * achieved / peak_tf if peak_tf else None,
-                     "traffic": NCU_DRAM_BYTES_PER_CONV_LAUNCH if (name == "cfg2" and B == NCU_DRAM_BATCH) else None,
-                     "traffic_source": "offline ncu constant (dram__bytes_read+write per launch, mean over the conv "
-                                       "launches of one step): " + NCU_DRAM_SOURCE,
+                     "traffic": (NCU_DRAM_BYTES_PER_IMAGE * B * args.steps / conv_launches
+                                 if (name == "cfg2" and conv_launches) else None),
+                     "traffic_source": "offline ncu constant: conv-kernel DRAM bytes (read + write) per scored image "
+                                       "from " + NCU_DRAM_SOURCE + ", scaled to this run's images and launches per step",
                      "algorithmic_bytes_per_launch": conv_bytes / conv_launches if conv_launches else None,
                      "kernel": "igemm_tc_kernel + igemm_tc2_kernel (tcgen05 implicit-GEMM conv/GEMM: one-CTA and "
                                "CTA-pair cta_group::2 instantiations)",

@@ -258,29 +258,26 @@ __constant__ int c_jpeg_zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 
                                       15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
 // grid = images, block = 32.  coef must be zeroed beforehand (only non-zero coefficients are written).
+// NO shared memory, on purpose: the kernel runs on the copy stream while the persistent conv kernels occupy every SM
+// with ~226 of its 227 KB of shared memory.  A block that needs shared memory cannot join such an SM: it waits for a
+// gap between two conv launches, and the next conv launch then finds those SMs taken and loses its statically assigned
+// tiles' CTAs for the length of the walk (~50 ms) -- measured as a 15 % slowdown of scoring from files.  The decoder
+// tables (1.4 KB each) are read through L1 instead.
 __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __restrict__ imgs,
                                                           const JpegHuff* __restrict__ tables,
                                                           const uint8_t* __restrict__ bytes, short* __restrict__ coef) {
-  __shared__ JpegHuff s_t[4];   // DC0, DC1, AC0, AC1
-  const JpegImage& im = imgs[blockIdx.x];
-  for (int k = 0; k < 4; ++k) {
-    const int ti = k < 2 ? im.huff_dc[k] : im.huff_ac[k - 2];
-    if (ti >= 0) {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(&tables[ti]);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(&s_t[k]);
-      for (int i = threadIdx.x; i < (int)(sizeof(JpegHuff) / 4); i += 32) dst[i] = src[i];
-    }
-  }
-  // the per-component fields the walk needs, out of the 700-byte descriptor in global memory
-  __shared__ int s_h[3], s_v[3], s_bw[3], s_td[3], s_ta[3];
-  __shared__ long long s_off[3];
-  if (threadIdx.x < 3 && threadIdx.x < im.ncomp) {
-    const JpegComp& cp = im.comp[threadIdx.x];
-    s_h[threadIdx.x] = cp.h; s_v[threadIdx.x] = cp.v; s_bw[threadIdx.x] = cp.blocks_w;
-    s_td[threadIdx.x] = cp.td & 1; s_ta[threadIdx.x] = 2 + (cp.ta & 1); s_off[threadIdx.x] = cp.coef_off;
-  }
-  __syncwarp();
   if (threadIdx.x != 0) return;
+  const JpegImage& im = imgs[blockIdx.x];
+  const JpegHuff* t_dc[3];
+  const JpegHuff* t_ac[3];
+  int s_h[3], s_v[3], s_bw[3];
+  long long s_off[3];
+  for (int c = 0; c < 3; ++c) {
+    const JpegComp& cp = im.comp[c < im.ncomp ? c : 0];
+    s_h[c] = cp.h; s_v[c] = cp.v; s_bw[c] = cp.blocks_w; s_off[c] = cp.coef_off;
+    t_dc[c] = tables + max(0, im.huff_dc[cp.td & 1]);
+    t_ac[c] = tables + max(0, im.huff_ac[cp.ta & 1]);
+  }
   JpegBits br;
   br.p = bytes + im.scan_off;
   br.end = br.p + im.scan_len;
@@ -296,8 +293,8 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __res
         --left;
       }
       for (int c = 0; c < ncomp; ++c) {
-        const JpegHuff& dc = s_t[s_td[c]];
-        const JpegHuff& ac = s_t[s_ta[c]];
+        const JpegHuff& dc = *t_dc[c];
+        const JpegHuff& ac = *t_ac[c];
         const int ch = s_h[c], cv = s_v[c], bw = s_bw[c];
         short* cbase = coef + s_off[c];
         for (int by = 0; by < cv; ++by) {
