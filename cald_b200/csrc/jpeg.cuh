@@ -257,17 +257,33 @@ __constant__ int c_jpeg_zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 
                                       41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22,
                                       15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
-// grid = images, block = 32.  coef must be zeroed beforehand (only non-zero coefficients are written).
-// NO shared memory, on purpose: the kernel runs on the copy stream while the persistent conv kernels occupy every SM
-// with ~226 of its 227 KB of shared memory.  A block that needs shared memory cannot join such an SM: it waits for a
-// gap between two conv launches, and the next conv launch then finds those SMs taken and loses its statically assigned
-// tiles' CTAs for the length of the walk (~50 ms) -- measured as a 15 % slowdown of scoring from files.  The decoder
-// tables (1.4 KB each) are read through L1 instead.
+// grid = JPEG_WALK_BLOCKS one-warp blocks that hand the chunk's images out among themselves; coef must be zeroed
+// beforehand (only non-zero coefficients are written); sched = {next image, per-SM claim flags}, zeroed per launch.
+//
+// The kernel runs on the copy stream WHILE the persistent conv kernels hold every SM, so it has to fit beside them and
+// must never keep a conv CTA from launching:
+//  * no shared memory: the one-CTA conv kernel leaves exactly the 1 KB a block reserves (measured with
+//    tools/overlap_probe.py: a block with 0 B co-resides, one with 4 KB delays the conv train by the block's lifetime);
+//    the decoder tables (1.4 KB each) are read through L1 instead;
+//  * at most ONE walking block per SM: beside a CTA-pair conv kernel (202 KB) the block scheduler can stack several
+//    blocks on one SM, and the next one-CTA conv launch then finds no room there for ~50 ms -- with statically assigned
+//    tiles that stalls the whole launch (measured: scoring from files 15 % slower than from pixels).  Every block
+//    therefore claims its SM (%smid) first; a block that finds the SM taken exits at once, the owners take images
+//    from a shared counter until none is left.
+constexpr int JPEG_WALK_BLOCKS = 2 * 148;
+constexpr int JPEG_SCHED_INTS = 1 + 256;
 __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __restrict__ imgs,
                                                           const JpegHuff* __restrict__ tables,
-                                                          const uint8_t* __restrict__ bytes, short* __restrict__ coef) {
+                                                          const uint8_t* __restrict__ bytes, short* __restrict__ coef,
+                                                          int n_images, int* __restrict__ sched) {
   if (threadIdx.x != 0) return;
-  const JpegImage& im = imgs[blockIdx.x];
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (atomicCAS(&sched[1 + (smid & 255u)], 0, 1) != 0) return;
+  for (;;) {
+  const int img_i = atomicAdd(&sched[0], 1);
+  if (img_i >= n_images) return;
+  const JpegImage& im = imgs[img_i];
   const JpegHuff* t_dc[3];
   const JpegHuff* t_ac[3];
   int s_h[3], s_v[3], s_bw[3];
@@ -321,6 +337,7 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __res
       }
     }
   }
+  }  // next image
 }
 
 // ---------------------------------------------------------------- device: inverse DCT (jidctint.c, JDCT_ISLOW)

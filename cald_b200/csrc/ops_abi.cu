@@ -198,3 +198,73 @@ extern "C" int cald_op_conv2d_dual(const float* x, int n, int h, int w, int cin,
   ar.destroy();
   OPS_CATCH
 }
+
+
+// ---------------------------------------------------------------- measurement probe (tools/overlap_probe.py)
+// Can a small kernel on a second stream run WHILE the persistent conv kernels occupy every SM (one CTA per SM with
+// ~226 KB of shared memory)?  The pool-ingest decode relies on it.  A 32-block, one-warp kernel that spins for spin_ms
+// is timed alone and launched in the middle of a train of conv launches; the conv train is timed with and without it.
+__global__ void spin_kernel(long long ns, int smem_probe) {
+  extern __shared__ unsigned char probe_smem[];
+  if (smem_probe && threadIdx.x == 0) probe_smem[0] = 1;
+  if (threadIdx.x != 0) return;
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while ((long long)(t - t0) < ns);
+}
+
+extern "C" int cald_op_overlap_probe(int n, int h, int w, int cin, int cout, int k, int iters, int spin_ms,
+                                     int spin_smem_bytes, double* out /*[4]*/) {
+  OPS_TRY
+  cudaStream_t st, st2;
+  CALD_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CALD_CUDA_CHECK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+  Arena ar;
+  size_t in_e = (size_t)n * h * w * cin, out_e = (size_t)n * h * w * ((cout + 7) / 8 * 8);
+  ar.init((in_e + out_e) * 8 + ((size_t)64 << 20));
+  ConvEngine eng;
+  int dev;
+  CALD_CUDA_CHECK(cudaGetDevice(&dev));
+  CALD_CUDA_CHECK(cudaDeviceGetAttribute(&eng.num_sms, cudaDevAttrMultiProcessorCount, dev));
+  std::vector<float> wh((size_t)cout * cin * k * k, 0.01f);
+  ConvW cw = upload_conv_weight(wh.data(), nullptr, cout, cin, k, true, nullptr, RzPlan());
+  Act a = alloc_act(ar, n, h, w, cin, true), y = alloc_act(ar, n, h, w, cw.cout_pad, true);
+  CALD_CUDA_CHECK(cudaMemsetAsync(a.hi, 0, a.bytes(), st));
+  ConvOpts o;
+  o.relu = true;
+  cudaEvent_t e0, e1, s0, s1;
+  for (cudaEvent_t* ev : {&e0, &e1, &s0, &s1}) CALD_CUDA_CHECK(cudaEventCreate(ev));
+  auto train = [&](bool with_spin, double& conv_ms, double& spin_ms_out) {
+    CALD_CUDA_CHECK(cudaDeviceSynchronize());
+    CALD_CUDA_CHECK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) {
+      eng.run(a, cw, y, o, st);
+      if (with_spin && i == 1) {
+        CALD_CUDA_CHECK(cudaEventRecord(s0, st2));
+        spin_kernel<<<32, 32, spin_smem_bytes, st2>>>((long long)spin_ms * 1000000ll, spin_smem_bytes > 0);
+        CALD_CUDA_CHECK(cudaEventRecord(s1, st2));
+      }
+    }
+    CALD_CUDA_CHECK(cudaEventRecord(e1, st));
+    CALD_CUDA_CHECK(cudaDeviceSynchronize());
+    float ms = 0;
+    CALD_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    conv_ms = ms;
+    if (with_spin) { CALD_CUDA_CHECK(cudaEventElapsedTime(&ms, s0, s1)); spin_ms_out = ms; }
+  };
+  double d;
+  train(false, out[0], d);          // warm-up
+  train(false, out[0], d);
+  CALD_CUDA_CHECK(cudaEventRecord(s0, st2));
+  spin_kernel<<<32, 32, spin_smem_bytes, st2>>>((long long)spin_ms * 1000000ll, spin_smem_bytes > 0);
+  CALD_CUDA_CHECK(cudaEventRecord(s1, st2));
+  CALD_CUDA_CHECK(cudaDeviceSynchronize());
+  float ms = 0;
+  CALD_CUDA_CHECK(cudaEventElapsedTime(&ms, s0, s1));
+  out[2] = ms;
+  train(true, out[1], out[3]);
+  free_conv_weight(cw);
+  ar.destroy();
+  cudaStreamDestroy(st); cudaStreamDestroy(st2);
+  OPS_CATCH
+}

@@ -60,6 +60,13 @@ int cald_op_aug_image(int kind, const uint8_t* img, int h, int w, uint8_t* out, 
  * with the same factor, bit-exact u8 arithmetic of libImaging/Blend.c / Convert.c.  img, out: u8 [h][w][3]. */
 int cald_op_color_adjust(const uint8_t* img, int h, int w, double factor, uint8_t* out);
 
+/* Measurement probe (tools/overlap_probe.py): times a train of `iters` conv launches alone (out[0], ms) and with a
+ * 32-block one-warp kernel that spins for spin_ms (and declares spin_smem_bytes of dynamic shared memory) launched on a
+ * second stream after the second conv (out[1]); out[2] / out[3] = the spin kernel's own start-to-end time alone / inside
+ * the train.  Answers whether small kernels can co-reside with the persistent conv CTAs (one per SM, ~226 KB smem). */
+int cald_op_overlap_probe(int n, int h, int w, int cin, int cout, int k, int iters, int spin_ms, int spin_smem_bytes,
+                          double* out);
+
 #ifdef __cplusplus
 }
 #endif
