@@ -1356,10 +1356,12 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
       lsc_kernel<<<B, 32 * CONS_WARPS, 0, st>>>(ref.det, aug.det, dc, A, top, d_out);
       CALD_CUDA_CHECK(cudaGetLastError());
       e->launches += 3;
+      // (a device -> PAGEABLE-host cudaMemcpyAsync returns only when the copy is done, i.e. after everything queued
+      // before it: the next chunk's upload has to be started BEFORE the result copies, not after them)
+      if (before_wait) before_wait();
       CALD_CUDA_CHECK(cudaMemcpyAsync(out_cons, d_out, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
       std::vector<int> h_rc(B);
       CALD_CUDA_CHECK(cudaMemcpyAsync(h_rc.data(), ref.det.count, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-      if (before_wait) before_wait();
       CALD_CUDA_CHECK(cudaStreamSynchronize(st));
       e->last_ref_counts.insert(e->last_ref_counts.end(), h_rc.begin(), h_rc.end());
       check_overflow(e);
@@ -1382,10 +1384,14 @@ void score_chunk(cald_engine* e, int B, const uint8_t* const* d_images, const in
   if (scorer == 0) {
     std::vector<float> h_cons((size_t)B * std::max(A, 1)), h_cls((size_t)B * (1 + A) * ncls1);
     std::vector<int> h_ndet(B);
+    // Everything of this chunk is enqueued: start the next chunk's upload / decode NOW.  The result copies below go to
+    // pageable host memory, and a device -> pageable cudaMemcpyAsync only returns once the copy has completed -- i.e.
+    // after the whole chunk has run.  (Round 2 first had the prefetch behind these copies: the timeline showed chunk
+    // c+1's decode starting exactly when chunk c's compute ended, nothing overlapped.)
+    if (before_wait) before_wait();
     if (A > 0) CALD_CUDA_CHECK(cudaMemcpyAsync(h_cons.data(), d_cons, (size_t)B * A * 4, cudaMemcpyDeviceToHost, st));
     CALD_CUDA_CHECK(cudaMemcpyAsync(h_cls.data(), d_cls, h_cls.size() * 4, cudaMemcpyDeviceToHost, st));
     CALD_CUDA_CHECK(cudaMemcpyAsync(h_ndet.data(), rs.n_det, B * 4, cudaMemcpyDeviceToHost, st));
-    if (before_wait) before_wait();
     CALD_CUDA_CHECK(cudaStreamSynchronize(st));
     check_overflow(e);
     e->trace("results_on_host");
@@ -1485,17 +1491,23 @@ struct UploadPipe {
   // CALD_TRACE_JPEG=1: device time of every chunk's decode (copy stream), printed when the pipe is destroyed
   bool trace_jpeg = getenv("CALD_TRACE_JPEG") != nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_ev;
+  std::vector<cudaEvent_t> trace_chunk;   // compute stream: the point where chunk c may start (after its wait)
+  cudaEvent_t trace_base = nullptr;
   ~UploadPipe() {
     if (!trace_jpeg || trace_ev.empty()) return;
     cudaStreamSynchronize(e->copy_st);
-    fprintf(stderr, "[jpeg decode per chunk, ms]");
-    for (auto& pr : trace_ev) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, pr.first, pr.second);
-      fprintf(stderr, " %.1f", ms);
-      cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    cudaStreamSynchronize(e->st);
+    fprintf(stderr, "[jpeg timeline, ms since call start] decode(c) = start..end on the copy stream; compute(c) starts at\n");
+    for (size_t c = 0; c < trace_ev.size(); ++c) {
+      float a = 0, b = 0, g = 0;
+      cudaEventElapsedTime(&a, trace_base, trace_ev[c].first);
+      cudaEventElapsedTime(&b, trace_base, trace_ev[c].second);
+      if (c < trace_chunk.size()) cudaEventElapsedTime(&g, trace_base, trace_chunk[c]);
+      fprintf(stderr, "  chunk %zu: decode %.1f..%.1f  compute starts %.1f\n", c, a, b, g);
+      cudaEventDestroy(trace_ev[c].first); cudaEventDestroy(trace_ev[c].second);
     }
-    fprintf(stderr, "\n");
+    for (cudaEvent_t ev : trace_chunk) cudaEventDestroy(ev);
+    cudaEventDestroy(trace_base);
   }
 
   static size_t padded(int h, int w) { return ((size_t)h * w * 3 + 255) & ~(size_t)255; }
@@ -1507,6 +1519,7 @@ struct UploadPipe {
              const size_t* file_sizes = nullptr)
       : e(eng), n_images(n), per_chunk(std::max(1, chunk)), imgs(images), hs(heights), ws(widths) {
     jpeg = file_sizes != nullptr;
+    if (jpeg && trace_jpeg) { cudaEventCreate(&trace_base); cudaEventRecord(trace_base, e->st); }
     if (jpeg) {
       meta.resize(n); tabs.resize(n); scan_begin.resize(n); scan_end.resize(n); jh.resize(n); jw.resize(n);
       for (int i = 0; i < n; ++i) {
@@ -1652,6 +1665,7 @@ struct UploadPipe {
     start(c);
     const int k = c & 1, i0 = c * per_chunk, i1 = std::min(n_images, i0 + per_chunk);
     CALD_CUDA_CHECK(cudaStreamWaitEvent(e->st, e->upload_done[k], 0));
+    if (jpeg && trace_jpeg) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, e->st); trace_chunk.push_back(ev); }
     DeviceImages d;
     size_t off = 0;
     for (int i = i0; i < i1; ++i) { d.ptr.push_back(slab[k] + off); off += padded(hs[i], ws[i]); }
@@ -2050,8 +2064,8 @@ int cald_score_ltc(cald_engine* e, int n_images, const uint8_t* const* images, c
     CALD_CUDA_CHECK(cudaGetLastError());
     KLAUNCH(e);
     std::vector<float> h(B);
+    pipe.start(chunk + 1);   // before the (host-blocking) copy into pageable memory
     CALD_CUDA_CHECK(cudaMemcpyAsync(h.data(), d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, e->st));
-    pipe.start(chunk + 1);
     CALD_CUDA_CHECK(cudaStreamSynchronize(e->st));
     for (int b = 0; b < B; ++b) out_uncertainty[pos + b] = (double)h[b];
     e->arena.free(d_out);
@@ -2081,6 +2095,7 @@ int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, cons
     std::vector<int> h_count(B), h_labels((size_t)B * dc), h_pidx((size_t)B * dc);
     std::vector<float> h_scores_all;
     cudaStream_t st = e->st;
+    pipe.start(chunk + 1);   // before the (host-blocking) copies into pageable memory
     CALD_CUDA_CHECK(cudaMemcpyAsync(h_count.data(), vs.det.count, B * 4, cudaMemcpyDeviceToHost, st));
     CALD_CUDA_CHECK(cudaMemcpyAsync(h_labels.data(), vs.det.labels, (size_t)B * dc * 4, cudaMemcpyDeviceToHost, st));
     CALD_CUDA_CHECK(cudaMemcpyAsync(h_pidx.data(), vs.det.prop_idx, (size_t)B * dc * 4, cudaMemcpyDeviceToHost, st));
@@ -2092,7 +2107,6 @@ int cald_detect(cald_engine* e, int n_images, const uint8_t* const* images, cons
       h_scores_all.resize((size_t)B * e->cap * C);
       CALD_CUDA_CHECK(cudaMemcpyAsync(h_scores_all.data(), vs.scores, h_scores_all.size() * 4, cudaMemcpyDeviceToHost, st));
     }
-    pipe.start(chunk + 1);
     CALD_CUDA_CHECK(cudaStreamSynchronize(st));
     check_overflow(e);
     for (int b = 0; b < B; ++b) {
