@@ -183,7 +183,8 @@ def get_uncertainty_files(task_model, paths, augs, num_cls, device=0, **engine_k
     n_cut = sum(1 for k, _ in views if k == _eng.AUG_CUTOUT)
     n_swap = sum(1 for k, _ in views if k == _eng.AUG_COLOR_SWAP)
     # files are small (~150 KB): hand the engine eight chunks per call, so that only one chunk in eight has its
-    # decode latency (a serial entropy walk per image, ~50 ms) exposed instead of hidden behind the previous chunk
+    # decode latency (the entropy walk of its images + the device decode) exposed instead of hidden behind the
+    # previous chunk's forward passes
     group = 1 if (n_swap and n_cut) else 8 * eng.images_per_chunk(max(1, len(views)))
 
     def read(p):

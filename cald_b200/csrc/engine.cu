@@ -1475,6 +1475,13 @@ struct UploadPipe {
   // ---- JPEG mode (pool ingest, jpeg.cuh): the compressed scans travel instead of pixels and the chunk is decoded
   //      into its slab by three kernels on the copy stream, concurrently with the previous chunk's forward passes
   bool jpeg = false;
+  // Where the entropy-coded segment is walked.  Host (default): a few host threads walk the chunk's scans into the
+  // page-locked staging buffer while the previous chunk computes (the walk is a serial bit parser, ~1 ms per image on a
+  // CPU core against ~50 ms on one GPU lane) and the coefficients travel; the device does dequantisation, inverse DCT,
+  // upsampling and colour conversion with short-lived blocks.  Device (CALD_JPEG_WALK=device): the compressed scan
+  // travels (20x fewer bytes) and one GPU lane per image walks it -- but those blocks live ~100 ms beside the
+  // persistent conv CTAs and cost the conv kernels ~15 % while they run (measured, profiles/r02_summary.md).
+  bool host_walk = true;
   std::vector<JpegImage> meta;                 // per file, offsets relative to its chunk
   std::vector<std::vector<JpegHuff>> tabs;     // per file
   std::vector<size_t> scan_begin, scan_end;
@@ -1519,6 +1526,7 @@ struct UploadPipe {
              const size_t* file_sizes = nullptr)
       : e(eng), n_images(n), per_chunk(std::max(1, chunk)), imgs(images), hs(heights), ws(widths) {
     jpeg = file_sizes != nullptr;
+    if (const char* m = getenv("CALD_JPEG_WALK")) host_walk = strcmp(m, "device") != 0;
     if (jpeg && trace_jpeg) { cudaEventCreate(&trace_base); cudaEventRecord(trace_base, e->st); }
     if (jpeg) {
       meta.resize(n); tabs.resize(n); scan_begin.resize(n); scan_end.resize(n); jh.resize(n); jw.resize(n);
@@ -1590,14 +1598,14 @@ struct UploadPipe {
     const int k = c & 1, i0 = c * per_chunk, i1 = std::min(n_images, i0 + per_chunk);
     cudaStream_t cs = e->copy_st;
     if (jpeg) {
-      uint8_t* stage = staging(k, cap_bytes + 16);
+      uint8_t* stage = staging(k, host_walk ? cap_coef * 2 + 16 : cap_bytes + 16);
       h_meta[k].clear(); h_tabs[k].clear();
       size_t ob = 0, oc = 0, op = 0, oo = 0;
       int max_w = 0, max_h = 0, max_blocks = 0;
       for (int i = i0; i < i1; ++i) {
         JpegImage im = meta[i];
         const size_t len = scan_end[i] - scan_begin[i];
-        memcpy(stage + ob, imgs[i] + scan_begin[i], len);
+        if (!host_walk) memcpy(stage + ob, imgs[i] + scan_begin[i], len);
         im.scan_off = (long long)ob; im.scan_len = (long long)len;
         ob += (len + 15) & ~(size_t)15;
         for (int q = 0; q < im.ncomp; ++q) {
@@ -1618,21 +1626,45 @@ struct UploadPipe {
         h_meta[k].push_back(im);
       }
       const int nb = i1 - i0;
-      CALD_CUDA_CHECK(cudaMemcpyAsync(d_bytes[k], stage, ob, cudaMemcpyHostToDevice, cs));
-      CALD_CUDA_CHECK(cudaEventRecord(e->pinned_free[k], cs));
-      CALD_CUDA_CHECK(cudaMemcpyAsync(d_meta[k], h_meta[k].data(), (size_t)nb * sizeof(JpegImage), cudaMemcpyHostToDevice, cs));
-      if (!h_tabs[k].empty())
-        CALD_CUDA_CHECK(cudaMemcpyAsync(d_tabs[k], h_tabs[k].data(), h_tabs[k].size() * sizeof(JpegHuff), cudaMemcpyHostToDevice, cs));
       cudaEvent_t ta = nullptr, tb = nullptr;
       if (trace_jpeg) { cudaEventCreate(&ta); cudaEventCreate(&tb); cudaEventRecord(ta, cs); }
-      CALD_CUDA_CHECK(cudaMemsetAsync(d_coef[k], 0, oc * 2, cs));
-      CALD_CUDA_CHECK(cudaMemsetAsync(d_sched[k], 0, JPEG_SCHED_INTS * 4, cs));
-      jpeg_huffman_kernel<<<JPEG_WALK_BLOCKS, 32, 0, cs>>>(d_meta[k], d_tabs[k], d_bytes[k], d_coef[k], nb, d_sched[k]);
+      CALD_CUDA_CHECK(cudaMemcpyAsync(d_meta[k], h_meta[k].data(), (size_t)nb * sizeof(JpegImage), cudaMemcpyHostToDevice, cs));
+      if (host_walk) {
+        // walk the scans on a few host threads straight into the page-locked staging buffer (zeroed first: only the
+        // non-zero coefficients are written), then one DMA of the chunk's coefficients
+        short* hc = reinterpret_cast<short*>(stage);
+        const int nthr = std::max(1, std::min(4, nb));
+        auto work = [&](int t) {
+          for (int j = t; j < nb; j += nthr) {
+            const JpegImage& im = h_meta[k][j];
+            size_t lo = (size_t)im.comp[0].coef_off, hi = lo;
+            for (int q = 0; q < im.ncomp; ++q)
+              hi = std::max(hi, (size_t)im.comp[q].coef_off + (size_t)im.comp[q].blocks_w * im.comp[q].blocks_h * 64);
+            memset(hc + lo, 0, (hi - lo) * 2);
+            jpeg_walk(im, h_tabs[k].data(), imgs[i0 + j] + scan_begin[i0 + j], hc);
+          }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthr; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (std::thread& th : pool) th.join();
+        CALD_CUDA_CHECK(cudaMemcpyAsync(d_coef[k], stage, oc * 2, cudaMemcpyHostToDevice, cs));
+        CALD_CUDA_CHECK(cudaEventRecord(e->pinned_free[k], cs));
+      } else {
+        CALD_CUDA_CHECK(cudaMemcpyAsync(d_bytes[k], stage, ob, cudaMemcpyHostToDevice, cs));
+        CALD_CUDA_CHECK(cudaEventRecord(e->pinned_free[k], cs));
+        if (!h_tabs[k].empty())
+          CALD_CUDA_CHECK(cudaMemcpyAsync(d_tabs[k], h_tabs[k].data(), h_tabs[k].size() * sizeof(JpegHuff), cudaMemcpyHostToDevice, cs));
+        CALD_CUDA_CHECK(cudaMemsetAsync(d_coef[k], 0, oc * 2, cs));
+        CALD_CUDA_CHECK(cudaMemsetAsync(d_sched[k], 0, JPEG_SCHED_INTS * 4, cs));
+        jpeg_huffman_kernel<<<JPEG_WALK_BLOCKS, 32, 0, cs>>>(d_meta[k], d_tabs[k], d_bytes[k], d_coef[k], nb, d_sched[k]);
+        e->launches += 1;
+      }
       jpeg_idct_kernel<<<dim3((max_blocks + 127) / 128, nb * 3), 128, 0, cs>>>(d_meta[k], d_coef[k], d_planes[k]);
       jpeg_rgb_kernel<<<dim3((max_w + 127) / 128, max_h, nb), 128, 0, cs>>>(d_meta[k], d_planes[k], slab[k]);
       CALD_CUDA_CHECK(cudaGetLastError());
       if (trace_jpeg) { cudaEventRecord(tb, cs); trace_ev.push_back({ta, tb}); }
-      e->launches += 3;
+      e->launches += 2;
     } else if (all_pinned) {
       size_t off = 0;
       for (int i = i0; i < i1; ++i) {

@@ -202,15 +202,19 @@ struct JpegBits {
   // the walk is a single dependent instruction chain, so every load's latency is exposed)
   unsigned long long win;   // the aligned 8-byte window that contains *p
   const uint8_t* win_at;    // its address (null = none loaded)
-  __device__ __forceinline__ unsigned byte_at(const uint8_t* q) {
+  __host__ __device__ __forceinline__ unsigned byte_at(const uint8_t* q) {
+#ifdef __CUDA_ARCH__
     const uint8_t* a = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)7);
     if (a != win_at) {
-      win = *reinterpret_cast<const unsigned long long*>(a);   // the scan buffer is padded to 16 bytes
+      win = *reinterpret_cast<const unsigned long long*>(a);   // the device scan buffer is padded to 16 bytes
       win_at = a;
     }
     return (unsigned)(win >> (8 * (unsigned)(q - a))) & 0xffu;
+#else
+    return *q;                                                   // host: the caller's file buffer, no padding
+#endif
   }
-  __device__ __forceinline__ void fill() {
+  __host__ __device__ __forceinline__ void fill() {
     while (n <= 56) {
       unsigned b = 0;
       if (p < end) {
@@ -227,15 +231,15 @@ struct JpegBits {
       n += 8;
     }
   }
-  __device__ __forceinline__ unsigned peek(int k) { return (unsigned)(acc >> (64 - k)); }
-  __device__ __forceinline__ void skip(int k) { acc <<= k; n -= k; }
-  __device__ __forceinline__ int receive_extend(int s) {
+  __host__ __device__ __forceinline__ unsigned peek(int k) { return (unsigned)(acc >> (64 - k)); }
+  __host__ __device__ __forceinline__ void skip(int k) { acc <<= k; n -= k; }
+  __host__ __device__ __forceinline__ int receive_extend(int s) {
     if (n < s) fill();
     const int v = (int)peek(s);
     skip(s);
     return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
   }
-  __device__ __forceinline__ int decode(const JpegHuff& t) {
+  __host__ __device__ __forceinline__ int decode(const JpegHuff& t) {
     if (n < 16) fill();
     const unsigned l9 = t.look[peek(JPEG_LOOK_BITS)];
     if (l9) { skip((int)(l9 >> 8)); return (int)(l9 & 0xff); }
@@ -246,7 +250,7 @@ struct JpegBits {
     skip(l);
     return t.huffval[(code + t.valoff[l]) & 0xff];
   }
-  __device__ void restart() {                  // byte-align and step over the RSTn marker
+  __host__ __device__ void restart() {                  // byte-align and step over the RSTn marker
     acc = 0; n = 0;
     while (p + 1 < end && !(byte_at(p) == 0xFF && byte_at(p + 1) >= 0xD0 && byte_at(p + 1) <= 0xD7)) ++p;
     if (p + 1 < end) p += 2;
@@ -257,33 +261,20 @@ __constant__ int c_jpeg_zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 
                                       41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22,
                                       15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
-// grid = JPEG_WALK_BLOCKS one-warp blocks that hand the chunk's images out among themselves; coef must be zeroed
-// beforehand (only non-zero coefficients are written); sched = {next image, per-SM claim flags}, zeroed per launch.
-//
-// The kernel runs on the copy stream WHILE the persistent conv kernels hold every SM, so it has to fit beside them and
-// must never keep a conv CTA from launching:
-//  * no shared memory: the one-CTA conv kernel leaves exactly the 1 KB a block reserves (measured with
-//    tools/overlap_probe.py: a block with 0 B co-resides, one with 4 KB delays the conv train by the block's lifetime);
-//    the decoder tables (1.4 KB each) are read through L1 instead;
-//  * at most ONE walking block per SM: beside a CTA-pair conv kernel (202 KB) the block scheduler can stack several
-//    blocks on one SM, and the next one-CTA conv launch then finds no room there for ~50 ms -- with statically assigned
-//    tiles that stalls the whole launch (measured: scoring from files 15 % slower than from pixels).  Every block
-//    therefore claims its SM (%smid) first; a block that finds the SM taken exits at once, the owners take images
-//    from a shared counter until none is left.
-constexpr int JPEG_WALK_BLOCKS = 2 * 148;
-constexpr int JPEG_SCHED_INTS = 1 + 256;
-__global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __restrict__ imgs,
-                                                          const JpegHuff* __restrict__ tables,
-                                                          const uint8_t* __restrict__ bytes, short* __restrict__ coef,
-                                                          int n_images, int* __restrict__ sched) {
-  if (threadIdx.x != 0) return;
-  unsigned smid;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  if (atomicCAS(&sched[1 + (smid & 255u)], 0, 1) != 0) return;
-  for (;;) {
-  const int img_i = atomicAdd(&sched[0], 1);
-  if (img_i >= n_images) return;
-  const JpegImage& im = imgs[img_i];
+__host__ __device__ inline int jpeg_max0(int v) { return v < 0 ? 0 : v; }
+
+// The entropy-coded segment of one image -> its non-zero coefficients (natural order), jdhuff.c.  Shared by the device
+// kernel and the host path (jpeg_walk_host below).
+__host__ __device__ inline void jpeg_walk(const JpegImage& im, const JpegHuff* tables, const uint8_t* scan,
+                                          short* coef) {
+#ifdef __CUDA_ARCH__
+  const int* zigzag = c_jpeg_zigzag;
+#else
+  static const int zz_host[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48,
+                                  41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22,
+                                  15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+  const int* zigzag = zz_host;
+#endif
   const JpegHuff* t_dc[3];
   const JpegHuff* t_ac[3];
   int s_h[3], s_v[3], s_bw[3];
@@ -291,11 +282,11 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __res
   for (int c = 0; c < 3; ++c) {
     const JpegComp& cp = im.comp[c < im.ncomp ? c : 0];
     s_h[c] = cp.h; s_v[c] = cp.v; s_bw[c] = cp.blocks_w; s_off[c] = cp.coef_off;
-    t_dc[c] = tables + max(0, im.huff_dc[cp.td & 1]);
-    t_ac[c] = tables + max(0, im.huff_ac[cp.ta & 1]);
+    t_dc[c] = tables + jpeg_max0(im.huff_dc[cp.td & 1]);
+    t_ac[c] = tables + jpeg_max0(im.huff_ac[cp.ta & 1]);
   }
   JpegBits br;
-  br.p = bytes + im.scan_off;
+  br.p = scan;
   br.end = br.p + im.scan_len;
   br.acc = 0; br.n = 0;
   br.win = 0; br.win_at = nullptr;
@@ -329,7 +320,7 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __res
               }
               k += r;
               const int v = br.receive_extend(s);
-              if (k < 64) blk[c_jpeg_zigzag[k]] = (short)v;
+              if (k < 64) blk[zigzag[k]] = (short)v;
               ++k;
             }
           }
@@ -337,6 +328,35 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __res
       }
     }
   }
+}
+
+// grid = JPEG_WALK_BLOCKS one-warp blocks that hand the chunk's images out among themselves; coef must be zeroed
+// beforehand (only non-zero coefficients are written); sched = {next image, per-SM claim flags}, zeroed per launch.
+//
+// The kernel runs on the copy stream WHILE the persistent conv kernels hold every SM, so it has to fit beside them and
+// must never keep a conv CTA from launching:
+//  * no shared memory: the one-CTA conv kernel leaves exactly the 1 KB a block reserves (measured with
+//    tools/overlap_probe.py: a block with 0 B co-resides, one with 4 KB delays the conv train by the block's lifetime);
+//    the decoder tables (1.4 KB each) are read through L1 instead;
+//  * at most ONE walking block per SM: beside a CTA-pair conv kernel (202 KB) the block scheduler can stack several
+//    blocks on one SM, and the next one-CTA conv launch then finds no room there for ~50 ms -- with statically assigned
+//    tiles that stalls the whole launch (measured: scoring from files 15 % slower than from pixels).  Every block
+//    therefore claims its SM (%smid) first; a block that finds the SM taken exits at once, the owners take images
+//    from a shared counter until none is left.
+constexpr int JPEG_WALK_BLOCKS = 2 * 148;
+constexpr int JPEG_SCHED_INTS = 1 + 256;
+__global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __restrict__ imgs,
+                                                          const JpegHuff* __restrict__ tables,
+                                                          const uint8_t* __restrict__ bytes, short* __restrict__ coef,
+                                                          int n_images, int* __restrict__ sched) {
+  if (threadIdx.x != 0) return;
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (atomicCAS(&sched[1 + (smid & 255u)], 0, 1) != 0) return;
+  for (;;) {
+  const int img_i = atomicAdd(&sched[0], 1);
+  if (img_i >= n_images) return;
+  jpeg_walk(imgs[img_i], tables, bytes + imgs[img_i].scan_off, coef);
   }  // next image
 }
 

@@ -103,9 +103,11 @@ int cald_score(cald_engine* e, int n_images, const uint8_t* const* images, const
 
 /* Pool ingest: the reference reads its pools with PIL on DataLoader workers --
  * Image.open(path).convert('RGB'), detection/voc_utils.py:52-58, detection/coco_utils.py:209-220.  These entry points
- * take the FILES instead: the host walks the marker segments, the compressed scan travels to the device and is decoded
- * there (Huffman, JDCT_ISLOW inverse DCT, fancy chroma upsampling, YCbCr -> RGB: bit for bit what Pillow's libjpeg
- * produces), overlapped with the previous chunk's forward passes.  Supported: 8-bit sequential Huffman JPEG (SOF0 /
+ * take the FILES instead: the host walks the marker segments and (on a few threads, while the previous chunk's forward
+ * passes run) the serial entropy-coded segment; the coefficients travel to the device, which does everything parallel
+ * (dequantisation, JDCT_ISLOW inverse DCT, fancy chroma upsampling, YCbCr -> RGB: bit for bit what Pillow's libjpeg
+ * produces).  CALD_JPEG_WALK=device moves the entropy walk to the device too (the compressed scan travels; slower,
+ * DESIGN.md section 5).  Supported: 8-bit sequential Huffman JPEG (SOF0 /
  * SOF1), grayscale or YCbCr 4:4:4 / 4:2:2 / 4:2:0, restart intervals; anything else fails the call with a message.
  *
  * cald_jpeg_info   : frame size of one file (host only, needs no engine).

@@ -26,8 +26,12 @@ def eng():
     return e
 
 
-def test_device_decode_is_pillow_bit_for_bit(eng):
+@pytest.mark.parametrize("walk", ["host", "device"])
+def test_device_decode_is_pillow_bit_for_bit(eng, walk, monkeypatch):
+    """Both placements of the entropy walk (engine.cu:UploadPipe.host_walk): host threads walking the scans into the
+    page-locked staging buffer (default) and the one-lane-per-image device kernel (CALD_JPEG_WALK=device)."""
     from cald_b200 import synth
+    monkeypatch.setenv("CALD_JPEG_WALK", walk)
     rs = np.random.RandomState(0)
     files = []
     for k, (h, w, kw) in enumerate([
@@ -50,8 +54,10 @@ def test_device_decode_is_pillow_bit_for_bit(eng):
         assert np.array_equal(g, want), (k, np.abs(g.astype(int) - want.astype(int)).max())
 
 
-def test_scoring_files_equals_scoring_their_pixels(eng):
+@pytest.mark.parametrize("walk", ["host", "device"])
+def test_scoring_files_equals_scoring_their_pixels(eng, walk, monkeypatch):
     from cald_b200 import api, synth
+    monkeypatch.setenv("CALD_JPEG_WALK", walk)
     from cald_b200.engine import expand_augs
     imgs = [synth.synth_image(i, 200, 300) for i in range(5)] + [synth.synth_image(9, 300, 200)]
     files = [jpeg_bytes(im, quality=90, subsampling=2) for im in imgs]

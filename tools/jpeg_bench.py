@@ -45,9 +45,13 @@ eng.score(pix[:64], views, 1.3, u[:200 * 64])                 # warm-up
 t = time.time()
 c1, v1, _ = eng.score(pix, views, 1.3, u)
 t_pix = time.time() - t
-t = time.time()
-c2, v2, _, _, _ = eng.score_jpeg(files, views, 1.3, u)
-t_jpg = time.time() - t
-assert np.array_equal(c1, c2) and np.array_equal(v1, v2)
-print("scoring %d images: from decoded pixels %.1f img/s, from JPEG files %.1f img/s (identical scores)" % (
-    n, n / t_pix, n / t_jpg))
+rates = {}
+for walk in ("host", "device"):                                # where the entropy-coded segment is walked (UploadPipe)
+    os.environ["CALD_JPEG_WALK"] = walk
+    eng.score_jpeg(files[:64], views, 1.3, u[:200 * 64])      # warm-up (staging buffers of this mode)
+    t = time.time()
+    c2, v2, _, _, _ = eng.score_jpeg(files, views, 1.3, u)
+    rates[walk] = n / (time.time() - t)
+    assert np.array_equal(c1, c2) and np.array_equal(v1, v2)
+print("scoring %d images: from decoded pixels %.1f img/s, from JPEG files %.1f img/s (entropy walk on host threads) / "
+      "%.1f img/s (entropy walk on the device); identical scores" % (n, n / t_pix, rates["host"], rates["device"]))
