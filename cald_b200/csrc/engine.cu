@@ -2002,6 +2002,32 @@ int cald_jpeg_info(const uint8_t* file, size_t size, int* height, int* width, in
   }
 }
 
+int cald_jpeg_coefficients(const uint8_t* file, size_t size, int16_t* out, size_t capacity, size_t* n_coef, int* blocks_w,
+                           int* blocks_h) {
+  try {
+    JpegImage im;
+    std::vector<JpegHuff> t;
+    size_t a, b;
+    jpeg_parse(file, size, im, t, a, b);
+    size_t total = 0;
+    for (int q = 0; q < im.ncomp; ++q) {
+      im.comp[q].coef_off = (long long)total;
+      total += (size_t)im.comp[q].blocks_w * im.comp[q].blocks_h * 64;
+      if (blocks_w) blocks_w[q] = im.comp[q].blocks_w;
+      if (blocks_h) blocks_h[q] = im.comp[q].blocks_h;
+    }
+    if (n_coef) *n_coef = total;
+    if (!out || capacity < total) throw std::runtime_error("cald_jpeg_coefficients: output buffer too small");
+    im.scan_off = 0; im.scan_len = (long long)(b - a);
+    memset(out, 0, total * sizeof(int16_t));
+    jpeg_walk(im, t.data(), file + a, out);     // the function UploadPipe's host threads (and the device kernel) run
+    return 0;
+  } catch (const std::exception& ex) {
+    g_create_err = ex.what();
+    return -1;
+  }
+}
+
 int cald_jpeg_decode(cald_engine* e, int n_files, const uint8_t* const* files, const size_t* file_sizes,
                      uint8_t* const* out_images) {
   API_TRY(e)

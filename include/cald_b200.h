@@ -111,10 +111,17 @@ int cald_score(cald_engine* e, int n_images, const uint8_t* const* images, const
  * SOF1), grayscale or YCbCr 4:4:4 / 4:2:2 / 4:2:0, restart intervals; anything else fails the call with a message.
  *
  * cald_jpeg_info   : frame size of one file (host only, needs no engine).
+ * cald_jpeg_coefficients : the host half of the ingest on its own (needs no engine or GPU): the quantised DCT
+ *                    coefficients of one file as the entropy walk produces them, int16, component after component,
+ *                    each [blocks_h][blocks_w][64] in natural (de-zigzagged) order with blocks_w / blocks_h covering
+ *                    whole MCUs.  blocks_w / blocks_h: int[3], filled for the file's components.  Returns -1 with a
+ *                    message if `capacity` (in int16 elements) is too small; *n_coef always receives the needed count.
  * cald_jpeg_decode : out_images[i] = caller's HOST buffer of height*width*3 bytes (u8 RGB, HWC).
  * cald_score_jpeg  : cald_score() over files; out_heights / out_widths (optional) return the decoded sizes.  Noise
  *                    views (GAUSS / SALTPEPPER) need caller-drawn planes of the image size and are refused here. */
 int cald_jpeg_info(const uint8_t* file, size_t size, int* height, int* width, int* components);
+int cald_jpeg_coefficients(const uint8_t* file, size_t size, int16_t* out, size_t capacity, size_t* n_coef, int* blocks_w,
+                           int* blocks_h);
 int cald_jpeg_decode(cald_engine* e, int n_files, const uint8_t* const* files, const size_t* file_sizes,
                      uint8_t* const* out_images);
 int cald_score_jpeg(cald_engine* e, int n_files, const uint8_t* const* files, const size_t* file_sizes, int n_augs,
