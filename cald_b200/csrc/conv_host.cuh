@@ -9,6 +9,7 @@
 #include <string>
 #include "igemm.cuh"
 #include "igemm2.cuh"
+#include "igemm_t.cuh"
 
 // Relative loss of the fp32 TMEM accumulator per tcgen05.mma accumulate.  The tensor core adds into the accumulator
 // with truncation (round toward zero): each of the n MMA k-steps of a contraction shrinks the running sum by c on
@@ -37,6 +38,9 @@ struct ConvW {
   pl16* w = nullptr;
   float* bias = nullptr;
   int cout = 0, cout_pad = 0, cin = 0, taps = 1;
+  // [2][128][taps*cin]: the stacked operands of the transposed-role kernel (igemm_t.cuh), built on first use for the
+  // 64-output-channel layers that take it
+  mutable pl16* wt = nullptr;
   size_t plane_elems() const { return (size_t)cout_pad * taps * cin; }
 };
 
@@ -172,6 +176,11 @@ inline std::atomic<long long>& pair_launch_counter() {
   return n;
 }
 
+inline std::atomic<long long>& tform_launch_counter() {
+  static std::atomic<long long> c{0};
+  return c;
+}
+
 struct ConvEngine {
   int num_sms = 148;
   ConvImpl impl = CONV_TC;
@@ -184,6 +193,9 @@ struct ConvEngine {
   bool use_cta2 = env_flag("CALD_CTA2", true);
   int cta2_min_kb = env_int("CALD_CTA2_MIN_KB", 16);
   int cta2_min_kb64 = env_int("CALD_CTA2_MIN_KB64", 9);
+  // transposed-role kernel (igemm_t.cuh) for the spatial 64-output-channel layers (stem, layer1 3x3); CALD_TFORM=0
+  // falls back to the BLOCK_N = 64 instantiations above
+  bool use_tform = env_flag("CALD_TFORM", true);
   static double env_double(const char* name, double dflt) {
     const char* v = getenv(name);
     return v && *v ? atof(v) : dflt;
@@ -296,6 +308,20 @@ struct ConvEngine {
     CALD_CUDA_CHECK(cudaGetLastError());
   }
 
+  void launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const ConvParams& p,
+                cudaStream_t st) {
+    static std::once_flag attr_once;
+    std::call_once(attr_once, [] {
+      CALD_CUDA_CHECK(cudaFuncSetAttribute(igemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IGT_SMEM_BYTES));
+    });
+    int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
+    igemm_t_kernel<<<grid, IG_THREADS, IGT_SMEM_BYTES, st>>>(ta, tw, tc, p);
+    tform_launch_counter()++;
+    if (profiling) CALD_CUDA_CHECK(cudaEventRecord(next_event(), st));
+    CALD_CUDA_CHECK(cudaGetLastError());
+  }
+
   // out must be pre-shaped by the caller (n, h, w, c = cout_pad or larger ldc).
   void run(const Act& in, const ConvW& w, Act& out, const ConvOpts& o, cudaStream_t st) {
     if (o.stem_window) {
@@ -376,6 +402,20 @@ struct ConvEngine {
     }
     int BN = force_block_n ? force_block_n : (w.cout_pad <= 64 ? 64 : 128);
     if (!force_block_n && !split && w.cout_pad % 256 == 0) BN = 256;
+    // 3x3 convs with 64 output channels (layer1): channels on M (hi and lo weight planes stacked), a 16 x 16 pixel
+    // patch on N -- two N = 256 instructions per k-step instead of N = 128 + N = 64 (igemm_t.cuh).  Measured inside the
+    // cfg-2 step: 633 us per 32-view launch against 708 us on the CTA-pair kernel.  The stem would qualify too
+    // (CALD_TFORM_STEM=1) but is 4 % SLOWER there: its four k-blocks per patch leave the per-slab epilogue exposed.
+    static const bool tform_stem = env_flag("CALD_TFORM_STEM", false);
+    const bool tform = use_tform && impl == CONV_TC && split && spatial && !force_block_n && w.cout_pad == 64 &&
+                       out.c == 64 && (w.taps == 9 || (o.stem_window && tform_stem)) && o.stride == 1 && !o.in_stride2 && !dual &&
+                       o.res_mode == RES_NONE && !o.no_bf16_out && o.out_f32 == nullptr && use_tma_store &&
+                       !(kc > 0 && w.taps * (w.cin / 64) > kc && w.taps * (w.cin / 64) > chunk_above_kb);
+    if (tform) {
+      p.th = IGT_TH; p.tw = IGT_TW;
+      p.tiles_x = (p.W + p.tw - 1) / p.tw;
+      p.tiles_y = (p.H + p.th - 1) / p.th;
+    }
     p.a_bytes = p.th * p.tw * 128;
     p.n_blocks = (w.cout_pad + BN - 1) / BN;
     p.num_tiles = p.n_blocks * p.tiles_x * p.tiles_y * p.n_img;
@@ -430,7 +470,8 @@ struct ConvEngine {
                    out.c == w.cout_pad && use_tma_store) ? 1 : 0;
     if (p.tma_store) {
       if (spatial) {
-        tc = make_tmap(out.hi, out.c, out.w, out.h, (uint64_t)out.n * (split ? 2 : 1), p.tw, p.th);
+        // the transposed-role kernel stores slabs of two patch rows
+        tc = make_tmap(out.hi, out.c, out.w, out.h, (uint64_t)out.n * (split ? 2 : 1), p.tw, tform ? 2 : p.th);
         p.c_lo_img = out.n;
       } else {
         tc = make_tmap(out.hi, out.c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);
@@ -477,7 +518,7 @@ struct ConvEngine {
     // the pair kernel pays a cross-CTA handshake per tile: at BLOCK_N = 128 it wins from 16 k-blocks per tile up
     // (measured, +8..22 % on the 3x3 and K >= 1024 layers) and loses below 8 (the short-K layers are epilogue / HBM
     // bound).  BLOCK_N = 64: the layer1 3x3 convs gain 5 %; the stem (4 k-blocks) loses 12 % and stays on one CTA.
-    bool pair = use_cta2 && split && p.res_kb == 0 && !o.stem_window &&
+    bool pair = !tform && use_cta2 && split && p.res_kb == 0 && !o.stem_window &&
                 ((BN == 128 && num_kb >= cta2_min_kb) ||
                  (BN == 64 && w.taps == 9 && num_kb >= cta2_min_kb64 && !chunked));
     if (profiling) {
@@ -493,13 +534,22 @@ struct ConvEngine {
       LayerRec r;
       snprintf(r.sig, sizeof(r.sig), "%dx%dx%d k%d%s cin%d cout%d BN%d%s%s%s%s%s", p.n_img, p.H, p.W,
                o.stem_window ? 7 : (w.taps == 9 ? 3 : 1), o.stride == 2 ? "s2" : "", o.stem_window ? 3 : w.cin, w.cout, BN,
-               chunked ? " chunk" : "", pair ? " pair" : "",
+               chunked ? " chunk" : "", tform ? " tform" : (pair ? " pair" : ""),
                dual ? (o.aux_stride == 2 ? " +ds2" : " +ds") : (p.res_kb ? " resmma" : (o.res_mode != RES_NONE ? " res" : "")),
                p.tma_store ? " tma" : " direct", o.relu ? " relu" : "");
       r.flops = fl; r.bytes = by;
       recs.push_back(r);
     }
-    if (pair) {
+    if (tform) {
+      const int K = w.taps * w.cin;
+      if (!w.wt) {
+        CALD_CUDA_CHECK(cudaMalloc((void**)&w.wt, (size_t)2 * 128 * K * sizeof(pl16)));
+        igemm_t_stack_weights_kernel<<<64, 256, 0, st>>>(w.w, w.wt, K);
+        CALD_CUDA_CHECK(cudaGetLastError());
+      }
+      const CUtensorMap tws = make_tmap(w.wt, (uint64_t)K, 128, 1, 2, 128, 1);
+      launch_t(ta, tws, tc, p, st);
+    } else if (pair) {
       const CUtensorMap tbh = make_tmap(w.w, (uint64_t)w.taps * w.cin, w.cout_pad, 1, 2, BN / 2, 1);
       if (BN == 64) launch_tc2<64, false>(ta, tb, tbh, tc, p, st);
       else if (chunked) launch_tc2<128, true>(ta, tb, tbh, tc, p, st);

@@ -8,6 +8,7 @@ static thread_local std::string g_ops_err;
 extern "C" const char* cald_ops_last_error(void) { return g_ops_err.c_str(); }
 
 extern "C" long long cald_ops_pair_launches(void) { return pair_launch_counter().load(); }
+extern "C" long long cald_ops_tform_launches(void) { return tform_launch_counter().load(); }
 
 #define OPS_TRY try {
 #define OPS_CATCH                                   \
@@ -65,7 +66,8 @@ ConvW upload_conv_weight(const float* w, const float* bias, int cout, int cin, i
 void free_conv_weight(ConvW& w) {
   if (w.w) cudaFree(w.w);
   if (w.bias) cudaFree(w.bias);
-  w.w = nullptr; w.bias = nullptr;
+  if (w.wt) cudaFree(w.wt);
+  w.w = nullptr; w.bias = nullptr; w.wt = nullptr;
 }
 }  // namespace cald
 

@@ -50,6 +50,8 @@ int cald_op_conv2d_dual(const float* x, int n, int h, int w, int cin, const floa
 /* Number of launches of the CTA-pair (tcgen05 cta_group::2) conv kernel in this process so far; the parity tests use
  * it to assert which kernel a call exercised (CALD_CTA2=0/1 selects it, see cald_b200/csrc/conv_host.cuh). */
 long long cald_ops_pair_launches(void);
+/* Same for the transposed-role kernel of the 64-output-channel layers (CALD_TFORM=0/1, cald_b200/csrc/igemm_t.cuh). */
+long long cald_ops_tform_launches(void);
 
 /* Pillow-exact augmentation images on the device (cald/cald_helper.py:47-53 resize, 135-223 rotate).
  * kind 2 = img.resize((int(w*0.8), int(h*0.8)), BILINEAR); kind 3 = img.rotate(5, expand=True).resize((w, h)) (BICUBIC).

@@ -155,6 +155,7 @@ def test_conv_cta_pair_kernel_matches_fp32_and_single_cta(case, monkeypatch):
     n, h, w, cin, cout, k, stride, res_mode, res_hw = case
     x, wt, b, res = _case(hash(case) % 1000, n, h, w, cin, cout, k, stride, True, True, res_mode, res_hw)
     want = _ref(x, wt, b, stride, True, res, res_mode)
+    monkeypatch.setenv("CALD_TFORM", "0")   # the 64-channel 3x3 cases would take the transposed-role kernel otherwise
     monkeypatch.setenv("CALD_CTA2", "0")
     before = L.cald_ops_pair_launches()
     single = ops.conv2d(x, wt, b, stride=stride, relu=True, res=res, res_mode=res_mode, prec=0, impl=0)
@@ -168,6 +169,47 @@ def test_conv_cta_pair_kernel_matches_fp32_and_single_cta(case, monkeypatch):
     assert np.abs(got - want).max() <= 5e-6 * scale + 1e-6
     # same split operands, same cross-term-separated accumulation: the two kernels agree far below the fp32 tolerance
     assert np.abs(got - single).max() <= 2e-6 * scale + 1e-7
+
+
+TFORM_CASES = [
+    # n, h, w, cin, cout, k: spatial 64-output-channel convs (layer1 3x3) -> igemm_t.cuh, 16 x 16 pixel patches
+    (1, 16, 16, 64, 64, 3),        # exactly one patch
+    (2, 20, 28, 64, 64, 3),        # ragged right and bottom edges
+    (1, 7, 9, 64, 64, 3),          # one partial patch: 4 of 8 slabs, the last one half a patch row pair
+    (3, 33, 47, 64, 64, 3),        # odd extents: a one-row slab at the bottom
+    (2, 200, 336, 64, 64, 3),      # the real layer1 shape: 546 patches, every CTA walks several, all ring phases
+    (1, 40, 40, 128, 64, 3),       # two k-blocks per tap
+]
+
+
+@pytest.mark.parametrize("case", TFORM_CASES)
+def test_conv_transposed_role_kernel_matches_fp32_and_pixel_major_kernels(case, monkeypatch):
+    """igemm_t.cuh (channels on M with the hi / lo weight planes stacked, 256 pixels on N) against torch fp32 and
+    against the pixel-major kernel on the same operands: same products, same k order, same accumulate counts."""
+    import ctypes
+    from cald_b200 import ops
+    from cald_b200._lib import lib
+    L = lib()
+    L.cald_ops_tform_launches.restype = ctypes.c_longlong
+    n, h, w, cin, cout, k = case
+    x, wt, b, _ = _case(sum(case), n, h, w, cin, cout, k)
+    want = _ref(x, wt, b, 1, True)
+    monkeypatch.setenv("CALD_TFORM", "0")
+    before = L.cald_ops_tform_launches()
+    old = ops.conv2d(x, wt, b, relu=True, prec=0, impl=0)
+    assert L.cald_ops_tform_launches() == before
+    monkeypatch.setenv("CALD_TFORM", "1")
+    got = ops.conv2d(x, wt, b, relu=True, prec=0, impl=0)
+    assert L.cald_ops_tform_launches() == before + 1, "the launch did not take the transposed-role kernel"
+    scale = np.abs(want).max()
+    print("tform %s: max |got - fp32| %.2e, max |got - pixel-major kernel| %.2e (scale %.2f)" % (
+        case, np.abs(got - want).max(), np.abs(got - old).max(), scale))
+    assert np.abs(got - want).max() <= 5e-6 * scale + 1e-6
+    assert np.abs(got - old).max() <= 2e-6 * scale + 1e-7
+    # no bias / no ReLU path
+    got2 = ops.conv2d(x, wt, None, relu=False, prec=0, impl=0)
+    want2 = _ref(x, wt, None, 1, False)
+    assert np.abs(got2 - want2).max() <= 5e-6 * np.abs(want2).max() + 1e-6
 
 
 DUAL_CASES = [
