@@ -131,6 +131,7 @@ struct ConvParams {
   int res_conv;        // 1: the extra k-blocks are a second 1x1 contraction (aux input x aux weights, e.g. the ResNet
                        //    downsample shortcut) accumulated into the same tile, not an identity-routed residual
   int r_scale;         // element stride of the aux input's tensor map (2 for a stride-2 shortcut), else 1
+  int res_narrow;      // 1: identity-routed residual k-blocks issue N = 64 instructions on their own 64 columns
 };
 
 // ATen nearest-neighbour source index (UpSampleKernel: nearest_idx), float scale.

@@ -196,6 +196,9 @@ struct ConvEngine {
   // transposed-role kernel (igemm_t.cuh) for the spatial 64-output-channel layers (stem, layer1 3x3); CALD_TFORM=0
   // falls back to the BLOCK_N = 64 instantiations above
   bool use_tform = env_flag("CALD_TFORM", true);
+  // identity-routed residual k-blocks as N = 64 instructions on the 64 accumulator columns they feed (CALD_RES_NARROW=0:
+  // N = BLOCK_N over the whole identity block; same sums, the other columns receive + 0)
+  bool res_narrow = env_flag("CALD_RES_NARROW", true);
   static double env_double(const char* name, double dflt) {
     const char* v = getenv(name);
     return v && *v ? atof(v) : dflt;
@@ -494,6 +497,7 @@ struct ConvEngine {
       }
       ti = make_tmap(identity(BN), 64, (uint64_t)(BN / 64) * BN, 1, 1, BN, 1);
       p.res_kb = BN / 64;
+      p.res_narrow = res_narrow ? 1 : 0;
       p.res_mode = RES_NONE;  // the epilogue no longer sees a residual
     }
     if (dual) {

@@ -285,6 +285,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // XSEP: the same instruction shape with N = 2 * BLOCK_N over [B_hi | B_lo]
       const uint32_t idesc_cat = (1u << 4) | (PL16_MMA_FMT << 7) | (PL16_MMA_FMT << 10) |
                                  ((uint32_t)((2 * BLOCK_N) >> 3) << 17) | ((uint32_t)(IG_BLOCK_M >> 4) << 24);
+      const uint32_t idesc64 = (1u << 4) | (PL16_MMA_FMT << 7) | (PL16_MMA_FMT << 10) | ((uint32_t)(64 >> 3) << 17) |
+                               ((uint32_t)(IG_BLOCK_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -312,8 +314,18 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (kb >= conv_kb && !p.res_conv) {
               // residual k-block: main += R_hi * I, cross += R_lo * I (the lo plane carries LO_SCALE like the cross terms)
               if (XSEP) {
-                tcgen05_mma_bf16(d + BLOCK_N, a_lo + ko, b_hi + ko, idesc, 1);
-                tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, 1);
+                // block j of the identity routes 64 residual channels to accumulator columns [64 j, 64 j + 64): only its
+                // rows [64 j, 64 j + 64) are non-zero, so an N = 64 instruction on those rows and columns adds the same
+                // values as the N = BLOCK_N one (the other columns received + 0) at ~2/3 of its tensor-pipe time
+                if (p.res_narrow) {
+                  const int j = kb - conv_kb;
+                  const uint64_t bj = b_hi + (uint64_t)((j * 64 * 128) >> 4) + ko;
+                  tcgen05_mma_bf16(d + BLOCK_N + j * 64, a_lo + ko, bj, idesc64, 1);
+                  tcgen05_mma_bf16(d + j * 64, a_hi + ko, bj, idesc64, 1);
+                } else {
+                  tcgen05_mma_bf16(d + BLOCK_N, a_lo + ko, b_hi + ko, idesc, 1);
+                  tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, 1);
+                }
               } else {
                 if (SPLIT) tcgen05_mma_bf16(d, a_lo + ko, b_hi + ko, idesc, (kin | k) != 0);
                 tcgen05_mma_bf16(d, a_hi + ko, b_hi + ko, idesc, SPLIT ? 1u : (uint32_t)((kin | k) != 0));
