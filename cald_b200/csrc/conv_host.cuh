@@ -405,11 +405,11 @@ struct ConvEngine {
     }
     int BN = force_block_n ? force_block_n : (w.cout_pad <= 64 ? 64 : 128);
     if (!force_block_n && !split && w.cout_pad % 256 == 0) BN = 256;
-    // 3x3 convs with 64 output channels (layer1): channels on M (hi and lo weight planes stacked), a 16 x 16 pixel
-    // patch on N -- two N = 256 instructions per k-step instead of N = 128 + N = 64 (igemm_t.cuh).  Measured inside the
-    // cfg-2 step: 633 us per 32-view launch against 708 us on the CTA-pair kernel.  The stem would qualify too
-    // (CALD_TFORM_STEM=1) but is 4 % SLOWER there: its four k-blocks per patch leave the per-slab epilogue exposed.
-    static const bool tform_stem = env_flag("CALD_TFORM_STEM", false);
+    // spatial convs with 64 output channels (stem, layer1 3x3): channels on M (hi and lo weight planes stacked), a
+    // 16 x 16 pixel patch on N -- two N = 256 instructions per k-step instead of N = 128 + N = 64 (igemm_t.cuh).
+    // Measured inside the cfg-2 step (profiles/r02_tform.md): layer1 3x3 708 -> 633 us, stem 1469 -> 1368 us per
+    // 32-view launch.  CALD_TFORM_STEM=0 keeps the stem on the pixel-major kernel (A/B).
+    static const bool tform_stem = env_flag("CALD_TFORM_STEM", true);
     const bool tform = use_tform && impl == CONV_TC && split && spatial && !force_block_n && w.cout_pad == 64 &&
                        out.c == 64 && (w.taps == 9 || (o.stem_window && tform_stem)) && o.stride == 1 && !o.in_stride2 && !dual &&
                        o.res_mode == RES_NONE && !o.no_bf16_out && o.out_f32 == nullptr && use_tma_store &&
@@ -473,8 +473,8 @@ struct ConvEngine {
                    out.c == w.cout_pad && use_tma_store) ? 1 : 0;
     if (p.tma_store) {
       if (spatial) {
-        // the transposed-role kernel stores slabs of two patch rows
-        tc = make_tmap(out.hi, out.c, out.w, out.h, (uint64_t)out.n * (split ? 2 : 1), p.tw, tform ? 2 : p.th);
+        // the transposed-role kernel stores slabs of IGT_SLAB_ROWS patch rows
+        tc = make_tmap(out.hi, out.c, out.w, out.h, (uint64_t)out.n * (split ? 2 : 1), p.tw, tform ? IGT_SLAB_ROWS : p.th);
         p.c_lo_img = out.n;
       } else {
         tc = make_tmap(out.hi, out.c, (uint64_t)p.W, 1, split ? 2 : 1, 128, 1);

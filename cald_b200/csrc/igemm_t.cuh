@@ -1,16 +1,17 @@
-// Transposed-role implicit-GEMM convolution for the 3x3 convs with 64 output channels (ResNet layer1), sm_100a.
+// Transposed-role implicit-GEMM convolution for the spatial convs with 64 output channels (stem 7x7/2, ResNet layer1
+// 3x3), sm_100a.
 //
 // Why a third kernel.  With pixels on M and channels on N (igemm.cuh / igemm2.cuh) a 64-channel layer in the split
 // arithmetic can only issue N = 128 ([B_hi | B_lo]) and N = 64 instructions, and a tcgen05.mma with both operands in
-// shared memory has a fixed cost besides the part that scales with N (fitted from the measurements below: about
-// 33 ns + 0.36 ns per column at boost clocks -- N = 64: 56 ns, N = 128: 79 ns, N = 256: 126 ns).  Here the roles are
-// swapped:
+// shared memory has a fixed cost besides the part that scales with N (fitted from the measurements in
+// profiles/r02_tform.md: about 33 ns + 0.36 ns per column at boost clocks -- N = 64: 56 ns, N = 128: 79 ns,
+// N = 256: 126 ns).  Here the roles are swapped:
 //
 //   D^T[128 x 256] = W_stack[128 x K] * Act^T[K x 256]
 //
-//   * M = 128 rows = the 64 output channels TWICE: the hi and the lo plane of the weights, interleaved in groups of 16
-//     rows ([hi 0..15 | lo 0..15 | hi 16..31 | lo 16..31 | ...]) so that a channel's main and cross-term accumulators
-//     sit in the same 32-lane TMEM quadrant, 16 lanes apart (one epilogue warp sees both);
+//   * M = 128 rows = the 64 output channels TWICE: the hi and the lo plane of the weights, stacked in halves of 16 rows
+//     per TMEM quadrant ([hi x16 | lo x16] x 4) so that a channel's main and cross-term accumulators sit in the same
+//     32-lane quadrant, 16 lanes apart (one epilogue warp sees both);
 //   * N = 256 = the pixels of a 16 x 16 output patch (one TMA box per plane and tap);
 //   * per k-step two FULL-WIDTH instructions:  [W_hi ; W_lo] x A_hi^T   (main rows += W_hi*A_hi, cross rows += W_lo*A_hi)
 //                                              [ 0   ; W_hi] x A_lo^T   (cross rows += W_hi*A_lo)
@@ -18,16 +19,14 @@
 //     so the truncation pre-compensation in the weights (RzPlan) is unchanged and the sums are the same products in
 //     the same k order: results are BIT-IDENTICAL to the pixel-major kernels (tests/test_gpu_conv.py).
 //
-// Measured (profiles/r02_tform.md): the layer1 3x3 conv alone, 16 views, boost clocks: one CTA 0.2895 ms, CTA pair
-// 0.2737 ms, this kernel 0.2686 ms; inside the power-capped cfg-2 step 708 -> 633 us per 32-view launch (-10.6 %).
-// The quarter of the second instruction that multiplies zeros is what keeps the gain small.  The stem (4 k-blocks per
-// patch) is 4 % slower on this kernel -- with so few MMAs per patch the per-slab epilogue below (two named barriers, a
-// proxy fence and two TMA stores per 32 pixels) is exposed -- and stays on igemm.cuh.
+// Measured inside the power-capped cfg-2 step (profiles/r02_tform.md): layer1 3x3 708 -> 633 us per 32-view launch
+// (-10.6 %, MMA-bound: 72 instructions per patch), stem 1469 -> 1368 us (-6.9 %).  The quarter of the second instruction
+// that multiplies zeros is what keeps the gain small.
 //
-// Epilogue: a thread owns one (channel, plane) row of the accumulator and walks the tile in slabs of 32 pixels (two
-// patch rows): tcgen05.ld of 32 columns, one shuffle per value to bring main and cross together (the lower half-warp
-// finishes the slab's first patch row, the upper half-warp the second), bias, ReLU, split to half planes, 2-byte stores
-// into a 128B-swizzled [32 pixels][64 channels] staging slab, one TMA store per plane and slab (double-buffered).
+// Epilogue: 16x256b TMEM loads hand a thread the main and the cross-term value of the same (channel pair, pixel pair)
+// elements (the weight rows are stacked so that the two rows of such a fragment are adjacent channels): one FMA joins
+// them, bias, ReLU, split to half planes, one 4-byte bank-conflict-free store per pixel and plane into a
+// 128B-swizzled [64 pixels][64 channels] staging slab, one TMA store per plane and slab (double-buffered).
 #pragma once
 #include "igemm.cuh"
 
@@ -41,15 +40,18 @@ constexpr int IGT_STAGES = 2;
 constexpr int IGT_OFF_A_LO = IGT_ACT_BYTES;
 constexpr int IGT_OFF_W1 = 2 * IGT_ACT_BYTES;
 constexpr int IGT_OFF_W2 = 2 * IGT_ACT_BYTES + IGT_W_BYTES;
-constexpr int IGT_SLAB_PIX = 32;                        // pixels per output slab (two patch rows)
-constexpr int IGT_SLAB_BYTES = IGT_SLAB_PIX * 128;      // one plane of one slab: 4 KB
+constexpr int IGT_SLAB_ROWS = 4;                        // patch rows per output slab
+constexpr int IGT_SLAB_PIX = IGT_SLAB_ROWS * IGT_TW;    // 64 pixels
+constexpr int IGT_SLAB_BYTES = IGT_SLAB_PIX * 128;      // one plane of one slab: 8 KB
 constexpr int IGT_OUT_BYTES = 2 /*slots*/ * 2 /*planes*/ * IGT_SLAB_BYTES;
 constexpr int IGT_BAR_BYTES = 1024;
 constexpr int IGT_SMEM_BYTES = IGT_STAGES * IGT_STAGE_BYTES + IGT_BAR_BYTES + IGT_OUT_BYTES + 1024;
 
-// Stacked weight operands of a 64-output-channel layer: wt = [2][128][K]
-//   operand 0, row r: group g = r / 16, channel c = (g / 2) * 16 + r % 16:  g even -> W_hi[c], g odd -> W_lo[c]
-//   operand 1, row r:                                                      g even -> 0,       g odd -> W_hi[c]
+// Stacked weight operands of a 64-output-channel layer: wt = [2][128][K].  Row r = 32 q + 16 half + i (TMEM lane r of
+// the accumulator) belongs to channel c = 16 q + (i < 8 ? 2 i : 2 (i - 8) + 1): inside a 16-lane half, lanes i and
+// i + 8 hold ADJACENT channels, which is the row pair one thread receives from a 16x256b TMEM load.
+//   operand 0:  half 0 -> W_hi[c] (main rows),  half 1 -> W_lo[c] (cross-term rows)
+//   operand 1:  half 0 -> 0,                    half 1 -> W_hi[c]
 // w = [2][64][K] (hi plane, lo plane), the layout every other kernel reads.
 __global__ void igemm_t_stack_weights_kernel(const pl16* __restrict__ w, pl16* __restrict__ wt, int K) {
   const long long total = 2LL * 128 * K;
@@ -57,13 +59,25 @@ __global__ void igemm_t_stack_weights_kernel(const pl16* __restrict__ w, pl16* _
     const int k = (int)(i % K);
     const int r = (int)((i / K) % 128);
     const int op = (int)(i / ((long long)128 * K));
-    const int g = r >> 4, c = (g >> 1) * 16 + (r & 15);
+    const int half = (r >> 4) & 1, li = r & 15;
+    const int c = (r >> 5) * 16 + (li < 8 ? 2 * li : 2 * (li - 8) + 1);
     const pl16 hi = w[(long long)c * K + k], lo = w[(long long)(64 + c) * K + k];
     pl16 v;
-    if (op == 0) v = (g & 1) ? lo : hi;
-    else v = (g & 1) ? hi : float_to_pl16(0.f);
+    if (op == 0) v = half ? lo : hi;
+    else v = half ? hi : float_to_pl16(0.f);
     wt[i] = v;
   }
+}
+
+// 16 TMEM lanes x 32 columns -> 16 registers: r[4 n + 2 i1 + i0] = (lane base + lane / 4 + 8 i1, column 8 n + 2 (lane % 4) + i0)
+// (the m16n8 accumulator-fragment pattern, cute::SM100_TMEM_LOAD_16dp256b4x); no wait
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
 }
 
 __device__ __forceinline__ void igt_tile_coords(const ConvParams& p, int tile, int& img, int& y0, int& x0) {
@@ -185,14 +199,17 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;            // TMEM lane quadrant of this warp: stacked rows [32 * quad, 32 * quad + 32)
-    const bool upper = lane >= 16;        // lower half-warp holds the main rows, upper the cross-term rows
-    const int ch = quad * 16 + (lane & 15);
+    // TMEM quadrant of this warp = stacked rows [32 q, 32 q + 32): lanes 0..15 main, 16..31 cross terms of channels
+    // [16 q, 16 q + 16).  A 16x256b load hands thread t the rows t / 4 and t / 4 + 8 of a 16-lane half = the ADJACENT
+    // channels ch0, ch0 + 1 (stacking order above) at the columns (pixels) 8 n + 2 (t % 4) + {0, 1}: main and cross
+    // values of the same element arrive in the same thread, and a pixel's channel pair is one 4-byte staging store.
+    const int quad = warp & 3;
+    const int rp = lane >> 2, cp = lane & 3;
+    const int ch0 = quad * 16 + 2 * rp;
     const bool leader = (threadIdx.x == 64);
     const uint32_t out_base = smem_base + IGT_STAGES * IGT_STAGE_BYTES + IGT_BAR_BYTES;  // 1024-aligned
-    const float bias = p.bias ? p.bias[ch] : 0.f;
-    // this thread's 2-byte position inside a 128-byte staging row (before the per-row swizzle of the 16-byte chunk)
-    const uint32_t ch_chunk = (uint32_t)(ch >> 3), ch_in = (uint32_t)(ch & 7) * 2u;
+    const float bias0 = p.bias ? p.bias[ch0] : 0.f, bias1 = p.bias ? p.bias[ch0 + 1] : 0.f;
+    const uint32_t ch_chunk = (uint32_t)(ch0 >> 3), ch_in = (uint32_t)(ch0 & 7) * 2u;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t slab = 0;   // running slab counter: slot = slab & 1
@@ -201,46 +218,47 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       igt_tile_coords(p, tile, img, y0, x0);
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tcgen05_fence_after();
-      const uint32_t t0 = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+      const uint32_t t_main = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+      const uint32_t t_cross = t_main + (16u << 16);
       // patch rows below the image would be clipped by the TMA store anyway: their slabs are not computed
       const int rows_valid = p.H - y0 < IGT_TH ? p.H - y0 : IGT_TH;
-      const int n_slabs = (rows_valid + 1) / 2;
+      const int n_slabs = (rows_valid + IGT_SLAB_ROWS - 1) / IGT_SLAB_ROWS;
       for (int s = 0; s < n_slabs; ++s, ++slab) {
-        uint32_t r[32];
-        tmem_ld32(t0 + s * IGT_SLAB_PIX, r);
-        if (s == n_slabs - 1) {   // accumulator drained: hand the TMEM stage back to the MMA warp
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
-        }
         const uint32_t sb = out_base + (slab & 1u) * (2u * IGT_SLAB_BYTES);
         // the TMA store that last read this slot (two slabs ago) must have finished reading it
         if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          // lower half-warp finishes pixel j of the slab (first patch row), upper half-warp pixel 16 + j
-          const uint32_t send = upper ? r[j] : r[16 + j];
-          const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 16);
-          const float mainv = upper ? __uint_as_float(recv) : __uint_as_float(r[j]);
-          const float cross = upper ? __uint_as_float(r[16 + j]) : __uint_as_float(recv);
-          float v = fmaf(cross, CALD_LO_INV, mainv) + bias;
-          if (p.relu) v = fmaxf(v, 0.f);
-          // split to the two half planes (saturating conversions, lo = (v - hi) * 2^11 as an exponent add)
-          const uint32_t hw = cvt_pack2(v, 0.f);
-          float hf, unused;
-          unpack2(hw, hf, unused);
-          const uint32_t lw = cvt_pack2(scale_2p11(v - hf), 0.f);
-          const uint32_t prow = (upper ? 16u : 0u) + (uint32_t)j;
-          const uint32_t off = prow * 128u + ((ch_chunk ^ (prow & 7u)) << 4) + ch_in;
-          asm volatile("st.shared.b16 [%0], %1;" ::"r"(sb + off), "h"((unsigned short)(hw & 0xffffu)) : "memory");
-          asm volatile("st.shared.b16 [%0], %1;" ::"r"(sb + IGT_SLAB_BYTES + off), "h"((unsigned short)(lw & 0xffffu))
-                       : "memory");
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t m[16], c[16];
+          tmem_ld_16x256b_x4(t_main + s * IGT_SLAB_PIX + hf * 32, m);
+          tmem_ld_16x256b_x4(t_cross + s * IGT_SLAB_PIX + hf * 32, c);
+          tmem_ld_wait();
+          if (hf == 1 && s == n_slabs - 1) {   // accumulator drained: hand the TMEM stage back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+          }
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+#pragma unroll
+            for (int i0 = 0; i0 < 2; ++i0) {
+              float v0 = fmaf(__uint_as_float(c[4 * n + i0]), CALD_LO_INV, __uint_as_float(m[4 * n + i0])) + bias0;
+              float v1 = fmaf(__uint_as_float(c[4 * n + 2 + i0]), CALD_LO_INV, __uint_as_float(m[4 * n + 2 + i0])) + bias1;
+              if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              uint32_t hw, lw;
+              split_pack2(v0, v1, hw, lw);
+              const uint32_t px = (uint32_t)(hf * 32 + 8 * n + i0) + 2u * (uint32_t)cp;   // pixel inside the slab
+              const uint32_t off = px * 128u + ((ch_chunk ^ (px & 7u)) << 4) + ch_in;
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(sb + off), "r"(hw) : "memory");
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(sb + IGT_SLAB_BYTES + off), "r"(lw) : "memory");
+            }
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (leader) {
-          const int ys = y0 + 2 * s;
+          const int ys = y0 + IGT_SLAB_ROWS * s;
           tma_store_4d(&tmC, sb, 0, x0, ys, img);
           tma_store_4d(&tmC, sb + IGT_SLAB_BYTES, 0, x0, ys, img + p.c_lo_img);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
