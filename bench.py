@@ -53,11 +53,11 @@ CONFIGS = {
                  workload="FRCNN R50-FPN nc=91, synthetic 1333x800 pool sharded over the GPUs, score -> all-gather -> "
                           "argsort -> cls_kldiv -> select (cald_train.py:427-448)"),
 }
-# DRAM traffic of the conv kernels per scored image (dram__bytes_read.sum + dram__bytes_write.sum, ncu, summed over the 142
-# igemm_tc_kernel / igemm_tc2_kernel launches of one 16-image cfg2 step: 220.77 GB / 16).  An OFFLINE ncu constant (ncu
+# DRAM traffic of the conv kernels per scored image (dram__bytes_read.sum + dram__bytes_write.sum, ncu, summed over the 213
+# igemm_tc_kernel / igemm_tc2_kernel / igemm_t_kernel launches of one 16-image cfg2 step: 218.63 GB / 16).  An OFFLINE ncu constant (ncu
 # cannot run inside a timed bench), independent of the pass size to first order (every activation is written and read
 # once per image); `roofline.traffic` = this x images per step / conv launches per step.  Only reported for cfg2.
-NCU_DRAM_BYTES_PER_IMAGE = 13.798e9
+NCU_DRAM_BYTES_PER_IMAGE = 13.664e9
 NCU_DRAM_SOURCE = "profiles/r02_launches_step.csv"
 BASE_IMAGES = 32
 POOL_MAX_IMAGES = 1024   # distinct images per rank (3.3 GB at 1333x800); longer runs cycle through them
@@ -433,8 +433,8 @@ def main():
                      "traffic_source": "offline ncu constant: conv-kernel DRAM bytes (read + write) per scored image "
                                        "from " + NCU_DRAM_SOURCE + ", scaled to this run's images and launches per step",
                      "algorithmic_bytes_per_launch": conv_bytes / conv_launches if conv_launches else None,
-                     "kernel": "igemm_tc_kernel + igemm_tc2_kernel (tcgen05 implicit-GEMM conv/GEMM: one-CTA and "
-                               "CTA-pair cta_group::2 instantiations)",
+                     "kernel": "igemm_tc_kernel + igemm_tc2_kernel + igemm_t_kernel (tcgen05 implicit-GEMM conv/GEMM: "
+                               "one-CTA, CTA-pair cta_group::2 and transposed-role instantiations)",
                      "launches": int(conv_launches), "kernel_ms_per_step": conv_ms / args.steps,
                      "algorithmic_gflop_per_step": conv_flops / args.steps / 1e9,
                      "share_of_step": conv_ms / ms_instr if ms_instr else None, "peak_source": peak_src,
