@@ -407,7 +407,7 @@ struct ConvEngine {
     if (!force_block_n && !split && w.cout_pad % 256 == 0) BN = 256;
     // spatial convs with 64 output channels (stem, layer1 3x3): channels on M (hi and lo weight planes stacked), a
     // 16 x 16 pixel patch on N -- two N = 256 instructions per k-step instead of N = 128 + N = 64 (igemm_t.cuh).
-    // Measured inside the cfg-2 step (profiles/r02_tform.md): layer1 3x3 708 -> 633 us, stem 1469 -> 1368 us per
+    // Measured inside the cfg-2 step (profiles/r02_tform.md): layer1 3x3 708 -> 573 us, stem 1469 -> 1315 us per
     // 32-view launch.  CALD_TFORM_STEM=0 keeps the stem on the pixel-major kernel (A/B).
     static const bool tform_stem = env_flag("CALD_TFORM_STEM", true);
     const bool tform = use_tform && impl == CONV_TC && split && spatial && !force_block_n && w.cout_pad == 64 &&

@@ -16,12 +16,18 @@
 //   * per k-step two FULL-WIDTH instructions:  [W_hi ; W_lo] x A_hi^T   (main rows += W_hi*A_hi, cross rows += W_lo*A_hi)
 //                                              [ 0   ; W_hi] x A_lo^T   (cross rows += W_hi*A_lo)
 //     The main rows see one accumulate per k-step and the cross rows two, exactly like the XSEP columns of igemm.cuh,
-//     so the truncation pre-compensation in the weights (RzPlan) is unchanged and the sums are the same products in
-//     the same k order: results are BIT-IDENTICAL to the pixel-major kernels (tests/test_gpu_conv.py).
+//     so the truncation pre-compensation in the weights (RzPlan) is unchanged.  The main sums are bit-identical to the
+//     pixel-major kernels; the cross-term sums add the same products with the two partial sums of a k-block in the
+//     other order (all four W_lo*A_hi k-steps, then all four W_hi*A_lo ones: the halves of a k-block are separate ring
+//     slots), which moves results by <= 1e-7 of the output scale (tests/test_gpu_conv.py).
 //
-// Measured inside the power-capped cfg-2 step (profiles/r02_tform.md): layer1 3x3 708 -> 633 us per 32-view launch
-// (-10.6 %, MMA-bound: 72 instructions per patch), stem 1469 -> 1368 us (-6.9 %).  The quarter of the second instruction
-// that multiplies zeros is what keeps the gain small.
+// Ring of four HALF stages (48 KB: one activation plane + one stacked weight operand of a k-block): three loads are in
+// flight while one slot is being multiplied.  With two whole stages ncu showed 70 % tensor-pipe activity at 64 % L2
+// throughput -- the load latency was exposed.
+//
+// Measured inside the power-capped cfg-2 step (profiles/r02_tform.md), per 32-view launch: layer1 3x3 708 us (CTA-pair
+// kernel) -> 573 us (-19 %), stem 1469 us (one-CTA kernel) -> 1315 us (-10.5 %).  The quarter of the second instruction
+// that multiplies zeros is what keeps the gain from being larger.
 //
 // Epilogue: 16x256b TMEM loads hand a thread the main and the cross-term value of the same (channel pair, pixel pair)
 // elements (the weight rows are stacked so that the two rows of such a fragment are adjacent channels): one FMA joins
@@ -35,11 +41,12 @@ namespace cald {
 constexpr int IGT_TW = 16, IGT_TH = 16;                 // output patch = 256 pixels = N of the MMA
 constexpr int IGT_ACT_BYTES = 256 * 128;                // one plane of one k-block of the patch: 32 KB
 constexpr int IGT_W_BYTES = 128 * 128;                  // one stacked weight operand of one k-block: 16 KB
-constexpr int IGT_STAGE_BYTES = 2 * IGT_ACT_BYTES + 2 * IGT_W_BYTES;   // 96 KB
-constexpr int IGT_STAGES = 2;
-constexpr int IGT_OFF_A_LO = IGT_ACT_BYTES;
-constexpr int IGT_OFF_W1 = 2 * IGT_ACT_BYTES;
-constexpr int IGT_OFF_W2 = 2 * IGT_ACT_BYTES + IGT_W_BYTES;
+// The ring is made of HALF stages: (A_hi, [W_hi ; W_lo]) and (A_lo, [0 ; W_hi]) of a k-block travel and are consumed
+// separately -- four 48 KB slots keep three loads in flight while one is being multiplied (two 96 KB stages kept one:
+// ncu showed 70 % tensor-pipe activity at 64 % L2 throughput, the load latency was exposed)
+constexpr int IGT_STAGE_BYTES = IGT_ACT_BYTES + IGT_W_BYTES;   // 48 KB
+constexpr int IGT_STAGES = 4;
+constexpr int IGT_OFF_W = IGT_ACT_BYTES;
 constexpr int IGT_SLAB_ROWS = 4;                        // patch rows per output slab
 constexpr int IGT_SLAB_PIX = IGT_SLAB_ROWS * IGT_TW;    // 64 pixels
 constexpr int IGT_SLAB_BYTES = IGT_SLAB_PIX * 128;      // one plane of one slab: 8 KB
@@ -146,19 +153,20 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int img, y0, x0;
         igt_tile_coords(p, tile, img, y0, x0);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          const uint32_t fb = full_bar + 8 * stage;
-          const uint32_t sa = smem_base + stage * IGT_STAGE_BYTES;
           const int tap = kb / k_chunks;
           const int c0 = (kb - tap * k_chunks) * IG_BLOCK_K;
           const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
           const int bk = tap * p.Cin + c0;
-          mbar_expect_tx(fb, IGT_STAGE_BYTES);
-          tma_load_4d(sa, &tmA, fb, c0, ax, ay, img);
-          tma_load_4d(sa + IGT_OFF_A_LO, &tmA, fb, c0, ax, ay, img + p.a_lo_img);
-          tma_load_4d(sa + IGT_OFF_W1, &tmW, fb, bk, 0, 0, 0);
-          tma_load_4d(sa + IGT_OFF_W2, &tmW, fb, bk, 0, 0, 1);
-          if (++stage == IGT_STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {   // hi half stage, then lo half stage
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            const uint32_t fb = full_bar + 8 * stage;
+            const uint32_t sa = smem_base + stage * IGT_STAGE_BYTES;
+            mbar_expect_tx(fb, IGT_STAGE_BYTES);
+            tma_load_4d(sa, &tmA, fb, c0, ax, ay, img + h * p.a_lo_img);
+            tma_load_4d(sa + IGT_OFF_W, &tmW, fb, bk, 0, 0, h);
+            if (++stage == IGT_STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -177,21 +185,22 @@ igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tcgen05_fence_after();
         const uint32_t d = tmem_base + acc * 256;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar + 8 * stage, phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_base + stage * IGT_STAGE_BYTES;
-          const uint64_t a_hi = umma_desc_sw128(sa);
-          const uint64_t a_lo = umma_desc_sw128(sa + IGT_OFF_A_LO);
-          const uint64_t w1 = umma_desc_sw128(sa + IGT_OFF_W1);
-          const uint64_t w2 = umma_desc_sw128(sa + IGT_OFF_W2);
+          // first half stage: main += W_hi*A_hi, cross += W_lo*A_hi; second: cross += W_hi*A_lo (main += 0)
 #pragma unroll
-          for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
-            const uint64_t ko = (uint64_t)((k * IG_UMMA_K * 2) >> 4);
-            tcgen05_mma_bf16(d, w1 + ko, a_hi + ko, idesc, (kb | k) != 0);   // main += W_hi*A_hi, cross += W_lo*A_hi
-            tcgen05_mma_bf16(d, w2 + ko, a_lo + ko, idesc, 1);               // cross += W_hi*A_lo (main += 0)
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(full_bar + 8 * stage, phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_base + stage * IGT_STAGE_BYTES;
+            const uint64_t act = umma_desc_sw128(sa);
+            const uint64_t wst = umma_desc_sw128(sa + IGT_OFF_W);
+#pragma unroll
+            for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
+              const uint64_t ko = (uint64_t)((k * IG_UMMA_K * 2) >> 4);
+              tcgen05_mma_bf16(d, wst + ko, act + ko, idesc, (kb | k | h) != 0);
+            }
+            tcgen05_commit(empty_bar + 8 * stage);
+            if (++stage == IGT_STAGES) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit(empty_bar + 8 * stage);
-          if (++stage == IGT_STAGES) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit(tfull_bar + 8 * acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -185,7 +185,8 @@ TFORM_CASES = [
 @pytest.mark.parametrize("case", TFORM_CASES)
 def test_conv_transposed_role_kernel_matches_fp32_and_pixel_major_kernels(case, monkeypatch):
     """igemm_t.cuh (channels on M with the hi / lo weight planes stacked, 256 pixels on N) against torch fp32 and
-    against the pixel-major kernel on the same operands: same products, same k order, same accumulate counts."""
+    against the pixel-major kernel on the same operands: same products and accumulate counts, main sums in the same
+    order, the two cross-term partial sums of a k-block in the other one (measured: <= 1e-7 of the output scale)."""
     import ctypes
     from cald_b200 import ops
     from cald_b200._lib import lib
@@ -205,7 +206,7 @@ def test_conv_transposed_role_kernel_matches_fp32_and_pixel_major_kernels(case, 
     print("tform %s: max |got - fp32| %.2e, max |got - pixel-major kernel| %.2e (scale %.2f)" % (
         case, np.abs(got - want).max(), np.abs(got - old).max(), scale))
     assert np.abs(got - want).max() <= 5e-6 * scale + 1e-6
-    assert np.abs(got - old).max() <= 2e-6 * scale + 1e-7
+    assert np.abs(got - old).max() <= 3e-7 * scale
     # no bias / no ReLU path
     got2 = ops.conv2d(x, wt, None, relu=False, prec=0, impl=0)
     want2 = _ref(x, wt, None, 1, False)
