@@ -180,7 +180,7 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t full_leader = mapa_shared(full_bar, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -213,7 +213,7 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one_sync()) {
       const uint32_t idesc_base = (1u << 4) | (PL16_MMA_FMT << 7) | (PL16_MMA_FMT << 10) | ((uint32_t)(256 >> 4) << 24);  // M = 256
       const uint32_t idesc_cat = idesc_base | ((uint32_t)((2 * BLOCK_N) >> 3) << 17);
       const uint32_t idesc_half = idesc_base | ((uint32_t)(BLOCK_N >> 3) << 17);
